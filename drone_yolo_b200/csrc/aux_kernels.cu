@@ -1,0 +1,266 @@
+// aux_kernels.cu — the small memory-bound layers around the tensor-core convs (CUDA cores on purpose: none of
+// them is a dense contraction worth reshaping into a GEMM).
+//   stem_conv_kernel   model.0 Conv(3->c,3,2)+BN+SiLU fused with the fp32 NCHW -> bf16 NHWC conversion
+//                      (ultralytics/nn/modules/conv.py:49-55; engine/predictor.py:132-135)
+//   sppf_pool_kernel   SPPF's three chained MaxPool2d(5,1,2) + cat  (nn/modules/block.py:185-191)
+//   upsample2x_kernel  nn.Upsample(None,2,'nearest') written straight into a Concat slice (conv.py:331-333)
+//   dwconv3x3s2_kernel DWConv(c1,c2,3,2), groups=c2, c1=2*c2, of the "-sf" graph (conv.py:102-107)
+#include "dy_common.cuh"
+
+namespace dy {
+
+// ------------------------------------------------------------------------------------------------
+// Stem: one thread per output pixel keeps the 3x3x3 input patch in registers and sweeps the output
+// channels 8 at a time (weights broadcast from shared memory as float4), storing 16 B per sweep.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kStemThreads = 128;
+static constexpr int kStemMaxC = 128;
+
+__global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __restrict__ in, int B, int H, int W,
+                                                                 const float* __restrict__ weight,
+                                                                 const float* __restrict__ bias, int Cout,
+                                                                 __nv_bfloat16* __restrict__ out, int out_ld) {
+  __shared__ __align__(16) float w_s[kStemMaxC * 28];
+  __shared__ float b_s[kStemMaxC];
+  for (int i = threadIdx.x; i < Cout * 28; i += kStemThreads) {
+    const int co = i / 28, k = i - co * 28;
+    w_s[i] = k < 27 ? weight[co * 27 + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < Cout; i += kStemThreads) b_s[i] = bias[i];
+  __syncthreads();
+
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const long long pix = static_cast<long long>(blockIdx.x) * kStemThreads + threadIdx.x;
+  if (pix >= total) return;
+  const int wo = static_cast<int>(pix % Wo);
+  const int ho = static_cast<int>((pix / Wo) % Ho);
+  const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+
+  float x[28];
+  x[27] = 0.f;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const float* img = in + static_cast<size_t>(b) * 3 * plane;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = 2 * ho - 1 + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = 2 * wo - 1 + kx;
+        const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
+        x[c * 9 + ky * 3 + kx] = ok ? __ldg(img + c * plane + static_cast<size_t>(y) * W + xx) : 0.f;
+      }
+    }
+
+  __nv_bfloat16* op = out + static_cast<size_t>(pix) * out_ld;
+  for (int co = 0; co < Cout; co += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = b_s[co + j];
+      const float4* wr = reinterpret_cast<const float4*>(w_s + (co + j) * 28);
+#pragma unroll
+      for (int k4 = 0; k4 < 7; ++k4) {
+        const float4 wv = wr[k4];
+        a = fmaf(x[4 * k4 + 0], wv.x, a);
+        a = fmaf(x[4 * k4 + 1], wv.y, a);
+        a = fmaf(x[4 * k4 + 2], wv.z, a);
+        a = fmaf(x[4 * k4 + 3], wv.w, a);
+      }
+      acc[j] = silu_fast(a);
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(op + co) = o;
+  }
+}
+
+int stem_launch(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
+                int out_ld, cudaStream_t stream) {
+  DY_CHECK_ARG(in && weight && bias && out, "stem: null pointer");
+  DY_CHECK_ARG(B > 0 && H > 0 && W > 0, "stem: bad shape");
+  DY_CHECK_ARG(Cout % 8 == 0 && Cout > 0 && Cout <= kStemMaxC, "stem: Cout must be a multiple of 8, <= %d", kStemMaxC);
+  DY_CHECK_ARG(out_ld % 8 == 0 && out_ld >= Cout && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem: out slice must be 16B aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const long long blocks = (total + kStemThreads - 1) / kStemThreads;
+  DY_CHECK_ARG(blocks < (1ll << 31), "stem: too many pixels");
+  stem_conv_kernel<<<static_cast<unsigned>(blocks), kStemThreads, 0, stream>>>(in, B, H, W, weight, bias, Cout,
+                                                                              static_cast<__nv_bfloat16*>(out), out_ld);
+  return launch_status("stem_conv_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPPF pooling.  One CTA owns one image x one 8-channel group (16 B per pixel) and keeps the whole HxW map in
+// shared memory; each mp5 is separable (5-wide row max, then 5-tall column max; window clipped == -inf padding).
+// ------------------------------------------------------------------------------------------------
+static constexpr int kPoolThreads = 256;
+
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162 t;
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.x), *reinterpret_cast<__nv_bfloat162*>(&b.x)); r.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.y), *reinterpret_cast<__nv_bfloat162*>(&b.y)); r.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.z), *reinterpret_cast<__nv_bfloat162*>(&b.z)); r.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.w), *reinterpret_cast<__nv_bfloat162*>(&b.w)); r.w = *reinterpret_cast<uint32_t*>(&t);
+  return r;
+}
+
+__global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(__nv_bfloat16* buf, int H, int W, int C, int ld) {
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  const int hw = H * W;
+  uint4* X = reinterpret_cast<uint4*>(pool_smem);
+  uint4* T = X + hw;
+  const int groups = C / 8;
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  __nv_bfloat16* base = buf + static_cast<size_t>(b) * hw * ld + g * 8;
+  for (int i = threadIdx.x; i < hw; i += kPoolThreads) X[i] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i) * ld);
+  __syncthreads();
+  for (int rep = 1; rep <= 3; ++rep) {
+    for (int i = threadIdx.x; i < hw; i += kPoolThreads) {
+      const int y = i / W, x = i - y * W;
+      uint4 m = X[i];
+      for (int dx = -2; dx <= 2; ++dx) { const int xx = x + dx; if (dx != 0 && xx >= 0 && xx < W) m = max_bf16x8(m, X[y * W + xx]); }
+      T[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < hw; i += kPoolThreads) {
+      const int y = i / W, x = i - y * W;
+      uint4 m = T[i];
+      for (int dy = -2; dy <= 2; ++dy) { const int yy = y + dy; if (dy != 0 && yy >= 0 && yy < H) m = max_bf16x8(m, T[yy * W + x]); }
+      *reinterpret_cast<uint4*>(base + static_cast<size_t>(i) * ld + rep * C) = m;
+      X[i] = m;     // only this thread reads/writes X[i] in this phase; T is the cross-thread source
+    }
+    __syncthreads();
+  }
+}
+
+int sppf_pool_launch(void* buf, int B, int H, int W, int C, int ld, cudaStream_t stream) {
+  DY_CHECK_ARG(buf && B > 0 && H > 0 && W > 0 && C > 0, "sppf_pool: bad argument");
+  DY_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ld >= 4 * C && (reinterpret_cast<uintptr_t>(buf) & 15) == 0,
+               "sppf_pool: C, ld must be multiples of 8 with ld >= 4*C");
+  const size_t smem = static_cast<size_t>(H) * W * 16 * 2;
+  DY_CHECK_ARG(smem <= 220 * 1024, "sppf_pool: %dx%d map does not fit shared memory", H, W);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    DY_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  sppf_pool_kernel<<<B * (C / 8), kPoolThreads, smem, stream>>>(static_cast<__nv_bfloat16*>(buf), H, W, C, ld);
+  return launch_status("sppf_pool_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x nearest upsample: one thread per (output pixel, 8-channel vector).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int B, int H, int W,
+                                                         int C, __nv_bfloat16* __restrict__ out, int out_ld) {
+  const int vec = C / 8;
+  const long long total = static_cast<long long>(B) * (2 * H) * (2 * W) * vec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vec);
+    long long pix = i / vec;
+    const int x = static_cast<int>(pix % (2 * W)); pix /= (2 * W);
+    const int y = static_cast<int>(pix % (2 * H));
+    const int b = static_cast<int>(pix / (2 * H));
+    const uint4 val = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + (y >> 1)) * W + (x >> 1)) * in_ld + v * 8);
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * 2 * H + y) * 2 * W + x) * out_ld + v * 8) = val;
+  }
+}
+
+int upsample2x_launch(const void* in, int in_ld, int B, int H, int W, int C, void* out, int out_ld, cudaStream_t stream) {
+  DY_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && C > 0, "upsample2x: bad argument");
+  DY_CHECK_ARG(C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0, "upsample2x: slices must be 16B aligned");
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  upsample2x_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), in_ld, B, H, W, C,
+                                                                       static_cast<__nv_bfloat16*>(out), out_ld);
+  return launch_status("upsample2x_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// DWConv 3x3 stride 2 pad 1, groups = Cout, 2 input channels per group, + bias + SiLU.
+// One thread per (output pixel, 8 output channels = 16 contiguous input channels).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int B, int H, int W,
+                                                          const float* __restrict__ weight, const float* __restrict__ bias,
+                                                          int Cout, __nv_bfloat16* __restrict__ out, int out_ld) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int vec = Cout / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * vec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vec);
+    long long pix = i / vec;
+    const int wo = static_cast<int>(pix % Wo); pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int b = static_cast<int>(pix / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + v * 8 + j);
+    const float* wp = weight + static_cast<size_t>(v) * 8 * 18;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = 2 * ho - 1 + ky;
+      if (y < 0 || y >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x = 2 * wo - 1 + kx;
+        if (x < 0 || x >= W) continue;
+        const __nv_bfloat16* ip = in + ((static_cast<size_t>(b) * H + y) * W + x) * in_ld + v * 16;
+        const uint4 v0 = *reinterpret_cast<const uint4*>(ip);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(ip + 8);
+        const uint32_t w32[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // output channel v*8+j reads input channels 2j, 2j+1 of this 16-wide vector
+          acc[j] = fmaf(bf16_lo(w32[j]), __ldg(wp + j * 18 + ky * 3 + kx), acc[j]);
+          acc[j] = fmaf(bf16_hi(w32[j]), __ldg(wp + j * 18 + 9 + ky * 3 + kx), acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = silu_fast(acc[j]);
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + ho) * Wo + wo) * out_ld + v * 8) = o;
+  }
+}
+
+int dwconv_launch(const void* in, int in_ld, int B, int H, int W, int Cin, const float* weight, const float* bias, int Cout,
+                  void* out, int out_ld, cudaStream_t stream) {
+  DY_CHECK_ARG(in && out && weight && bias && B > 0 && H > 0 && W > 0, "dwconv: bad argument");
+  DY_CHECK_ARG(Cin == 2 * Cout, "dwconv: only groups == Cout with Cin == 2*Cout is implemented (Cin %d, Cout %d)", Cin, Cout);
+  DY_CHECK_ARG(Cout % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0, "dwconv: slices must be 16B aligned, Cout % 8 == 0");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (Cout / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  dwconv3x3s2_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), in_ld, B, H, W, weight,
+                                                                        bias, Cout, static_cast<__nv_bfloat16*>(out), out_ld);
+  return launch_status("dwconv3x3s2_kernel");
+}
+
+}  // namespace dy
+
+extern "C" int dy_stem_conv(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
+                            int out_ld, void* stream) {
+  return dy::stem_launch(in, B, H, W, weight, bias, Cout, out, out_ld, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dy_sppf_pool(void* buf, int B, int H, int W, int C, int ld, void* stream) {
+  return dy::sppf_pool_launch(buf, B, H, W, C, ld, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dy_upsample2x(const void* in, int in_ld, int B, int H, int W, int C, void* out, int out_ld, void* stream) {
+  return dy::upsample2x_launch(in, in_ld, B, H, W, C, out, out_ld, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dy_dwconv3x3s2(const void* in, int in_ld, int B, int H, int W, int Cin, const float* weight, const float* bias,
+                              int Cout, void* out, int out_ld, void* stream) {
+  return dy::dwconv_launch(in, in_ld, B, H, W, Cin, weight, bias, Cout, out, out_ld, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,394 @@
+// conv_igemm.cu — Conv(k in {1,3}, stride in {1,2}) + bias + SiLU (+ residual) as an implicit GEMM on the
+// sm_100a tensor cores.  Replaces the aten/cuDNN conv2d + BatchNorm + SiLU (+ add, + cat) kernel chain the
+// reference launches for every Conv / RepVGGBlock / Bottleneck (ultralytics/nn/modules/conv.py:49-55,
+// block.py:337-350,1480-1490).
+//
+// GEMM view: M = output pixels (B*Ho*Wo), N = Cout, K = k*k*Cin.  D[M,N] = A[M,K] * W[N,K]^T.
+//   * A is never materialised: for every filter tap (r,s) and every 64-channel block the TMA engine loads a
+//     [pixel tile x 64 ch] box of the NHWC activation, shifted by the tap offset; out-of-image coordinates are
+//     zero-filled by TMA, which IS the conv padding.  Stride-2 convs read four "parity" views of the input
+//     (even/odd rows x even/odd columns), so that every tap is again a dense box.
+//   * W is packed [tap][Cout_pad][Cin_pad] (K contiguous) and loaded by a 3-D TMA box.
+//   * Both operands land in shared memory in the 128B-swizzled K-major layout tcgen05.mma expects; one elected
+//     thread issues M=128 x N=BN x K=16 MMAs accumulating fp32 in TMEM (double-buffered accumulator).
+//   * 4 epilogue warps read the accumulator with tcgen05.ld, add the folded-BN bias, apply SiLU, add the optional
+//     residual, and store bf16 (or fp32) straight into a channel slice of the destination buffer (concat-write).
+//   * Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//     warps 4..7 = epilogue.
+#include "dy_common.cuh"
+#include "dy_ptx.cuh"
+#include "conv_igemm.h"
+#include <cstring>
+
+namespace dy {
+
+using namespace ptx;
+
+static constexpr int kBlockM = 128;           // UMMA M
+static constexpr int kBlockK = 64;            // bf16 per 128B swizzle row
+static constexpr int kABytes = kBlockM * 128; // one A stage
+static constexpr int kMaxStages = 8;
+static constexpr int kThreads = 256;
+static constexpr int kTmemCols = 512;
+static constexpr int kAccStride = 256;        // TMEM column offset between the two accumulator stages
+
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int kiters = p.ntaps * p.kblocks;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < p.nmaps; ++i) prefetch_tmap(&p.tmA[i]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH * p.TB) * 128u + b_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+        const int th_i = m_tile % p.tiles_h;
+        const int tb_i = m_tile / p.tiles_h;
+        const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.TB, n0 = n_tile * p.BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const ConvTap tap = p.taps[t];
+          for (int kc = 0; kc < p.kblocks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(sa, &p.tmA[tap.map], &full_bar[stage], kc * kBlockK, w0 + tap.dx, h0 + tap.dy, b0);
+            tma_load_3d(sa + kABytes, &p.tmB, &full_bar[stage], kc * kBlockK, n0, t);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, p.BN);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
+        for (int kb = 0; kb < kiters; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32, 1024), umma_desc_sw128(b_addr + k * 32, 1024),
+                         idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> regs -> bias/SiLU/residual -> global =====================
+    const int q = warp - 4;                         // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                  // accumulator row == pixel of the tile
+    const int rows_valid = p.TW * p.TH * p.TB;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int th_i = m_tile % p.tiles_h;
+      const int tb_i = m_tile / p.tiles_h;
+      const int wl = row % p.TW;
+      const int hl = (row / p.TW) % p.TH;
+      const int bl = row / (p.TW * p.TH);
+      const int w = tw_i * p.TW + wl, h = th_i * p.TH + hl, b = tb_i * p.TB + bl;
+      const bool valid = (row < rows_valid) && (w < p.Wo) && (h < p.Ho) && (b < p.B);
+      const size_t pix = (static_cast<size_t>(b) * p.Ho + h) * p.Wo + w;
+      const int n0 = n_tile * p.BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccStride);
+      for (int c = 0; c < p.BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr + c * 16, r);
+        tmem_ld_wait();
+        const int n = n0 + c * 16;
+        if (valid && n < p.Cout) {
+          float v[16];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bb = __ldg(bp + j);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+          }
+          if (p.act == DY_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+          }
+          const bool full16 = (n + 16 <= p.Cout);
+          if (p.res != nullptr) {
+            const __nv_bfloat16* rp = p.res + pix * p.res_ld + n;
+            if (full16) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[2 * j] += bf16_lo(rw[j]); v[2 * j + 1] += bf16_hi(rw[j]); }
+            } else {
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n;
+            if (full16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) op[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
+            if (full16) {
+              uint4 o0, o1;
+              o0.x = pack_bf16(v[0], v[1]);   o0.y = pack_bf16(v[2], v[3]);
+              o0.z = pack_bf16(v[4], v[5]);   o0.w = pack_bf16(v[6], v[7]);
+              o1.x = pack_bf16(v[8], v[9]);   o1.y = pack_bf16(v[10], v[11]);
+              o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
+              reinterpret_cast<uint4*>(op)[0] = o0;
+              reinterpret_cast<uint4*>(op)[1] = o1;
+            } else {
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) op[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side: tile-shape choice and tensor-map encoding.
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(DY_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(DY_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] strides [%llu,%llu,%llu] box [%u,%u,%u,%u] base %p",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                (unsigned long long)strides_bytes[0], (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+                (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+                rank > 3 ? box[3] : 0, base);
+  }
+  return DY_OK;
+}
+
+int conv_pick_bn(int cout_pad) {
+  int best = 16;
+  for (int bn = 16; bn <= 256; bn += 16)
+    if (cout_pad % bn == 0) best = bn;
+  return best;
+}
+
+// Pixel-tile shape (TW x TH x TB <= 128 rows) maximising the fraction of MMA rows that are real pixels.
+static void pick_tile(int Wo, int Ho, int B, int* TW, int* TH, int* TB) {
+  double best = -1.0; int bw = 1, bh = 1, bb = 1;
+  for (int tw = 1; tw <= Wo && tw <= 128; ++tw) {
+    for (int th = 1; th <= Ho && tw * th <= 128; ++th) {
+      const int tb_max = 128 / (tw * th);                                // a tile may span several images
+      for (int tb = 1; tb <= tb_max && tb <= B; ++tb) {
+        const double tiles = double(ceil_div(Wo, tw)) * ceil_div(Ho, th) * ceil_div(B, tb);
+        const double eff = double(Wo) * Ho * B / (tiles * 128.0);
+        // prefer wide boxes (longer contiguous runs for TMA) on ties
+        const double score = eff + 1e-6 * tw;
+        if (score > best) { best = score; bw = tw; bh = th; bb = tb; }
+      }
+    }
+  }
+  *TW = bw; *TH = bh; *TB = bb;
+}
+
+int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
+  DY_CHECK_ARG(d && p && l, "null conv descriptor");
+  DY_CHECK_ARG(d->in && d->weight && d->bias && d->out, "conv: null tensor pointer");
+  DY_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported (1 or 3)", d->ksize);
+  DY_CHECK_ARG(d->stride == 1 || (d->stride == 2 && d->ksize == 3), "conv: stride %d with k=%d unsupported", d->stride, d->ksize);
+  DY_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: bad shape");
+  DY_CHECK_ARG(d->Cin % 8 == 0 && d->in_ld % 8 == 0 && d->in_ld >= d->Cin, "conv: Cin/in_ld must be multiples of 8 (16B rows)");
+  DY_CHECK_ARG((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0,
+               "conv: in/weight must be 16B aligned");
+  const int out_esz = d->out_dtype == DY_F32 ? 4 : 2;
+  DY_CHECK_ARG(d->out_dtype == DY_BF16 || d->out_dtype == DY_F32, "conv: bad out dtype");
+  DY_CHECK_ARG((d->out_ld * out_esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "conv: out slice must be 16B aligned");
+  DY_CHECK_ARG((reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "conv: bias must be 16B aligned");
+  if (d->residual)
+    DY_CHECK_ARG(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "conv: residual slice must be 16B aligned");
+
+  memset(p, 0, sizeof(*p));
+  const int k = d->ksize, s = d->stride;
+  const int Ho = (d->H + 2 * (k / 2) - k) / s + 1, Wo = (d->W + 2 * (k / 2) - k) / s + 1;
+  const int cin_pad = round_up(d->Cin, kBlockK), cout_pad = round_up(d->Cout, 16);
+  p->BN = conv_pick_bn(cout_pad);
+  p->n_tiles = cout_pad / p->BN;
+  p->kblocks = cin_pad / kBlockK;
+  p->ntaps = k * k;
+  p->Cout = d->Cout;
+  p->out = d->out; p->out_ld = d->out_ld; p->out_f32 = d->out_dtype == DY_F32;
+  p->res = reinterpret_cast<const __nv_bfloat16*>(d->residual); p->res_ld = d->res_ld;
+  p->bias = d->bias; p->act = d->act;
+
+  const uint64_t esz = 2;
+  const uint64_t ld = d->in_ld;
+  const char* base = reinterpret_cast<const char*>(d->in);
+  if (k == 1) {
+    // flat GEMM over all pixels: "image" of width M, height 1
+    const uint64_t M = uint64_t(d->B) * d->H * d->W;
+    DY_CHECK_ARG(M < (1ull << 31), "conv: too many pixels");
+    p->Ho = 1; p->Wo = int(M); p->B = 1;
+    p->TW = int(M < 128 ? M : 128); p->TH = 1; p->TB = 1;
+    const uint64_t dims[4] = {uint64_t(d->Cin), M, 1, 1};
+    const uint64_t strides[3] = {ld * esz, M * ld * esz, M * ld * esz};
+    const uint32_t box[4] = {kBlockK, uint32_t(p->TW), 1, 1};
+    int rc = encode_map(&p->tmA[0], base, 4, dims, strides, box);
+    if (rc) return rc;
+    p->nmaps = 1;
+    p->taps[0] = ConvTap{0, 0, 0, 0};
+  } else {
+    p->Ho = Ho; p->Wo = Wo; p->B = d->B;
+    pick_tile(Wo, Ho, d->B, &p->TW, &p->TH, &p->TB);
+    const uint32_t box[4] = {kBlockK, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+    if (s == 1) {
+      const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(d->W), uint64_t(d->H), uint64_t(d->B)};
+      const uint64_t strides[3] = {ld * esz, uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
+      int rc = encode_map(&p->tmA[0], base, 4, dims, strides, box);
+      if (rc) return rc;
+      p->nmaps = 1;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) p->taps[r * 3 + c] = ConvTap{0, int16_t(c - 1), int16_t(r - 1), 0};
+    } else {
+      DY_CHECK_ARG(d->H >= 2 && d->W >= 2, "conv: stride-2 needs H,W >= 2");
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((d->W - px + 1) / 2), uint64_t((d->H - py + 1) / 2), uint64_t(d->B)};
+          const uint64_t strides[3] = {2 * ld * esz, 2 * uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
+          int rc = encode_map(&p->tmA[py * 2 + px], base + (uint64_t(py) * d->W + px) * ld * esz, 4, dims, strides, box);
+          if (rc) return rc;
+        }
+      p->nmaps = 4;
+      // tap offset o in {-1,0,+1}: input coord 2*x+o  ->  parity (o&1), coarse coord x + (o<0 ? -1 : 0)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          const int oy = r - 1, ox = c - 1;
+          const int py = oy & 1, px = ox & 1;
+          p->taps[r * 3 + c] = ConvTap{int16_t(py * 2 + px), int16_t(ox < 0 ? -1 : 0), int16_t(oy < 0 ? -1 : 0), 0};
+        }
+    }
+  }
+  p->tiles_w = ceil_div(p->Wo, p->TW);
+  p->tiles_h = ceil_div(p->Ho, p->TH);
+  p->m_tiles = p->tiles_w * p->tiles_h * ceil_div(p->B, p->TB);
+
+  {
+    const uint64_t dims[3] = {uint64_t(cin_pad), uint64_t(cout_pad), uint64_t(p->ntaps)};
+    const uint64_t strides[2] = {uint64_t(cin_pad) * esz, uint64_t(cin_pad) * cout_pad * esz};
+    const uint32_t box[3] = {kBlockK, uint32_t(p->BN), 1};
+    int rc = encode_map(&p->tmB, d->weight, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+
+  const int stage_bytes = kABytes + p->BN * 128;
+  int stages = (227 * 1024 - 2048) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p->stages = stages;
+  l->smem_bytes = stages * stage_bytes + 1024;
+  const int total = p->m_tiles * p->n_tiles;
+  const int sms = num_sms();
+  l->grid = total < sms ? total : sms;
+  return DY_OK;
+}
+
+int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
+  static int max_smem_set = 0;
+  if (max_smem_set < l->smem_bytes) {
+    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    max_smem_set = 227 * 1024;
+  }
+  conv_igemm_kernel<<<l->grid, kThreads, l->smem_bytes, stream>>>(*p);
+  return launch_status("conv_igemm_kernel");
+}
+
+}  // namespace dy
+
+extern "C" int dy_conv2d(const dy_conv_desc* d, void* stream) {
+  dy::ConvParams p; dy::ConvLaunch l;
+  int rc = dy::conv_build_params(d, &p, &l);
+  if (rc) return rc;
+  return dy::conv_launch(&p, &l, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,490 @@
+// nms.cu — batched, bit-exact NMS for the Detect output.
+// Replaces ops.non_max_suppression (ultralytics/utils/ops.py:181-332) and the torchvision.ops.nms call inside it
+// (:312): ~12 aten launches + 2 host syncs per image in the reference become two launches per batch.
+//
+//  kernel 1  nms_filter_kernel   grid (chunks of 2048 anchors, B)
+//            confidence test `amax(cls) > conf` (:250) in fp32 like torch's scalar compare, best class with the
+//            first-max tie rule (:290) or all (anchor, class) pairs for multi_label (:286-288), optional class
+//            filter (:294-295), optional in-place xywh->xyxy of the prediction (:259-260).  Survivors are
+//            compacted IN ANCHOR ORDER inside the chunk (warp shuffles + one block scan) as unique 64-bit keys
+//                 key = (~score_bits << 32) | (anchor*nc + cls)
+//            so ascending key order == descending score, ties broken by the lower candidate index: the order
+//            torchvision's stable descending sort produces.
+//  kernel 2  nms_select_kernel   one CTA per image
+//            repeatedly (a) radix-selects the next 512 smallest keys (MSD histogram passes in shared memory),
+//            (b) bitonic-sorts them, (c) builds class-offset boxes `xyxy + cls*max_wh` (:305-311) exactly as fp32
+//            torch ops do (no FMA contraction), (d) suppresses them against the boxes kept so far, (e) builds the
+//            512x512 upper-triangular IoU>thr bitmask in shared memory and (f) lets one warp do the greedy scan.
+//            Stops at max_det kept boxes (:313) or after max_nms candidates (:301-302); writes rows
+//            (x1,y1,x2,y2,conf,cls), the per-image count and (optionally) the reference's kept indices.
+#include "dy_common.cuh"
+
+namespace dy {
+
+static constexpr int kFilterThreads = 256;
+static constexpr int kChunk = 2048;            // anchors per filter CTA (2 groups x 256 threads x 4 anchors)
+static constexpr int kSelThreads = 512;
+static constexpr int kK = 512;                 // candidates per greedy round (== kSelThreads)
+static constexpr int kWords = kK / 32;
+static constexpr int kBins = 2048;
+static constexpr int kMaxPasses = 8;
+static constexpr int kMaxClassWords = 32;      // class filter bitmask: nc <= 1024
+
+struct NmsParams {
+  const float* pred; float* pred_rw;
+  int B, nc, A, nchunks;
+  float conf; float iou_f; int iou_inclusive;
+  int max_det, max_nms; float max_wh;
+  int agnostic, multi_label, in_place, has_class_filter;
+  uint32_t class_mask[kMaxClassWords];
+  unsigned long long cap;                      // candidate capacity per image
+  unsigned long long* keys;                    // [B][cap]
+  int* img_count;                              // [B]
+  int* chunk_base;                             // [B][nchunks]
+  int* chunk_cnt;                              // [B][nchunks]
+  float* out; int* counts; long long* kept;
+  int npasses; int pass_shift[kMaxPasses]; int pass_bits[kMaxPasses];
+};
+
+__device__ __forceinline__ bool class_allowed(const NmsParams& p, int c) {
+  return !p.has_class_filter || ((p.class_mask[c >> 5] >> (c & 31)) & 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: filter + order-preserving compaction per chunk
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFilterThreads) nms_filter_kernel(const __grid_constant__ NmsParams p) {
+  __shared__ int warp_tot[kFilterThreads / 32];
+  __shared__ int s_base;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a_chunk = chunk * kChunk;
+  const size_t A = p.A;
+  const float* img = p.pred + static_cast<size_t>(b) * (4 + p.nc) * A;
+  const bool vec_ok = (p.A & 3) == 0;
+
+  // pass 1: per-thread candidate counts for its 2 groups of 4 consecutive anchors
+  float best[8]; int bestc[8]; int cnt[8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int a0 = a_chunk + g * (kChunk / 2) + tid * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best[g * 4 + k] = -INFINITY; bestc[g * 4 + k] = 0; cnt[g * 4 + k] = 0; }
+    if (a0 < p.A) {
+      for (int c = 0; c < p.nc; ++c) {
+        float v[4];
+        const float* src = img + (4 + c) * A + a0;
+        if (vec_ok) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = (a0 + k < p.A) ? __ldg(src + k) : -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (p.multi_label) {
+            if (v[k] > p.conf && class_allowed(p, c)) cnt[g * 4 + k]++;
+          } else if (v[k] > best[g * 4 + k]) { best[g * 4 + k] = v[k]; bestc[g * 4 + k] = c; }
+        }
+      }
+      if (!p.multi_label) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          cnt[g * 4 + k] = (best[g * 4 + k] > p.conf && class_allowed(p, bestc[g * 4 + k])) ? 1 : 0;
+      }
+      if (p.in_place) {   // prediction[..., :4] = xywh2xyxy(prediction[..., :4])  (ops.py:259-260, :432-449)
+        float* rw = p.pred_rw + static_cast<size_t>(b) * (4 + p.nc) * A;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int a = a0 + k;
+          if (a < p.A) {
+            const float cx = rw[a], cy = rw[A + a], hw = __fmul_rn(rw[2 * A + a], 0.5f), hh = __fmul_rn(rw[3 * A + a], 0.5f);
+            rw[a] = __fsub_rn(cx, hw); rw[A + a] = __fsub_rn(cy, hh);
+            rw[2 * A + a] = __fadd_rn(cx, hw); rw[3 * A + a] = __fadd_rn(cy, hh);
+          }
+        }
+      }
+    }
+  }
+
+  // block exclusive scan over (group, thread) order
+  int tot[2] = {cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]};
+  int offs[2]; int running = 0;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    int incl = tot[g];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += n; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kFilterThreads / 32; ++w) { const int t = warp_tot[w]; if (w < warp) wbase += t; all += t; }
+    offs[g] = running + wbase + incl - tot[g];
+    running += all;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int base = running ? atomicAdd(&p.img_count[b], running) : 0;
+    s_base = base;
+    p.chunk_base[b * p.nchunks + chunk] = base;
+    p.chunk_cnt[b * p.nchunks + chunk] = running;
+  }
+  __syncthreads();
+  if (running == 0) return;
+  unsigned long long* dst = p.keys + static_cast<size_t>(b) * p.cap + s_base;
+
+  // pass 2: write keys in order
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int a0 = a_chunk + g * (kChunk / 2) + tid * 4;
+    int o = offs[g];
+    if (tot[g] == 0) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (cnt[g * 4 + k] == 0) continue;
+      const int a = a0 + k;
+      if (p.multi_label) {
+        for (int c = 0; c < p.nc; ++c) {
+          const float v = __ldg(img + (4 + c) * A + a);
+          if (v > p.conf && class_allowed(p, c)) {
+            dst[o++] = (static_cast<unsigned long long>(~__float_as_uint(v)) << 32) |
+                       static_cast<unsigned long long>(static_cast<unsigned>(a) * static_cast<unsigned>(p.nc) + c);
+          }
+        }
+      } else {
+        dst[o++] = (static_cast<unsigned long long>(~__float_as_uint(best[g * 4 + k])) << 32) |
+                   static_cast<unsigned long long>(static_cast<unsigned>(a) * static_cast<unsigned>(p.nc) + bestc[g * 4 + k]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: per-image radix select + sort + greedy suppression
+// ------------------------------------------------------------------------------------------------
+// torchvision's test `inter / (area_i + area_j - inter) > iou_threshold` in fp32 (CPU kernel: the float quotient is
+// compared against the double threshold, which is `>= float(thr)` when float(thr) rounds up and `> float(thr)` else).
+__device__ __forceinline__ bool iou_suppresses(const float4& a, float area_a, const float4& b, float area_b,
+                                               float thr, int inclusive) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(w, h);
+  if (!(inter > 0.f)) return false;           // 0/x == 0 and 0/0 == NaN never exceed a threshold in [0,1]
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return inclusive ? (ovr >= thr) : (ovr > thr);
+}
+
+struct SelShared {
+  unsigned long long sel_key[kK];
+  float4 box[kK];
+  float area[kK];
+  unsigned int hist[kBins];
+  unsigned int mask[kWords * (kK + 1)];
+  unsigned int remv[kWords];
+  int scan_tmp[kSelThreads / 32];
+  int sel_count;
+  int kept;
+  int found_bin; unsigned int found_below;
+};
+
+static constexpr size_t kSelSharedBytes = (sizeof(SelShared) + 15) & ~size_t(15);
+
+__device__ __forceinline__ void load_offset_box(const NmsParams& p, const float* img, unsigned long long key,
+                                                float4* box, float* area) {
+  const unsigned id = static_cast<unsigned>(key & 0xffffffffull);
+  const unsigned a = id / static_cast<unsigned>(p.nc), cls = id - a * static_cast<unsigned>(p.nc);
+  const size_t A = p.A;
+  float x1, y1, x2, y2;
+  if (p.in_place) { x1 = img[a]; y1 = img[A + a]; x2 = img[2 * A + a]; y2 = img[3 * A + a]; }
+  else {
+    const float cx = img[a], cy = img[A + a], hw = __fmul_rn(img[2 * A + a], 0.5f), hh = __fmul_rn(img[3 * A + a], 0.5f);
+    x1 = __fsub_rn(cx, hw); y1 = __fsub_rn(cy, hh); x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
+  }
+  const float c = __fmul_rn(static_cast<float>(cls), p.agnostic ? 0.f : p.max_wh);   // x[:, 5:6] * max_wh
+  box->x = __fadd_rn(x1, c); box->y = __fadd_rn(y1, c); box->z = __fadd_rn(x2, c); box->w = __fadd_rn(y2, c);
+  *area = __fmul_rn(__fsub_rn(box->z, box->x), __fsub_rn(box->w, box->y));
+}
+
+__global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_constant__ NmsParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SelShared& s = *reinterpret_cast<SelShared*>(smem_raw);
+  // kept-box state lives behind SelShared: boxes, areas, keys, ranks (max_det entries each)
+  float4* kbox = reinterpret_cast<float4*>(smem_raw + kSelSharedBytes);
+  unsigned long long* kkey = reinterpret_cast<unsigned long long*>(kbox + p.max_det);
+  float* karea = reinterpret_cast<float*>(kkey + p.max_det);
+  int* krank = reinterpret_cast<int*>(karea + p.max_det);
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.img_count[b];
+  const float* img = (p.in_place ? p.pred_rw : p.pred) + static_cast<size_t>(b) * (4 + p.nc) * static_cast<size_t>(p.A);
+  const unsigned long long* keys = p.keys + static_cast<size_t>(b) * p.cap;
+  const int limit = min(n, p.max_nms);
+  if (tid == 0) s.kept = 0;
+  __syncthreads();
+
+  int processed = 0;
+  unsigned long long prev_T = 0ull;            // every key is > 0 (scores are finite, so ~bits != 0 ... and id part)
+  bool first = true;
+  while (processed < limit) {
+    const int K = min(kK, limit - processed);
+    // ---- (a) radix select: T = K-th smallest key among keys > prev_T (or >= for the first round) ----
+    unsigned long long prefix_val = 0ull, prefix_mask = 0ull;
+    unsigned int k_rem = static_cast<unsigned>(K);
+    const bool take_all = (n - processed) <= K;          // everything left fits in this round: skip the select
+    if (!take_all) {
+      for (int ps = 0; ps < p.npasses; ++ps) {
+        const int shift = p.pass_shift[ps];
+        const unsigned int dmask = (1u << p.pass_bits[ps]) - 1u;
+        for (int i = tid; i < kBins; i += kSelThreads) s.hist[i] = 0u;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+          const int i = i0 + tid;
+          unsigned int digit = 0xffffffffu;
+          if (i < n) {
+            const unsigned long long key = keys[i];
+            const bool live = first ? true : (key > prev_T);
+            if (live && (key & prefix_mask) == prefix_val) digit = static_cast<unsigned>(key >> shift) & dmask;
+          }
+          const unsigned peers = __match_any_sync(0xffffffffu, digit);
+          if (digit != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&s.hist[digit], __popc(peers));
+        }
+        __syncthreads();
+        // locate the bin holding the k_rem-th element: each thread owns 4 consecutive bins
+        const unsigned h0 = s.hist[tid * 4], h1 = s.hist[tid * 4 + 1], h2 = s.hist[tid * 4 + 2], h3 = s.hist[tid * 4 + 3];
+        const int mine = static_cast<int>(h0 + h1 + h2 + h3);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) s.scan_tmp[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s.scan_tmp[w];
+        const unsigned int excl = static_cast<unsigned>(wbase + incl - mine);
+        if (k_rem > excl && k_rem <= excl + static_cast<unsigned>(mine)) {
+          unsigned int below = excl; int bin = tid * 4;
+          if (k_rem > below + h0) { below += h0; bin++;
+            if (k_rem > below + h1) { below += h1; bin++;
+              if (k_rem > below + h2) { below += h2; bin++; } } }
+          s.found_bin = bin; s.found_below = below;
+        }
+        __syncthreads();
+        prefix_val |= static_cast<unsigned long long>(static_cast<unsigned>(s.found_bin)) << shift;
+        prefix_mask |= static_cast<unsigned long long>(dmask) << shift;
+        k_rem -= s.found_below;
+        __syncthreads();
+      }
+    }
+    const unsigned long long T = take_all ? ~0ull : prefix_val;
+
+    // ---- (b) gather keys in (prev_T, T] and sort them ascending (bitonic, 512 slots) ----
+    if (tid == 0) s.sel_count = 0;
+    s.sel_key[tid] = ~0ull;
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+      const unsigned long long key = keys[i];
+      const bool live = first ? true : (key > prev_T);
+      if (live && key <= T) {
+        const int slot = atomicAdd(&s.sel_count, 1);
+        if (slot < kK) s.sel_key[slot] = key;
+      }
+    }
+    __syncthreads();
+    for (int size = 2; size <= kK; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const int partner = tid ^ stride;
+        if (partner > tid) {
+          const unsigned long long x = s.sel_key[tid], y = s.sel_key[partner];
+          const bool up = (tid & size) == 0;
+          if ((x > y) == up) { s.sel_key[tid] = y; s.sel_key[partner] = x; }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- (c) class-offset boxes ----
+    const bool have = tid < K;
+    float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f); float myarea = 0.f;
+    if (have) { load_offset_box(p, img, s.sel_key[tid], &mybox, &myarea); s.box[tid] = mybox; s.area[tid] = myarea; }
+    // ---- (d) suppress against boxes kept in earlier rounds ----
+    bool dead = !have;
+    const int kept0 = s.kept;
+    if (have) {
+      for (int i = 0; i < kept0 && !dead; ++i) dead = iou_suppresses(kbox[i], karea[i], mybox, myarea, p.iou_f, p.iou_inclusive);
+    }
+    const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) s.remv[warp] = dead_bits;
+    __syncthreads();
+    // ---- (e) upper-triangular suppression bitmask: thread i owns row i; mask[w][i] covers j in [32w, 32w+32) ----
+    if (have) {
+      for (int w = 0; w < kWords; ++w) {
+        unsigned int bits = 0u;
+        const int j0 = w * 32;
+        if (j0 + 31 > tid && j0 < K && !dead) {
+          const int jend = min(32, K - j0);
+          for (int jj = 0; jj < jend; ++jj) {
+            const int j = j0 + jj;
+            if (j > tid && iou_suppresses(mybox, myarea, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+          }
+        }
+        s.mask[w * (kK + 1) + tid] = bits;
+      }
+    }
+    __syncthreads();
+    // ---- (f) greedy scan by warp 0: lane w holds remv word w ----
+    if (warp == 0) {
+      unsigned int remv = lane < kWords ? s.remv[lane] : 0xffffffffu;
+      int kept = kept0;
+      const int nwords = (K + 31) / 32;
+      for (int wi = 0; wi < nwords && kept < p.max_det; ++wi) {
+        unsigned int cur = __shfl_sync(0xffffffffu, remv, wi);
+        const int nb = min(32, K - wi * 32);
+        unsigned int avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+        while (avail && kept < p.max_det) {
+          const int bit = __ffs(avail) - 1;
+          const int i = wi * 32 + bit;
+          if (lane == 0) { kbox[kept] = s.box[i]; karea[kept] = s.area[i]; kkey[kept] = s.sel_key[i]; krank[kept] = processed + i; }
+          kept++;
+          if (lane < kWords) remv |= s.mask[lane * (kK + 1) + i];
+          cur = __shfl_sync(0xffffffffu, remv, wi);
+          avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+          avail &= ~((2u << bit) - 1u);          // only bits above the one just taken
+        }
+      }
+      if (lane == 0) s.kept = kept;
+    }
+    __syncthreads();
+    processed += K;
+    prev_T = T;
+    first = false;
+    if (s.kept >= p.max_det) break;
+  }
+
+  // ---- output rows x[i] = (x1,y1,x2,y2,conf,cls) (ops.py:327) ----
+  __syncthreads();
+  const int kept = s.kept;
+  if (tid == 0) p.counts[b] = kept;
+  const size_t A = p.A;
+  for (int t = tid; t < kept; t += kSelThreads) {
+    const unsigned long long key = kkey[t];
+    const unsigned id = static_cast<unsigned>(key & 0xffffffffull);
+    const unsigned a = id / static_cast<unsigned>(p.nc), cls = id - a * static_cast<unsigned>(p.nc);
+    float x1, y1, x2, y2;
+    if (p.in_place) { x1 = img[a]; y1 = img[A + a]; x2 = img[2 * A + a]; y2 = img[3 * A + a]; }
+    else {
+      const float cx = img[a], cy = img[A + a], hw = __fmul_rn(img[2 * A + a], 0.5f), hh = __fmul_rn(img[3 * A + a], 0.5f);
+      x1 = __fsub_rn(cx, hw); y1 = __fsub_rn(cy, hh); x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
+    }
+    float* o = p.out + (static_cast<size_t>(b) * p.max_det + t) * 6;
+    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+    o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
+    o[5] = static_cast<float>(cls);
+    if (p.kept) {
+      long long pos;
+      if (n > p.max_nms) pos = krank[t];       // x was re-ordered by score (ops.py:302): index == sorted rank
+      else {
+        // position in the anchor-ordered candidate list: candidates of earlier chunks + rank inside this chunk
+        const int chunk = static_cast<int>(a) / kChunk;
+        int before = 0;
+        for (int c = 0; c < chunk; ++c) before += p.chunk_cnt[b * p.nchunks + c];
+        const unsigned long long* lst = keys + p.chunk_base[b * p.nchunks + chunk];
+        int lo = 0, hi = p.chunk_cnt[b * p.nchunks + chunk];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (static_cast<unsigned>(lst[mid] & 0xffffffffull) < id) lo = mid + 1; else hi = mid; }
+        pos = before + lo;
+      }
+      p.kept[static_cast<size_t>(b) * p.max_det + t] = pos;
+    }
+  }
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+struct NmsWorkspace { size_t keys, img_count, chunk_base, chunk_cnt, total; unsigned long long cap; int nchunks; };
+
+static NmsWorkspace nms_workspace_layout(int B, int nc, int A, int multi_label) {
+  NmsWorkspace w{};
+  w.nchunks = ceil_div(A, kChunk);
+  w.cap = static_cast<unsigned long long>(A) * ((multi_label && nc > 1) ? nc : 1);
+  size_t off = 0;
+  w.keys = off; off = align16(off + static_cast<size_t>(B) * w.cap * 8);
+  w.img_count = off; off = align16(off + static_cast<size_t>(B) * 4);
+  w.chunk_base = off; off = align16(off + static_cast<size_t>(B) * w.nchunks * 4);
+  w.chunk_cnt = off; off = align16(off + static_cast<size_t>(B) * w.nchunks * 4);
+  w.total = off;
+  return w;
+}
+
+int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
+  DY_CHECK_ARG(d && d->pred && d->out && d->counts && d->workspace, "nms: null pointer");
+  DY_CHECK_ARG(d->B > 0 && d->nc > 0 && d->A > 0, "nms: bad shape");
+  DY_CHECK_ARG(d->B <= 65535, "nms: B > 65535 unsupported");
+  DY_CHECK_ARG(d->nc <= kMaxClassWords * 32, "nms: nc > %d unsupported", kMaxClassWords * 32);
+  DY_CHECK_ARG(static_cast<unsigned long long>(d->A) * d->nc < (1ull << 32), "nms: A*nc must fit 32 bits");
+  DY_CHECK_ARG(d->conf_thres >= 0.f && d->conf_thres <= 1.f, "nms: conf_thres outside [0,1]");
+  DY_CHECK_ARG(d->iou_thres >= 0.0 && d->iou_thres <= 1.0, "nms: iou_thres outside [0,1]");
+  DY_CHECK_ARG(d->max_det > 0 && d->max_det <= 4096, "nms: max_det must be in [1,4096]");
+  DY_CHECK_ARG(d->max_nms > 0, "nms: max_nms must be positive");
+  const int ml = d->multi_label && d->nc > 1;
+  const NmsWorkspace w = nms_workspace_layout(d->B, d->nc, d->A, ml);
+  DY_CHECK_ARG(d->workspace_bytes >= w.total, "nms: workspace too small (%zu < %zu)", d->workspace_bytes, w.total);
+  DY_CHECK_ARG((reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0, "nms: workspace must be 16B aligned");
+
+  NmsParams p{};
+  p.pred = d->pred; p.pred_rw = const_cast<float*>(d->pred);
+  p.B = d->B; p.nc = d->nc; p.A = d->A; p.nchunks = w.nchunks;
+  p.conf = d->conf_thres;
+  const float f = static_cast<float>(d->iou_thres);
+  p.iou_f = f; p.iou_inclusive = static_cast<double>(f) > d->iou_thres ? 1 : 0;
+  p.max_det = d->max_det; p.max_nms = d->max_nms; p.max_wh = d->max_wh;
+  p.agnostic = d->agnostic; p.multi_label = ml; p.in_place = d->xyxy_in_place;
+  p.has_class_filter = 0;
+  if (d->classes_host && d->n_classes > 0) {
+    p.has_class_filter = 1;
+    for (int i = 0; i < d->n_classes; ++i) {
+      const int c = d->classes_host[i];
+      if (c >= 0 && c < d->nc) p.class_mask[c >> 5] |= 1u << (c & 31);
+    }
+  }
+  char* ws = static_cast<char*>(d->workspace);
+  p.cap = w.cap;
+  p.keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
+  p.img_count = reinterpret_cast<int*>(ws + w.img_count);
+  p.chunk_base = reinterpret_cast<int*>(ws + w.chunk_base);
+  p.chunk_cnt = reinterpret_cast<int*>(ws + w.chunk_cnt);
+  p.out = d->out; p.counts = d->counts; p.kept = reinterpret_cast<long long*>(d->kept);
+
+  // MSD digit plan over the 64-bit key: 32 score bits, then the significant bits of anchor*nc+cls
+  int np = 0;
+  p.pass_shift[np] = 53; p.pass_bits[np++] = 11;
+  p.pass_shift[np] = 42; p.pass_bits[np++] = 11;
+  p.pass_shift[np] = 32; p.pass_bits[np++] = 10;
+  int idbits = 1;
+  while ((1ull << idbits) < static_cast<unsigned long long>(d->A) * d->nc) ++idbits;
+  int hi = idbits;
+  while (hi > 0) { const int nb = hi >= 11 ? 11 : hi; p.pass_shift[np] = hi - nb; p.pass_bits[np++] = nb; hi -= nb; }
+  p.npasses = np;
+
+  DY_CUDA(cudaMemsetAsync(p.img_count, 0, static_cast<size_t>(d->B) * 4, stream));
+  dim3 fgrid(w.nchunks, d->B);
+  nms_filter_kernel<<<fgrid, kFilterThreads, 0, stream>>>(p);
+  int rc = launch_status("nms_filter_kernel");
+  if (rc) return rc;
+  const size_t smem = kSelSharedBytes + static_cast<size_t>(d->max_det) * (16 + 8 + 4 + 4);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    DY_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  nms_select_kernel<<<d->B, kSelThreads, smem, stream>>>(p);
+  return launch_status("nms_select_kernel");
+}
+
+}  // namespace dy
+
+extern "C" size_t dy_nms_workspace_bytes(int B, int nc, int A, int multi_label) {
+  if (B <= 0 || nc <= 0 || A <= 0) return 0;
+  return dy::nms_workspace_layout(B, nc, A, multi_label).total;
+}
+
+extern "C" int dy_nms(const dy_nms_desc* d, void* stream) { return dy::nms_launch(d, static_cast<cudaStream_t>(stream)); }

@@ -1,0 +1,260 @@
+"""Tensor-level wrappers over the C-ABI (drone_yolo_b200/_C.py -> libdroneyolo.so).
+
+Activations are torch tensors of logical shape (B, C, H, W) in channels_last memory (i.e. NHWC bf16), possibly a
+channel slice `buf[:, c0:c1]` of a wider concat buffer.  PyTorch is used only for memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _C
+
+BLOCK_K = 64
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def nhwc_view(t: torch.Tensor, what: str = "tensor"):
+    """Validate a (B,C,H,W) channels-last (slice) tensor; return (ptr, ld, B, H, W, C)."""
+    _C.require_cuda(t)
+    if t.dim() != 4:
+        raise _C.DroneYoloError(f"{what}: expected a 4-D (B,C,H,W) tensor, got shape {tuple(t.shape)}")
+    B, Cc, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    ld = sw if W > 1 else (sh if H > 1 else max(Cc, sc))
+    ok = (sc == 1 or Cc == 1) and (W == 1 or sw == ld) and (H == 1 or sh == W * ld) and (B == 1 or sb == H * W * ld)
+    if not ok or ld < Cc:
+        raise _C.DroneYoloError(
+            f"{what}: expected channels_last (NHWC) memory or a channel slice of it, got shape {tuple(t.shape)} "
+            f"strides {t.stride()}"
+        )
+    return t.data_ptr(), ld, B, H, W, Cc
+
+
+def empty_nhwc(B: int, Cc: int, H: int, W: int, device, dtype=torch.bfloat16) -> torch.Tensor:
+    return torch.empty((B, H, W, Cc), device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) any layout/dtype -> bf16 channels_last with C padded to a multiple of 8 kept as a slice."""
+    B, Cc, H, W = x.shape
+    Cp = _ceil(Cc, 8)
+    buf = torch.zeros((B, H, W, Cp), device=x.device, dtype=torch.bfloat16)
+    buf[..., :Cc] = x.permute(0, 2, 3, 1)
+    return buf.permute(0, 3, 1, 2)[:, :Cc]
+
+
+def pack_conv_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
+    """fp32 [Cout,Cin,k,k] (+bias [Cout]) -> bf16 [k*k, Cout_pad, Cin_pad] tap-major K-contiguous, fp32 bias [Cout_pad].
+
+    BN folding / RepVGG merging must already have been done in fp32 (see nn.modules.*.fused_weight_bias)."""
+    Cout, Cin, kh, kw = w.shape
+    cout_p, cin_p = _ceil(Cout, 16), _ceil(Cin, BLOCK_K)
+    packed = torch.zeros((kh * kw, cout_p, cin_p), device=w.device, dtype=torch.float32)
+    packed[:, :Cout, :Cin] = w.float().permute(2, 3, 0, 1).reshape(kh * kw, Cout, Cin)
+    bias = torch.zeros((cout_p,), device=w.device, dtype=torch.float32)
+    if b is not None:
+        bias[:Cout] = b.float()
+    return packed.to(torch.bfloat16).contiguous(), bias.contiguous()
+
+
+def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, k: int, s: int, act: bool,
+              out: torch.Tensor, residual: Optional[torch.Tensor] = None) -> _C.ConvDesc:
+    xp, xld, B, H, W, Cin = nhwc_view(x, "conv input")
+    op, old, Bo, Ho, Wo, Co = nhwc_view(out, "conv output")
+    if x.dtype != torch.bfloat16:
+        raise _C.DroneYoloError(f"conv input must be bf16, got {x.dtype}")
+    p = k // 2
+    eh, ew = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    if (Bo, Ho, Wo, Co) != (B, eh, ew, cout):
+        raise _C.DroneYoloError(f"conv output shape {(Bo, Co, Ho, Wo)} != expected {(B, cout, eh, ew)}")
+    if w_packed.shape != (k * k, _ceil(cout, 16), _ceil(Cin, BLOCK_K)) or w_packed.dtype != torch.bfloat16:
+        raise _C.DroneYoloError(f"packed weight shape {tuple(w_packed.shape)} does not match Cin={Cin} Cout={cout} k={k}")
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise _C.DroneYoloError(f"conv output dtype {out.dtype} unsupported")
+    d = _C.ConvDesc()
+    d.in_, d.in_ld, d.B, d.H, d.W, d.Cin = xp, xld, B, H, W, Cin
+    d.weight, d.bias = w_packed.data_ptr(), bias.data_ptr()
+    d.Cout, d.ksize, d.stride = cout, k, s
+    d.out, d.out_ld = op, old
+    d.out_dtype = _C.DY_F32 if out.dtype == torch.float32 else _C.DY_BF16
+    if residual is not None:
+        rp, rld, Br, Hr, Wr, Cr = nhwc_view(residual, "conv residual")
+        if (Br, Hr, Wr, Cr) != (B, eh, ew, cout) or residual.dtype != torch.bfloat16:
+            raise _C.DroneYoloError("conv residual must be bf16 with the output's shape")
+        d.residual, d.res_ld = rp, rld
+    else:
+        d.residual, d.res_ld = None, 0
+    d.act = _C.DY_ACT_SILU if act else _C.DY_ACT_NONE
+    return d
+
+
+def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, residual=None, out=None,
+           out_dtype=torch.bfloat16) -> torch.Tensor:
+    """act(conv(x) + bias) [+ residual] on tcgen05 tensor cores (dy_conv2d)."""
+    B, _, H, W = x.shape
+    p = k // 2
+    if out is None:
+        out = empty_nhwc(B, cout, (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1, x.device, out_dtype)
+    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual)
+    _C.check(_C.lib().dy_conv2d(C.byref(d), _C.stream_ptr(x.device)), "dy_conv2d")
+    return out
+
+
+def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: NCHW fp32 contiguous [B,3,H,W]; w27 fp32 [Cout,27]; returns bf16 NHWC [B,Cout,H/2,W/2] view."""
+    _C.require_cuda(x, w27, bias)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[1] != 3:
+        raise _C.DroneYoloError("stem_conv expects a contiguous fp32 NCHW tensor with 3 channels")
+    B, _, H, W = x.shape
+    cout = w27.shape[0]
+    if out is None:
+        out = empty_nhwc(B, cout, (H - 1) // 2 + 1, (W - 1) // 2 + 1, x.device)
+    op, old, *_ = nhwc_view(out, "stem output")
+    _C.check(_C.lib().dy_stem_conv(x.data_ptr(), B, H, W, w27.data_ptr(), bias.data_ptr(), cout, op, old,
+                                   _C.stream_ptr(x.device)), "dy_stem_conv")
+    return out
+
+
+def sppf_pool(buf: torch.Tensor, c: int) -> torch.Tensor:
+    """buf: bf16 NHWC (B,>=4c,H,W); fills channels [c,4c) with mp5, mp5∘mp5, mp5∘mp5∘mp5 of channels [0,c)."""
+    p, ld, B, H, W, Cc = nhwc_view(buf, "sppf buffer")
+    if Cc < 4 * c or buf.dtype != torch.bfloat16:
+        raise _C.DroneYoloError("sppf_pool needs a bf16 buffer with at least 4*c channels")
+    _C.check(_C.lib().dy_sppf_pool(p, B, H, W, c, ld, _C.stream_ptr(buf.device)), "dy_sppf_pool")
+    return buf
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    xp, xld, B, H, W, Cc = nhwc_view(x, "upsample input")
+    if out is None:
+        out = empty_nhwc(B, Cc, 2 * H, 2 * W, x.device)
+    op, old, Bo, Ho, Wo, Co = nhwc_view(out, "upsample output")
+    if (Bo, Ho, Wo, Co) != (B, 2 * H, 2 * W, Cc) or x.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise _C.DroneYoloError("upsample2x: output must be bf16 (B,C,2H,2W)")
+    _C.check(_C.lib().dy_upsample2x(xp, xld, B, H, W, Cc, op, old, _C.stream_ptr(x.device)), "dy_upsample2x")
+    return out
+
+
+def dwconv3x3s2(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 NHWC (B,2c,H,W); w fp32 [c,2,3,3] (BN folded); returns SiLU(conv+bias) (B,c,H/2,W/2)."""
+    xp, xld, B, H, W, Cin = nhwc_view(x, "dwconv input")
+    cout = w.shape[0]
+    if out is None:
+        out = empty_nhwc(B, cout, (H - 1) // 2 + 1, (W - 1) // 2 + 1, x.device)
+    op, old, *_ = nhwc_view(out, "dwconv output")
+    w = w.reshape(cout, 18).float().contiguous()
+    _C.check(_C.lib().dy_dwconv3x3s2(xp, xld, B, H, W, Cin, w.data_ptr(), bias.data_ptr(), cout, op, old,
+                                     _C.stream_ptr(x.device)), "dy_dwconv3x3s2")
+    return out
+
+
+def decode_desc(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: int, out: torch.Tensor) -> _C.DecodeDesc:
+    """levels: per-level raw maps (B, 64+nc, H, W); contiguous NCHW or channels-last (slice), fp32 or bf16."""
+    d = _C.DecodeDesc()
+    no = 64 + nc
+    nl = len(levels)
+    if not 1 <= nl <= 4:
+        raise _C.DroneYoloError("decode supports 1..4 levels")
+    layouts, dts = set(), set()
+    for i, t in enumerate(levels):
+        _C.require_cuda(t)
+        B, Cc, H, W = t.shape
+        if Cc != no:
+            raise _C.DroneYoloError(f"decode level {i}: expected {no} channels, got {Cc}")
+        dts.add(t.dtype)
+        if t.is_contiguous() and not (H * W > 1 and t.stride(1) == 1):
+            layouts.add(_C.DY_NCHW)
+            d.ld[i] = 0
+        else:
+            _, ld, *_ = nhwc_view(t, f"decode level {i}")
+            layouts.add(_C.DY_NHWC)
+            d.ld[i] = ld
+        d.lvl[i], d.H[i], d.W[i], d.stride[i] = t.data_ptr(), H, W, float(strides[i])
+    if len(layouts) != 1 or len(dts) != 1:
+        raise _C.DroneYoloError("decode: all levels must share one layout and dtype")
+    dt = dts.pop()
+    if dt not in (torch.bfloat16, torch.float32):
+        raise _C.DroneYoloError(f"decode: unsupported dtype {dt}")
+    d.nl, d.B, d.nc = nl, levels[0].shape[0], nc
+    d.dtype = _C.DY_F32 if dt == torch.float32 else _C.DY_BF16
+    d.layout = layouts.pop()
+    d.out = out.data_ptr()
+    return d
+
+
+def detect_decode(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Detect._inference on the GPU: returns y (B, 4+nc, A) fp32."""
+    B = levels[0].shape[0]
+    A = sum(int(t.shape[2]) * int(t.shape[3]) for t in levels)
+    if out is None:
+        out = torch.empty((B, 4 + nc, A), device=levels[0].device, dtype=torch.float32)
+    elif out.shape != (B, 4 + nc, A) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise _C.DroneYoloError("decode: out must be contiguous fp32 (B,4+nc,A)")
+    d = decode_desc(levels, strides, nc, out)
+    _C.check(_C.lib().dy_detect_decode(C.byref(d), _C.stream_ptr(out.device)), "dy_detect_decode")
+    return out
+
+
+class NmsBuffers:
+    """Output + workspace buffers of one dy_nms call shape (reused across calls)."""
+
+    def __init__(self, B: int, nc: int, A: int, max_det: int, multi_label: bool, device):
+        self.key = (B, nc, A, max_det, bool(multi_label), str(device))
+        nbytes = _C.lib().dy_nms_workspace_bytes(B, nc, A, int(bool(multi_label)))
+        self.workspace = torch.empty((nbytes,), device=device, dtype=torch.uint8)
+        self.out = torch.zeros((B, max_det, 6), device=device, dtype=torch.float32)
+        self.counts = torch.zeros((B,), device=device, dtype=torch.int32)
+        self.kept = torch.zeros((B, max_det), device=device, dtype=torch.int64)
+        self._classes = None
+
+
+def nms_desc(pred: torch.Tensor, bufs: NmsBuffers, conf_thres: float, iou_thres: float, max_det: int, max_nms: int,
+             max_wh: float, agnostic: bool, multi_label: bool, classes, in_place: bool, want_kept: bool = True) -> _C.NmsDesc:
+    _C.require_cuda(pred)
+    if pred.dim() != 3 or pred.dtype != torch.float32 or not pred.is_contiguous():
+        raise _C.DroneYoloError("nms: prediction must be a contiguous fp32 (B, 4+nc, A) tensor")
+    B, ch, A = pred.shape
+    nc = ch - 4
+    d = _C.NmsDesc()
+    d.pred, d.B, d.nc, d.A = pred.data_ptr(), B, nc, A
+    d.conf_thres, d.iou_thres = float(conf_thres), float(iou_thres)
+    d.max_det, d.max_nms, d.max_wh = int(max_det), int(max_nms), float(max_wh)
+    d.agnostic, d.multi_label = int(bool(agnostic)), int(bool(multi_label))
+    if classes is not None:
+        arr = (C.c_int32 * len(classes))(*[int(c) for c in classes])
+        bufs._classes = arr  # keep alive
+        d.classes_host, d.n_classes = C.cast(arr, C.POINTER(C.c_int32)), len(classes)
+    else:
+        d.classes_host, d.n_classes = None, 0
+    d.xyxy_in_place = int(bool(in_place))
+    d.out, d.counts = bufs.out.data_ptr(), bufs.counts.data_ptr()
+    d.kept = bufs.kept.data_ptr() if want_kept else None
+    d.workspace, d.workspace_bytes = bufs.workspace.data_ptr(), bufs.workspace.numel()
+    return d
+
+
+def nms(pred: torch.Tensor, conf_thres: float, iou_thres: float, max_det: int = 300, max_nms: int = 30000,
+        max_wh: float = 7680, agnostic: bool = False, multi_label: bool = False, classes=None, in_place: bool = False,
+        bufs: Optional[NmsBuffers] = None):
+    """Batched NMS on the GPU. Returns (out (B,max_det,6), counts (B,), kept (B,max_det)) device tensors."""
+    B, ch, A = pred.shape
+    nc = ch - 4
+    ml = bool(multi_label) and nc > 1
+    if bufs is None or bufs.key != (B, nc, A, max_det, ml, str(pred.device)):
+        bufs = NmsBuffers(B, nc, A, max_det, ml, pred.device)
+    d = nms_desc(pred, bufs, conf_thres, iou_thres, max_det, max_nms, max_wh, agnostic, ml, classes, in_place)
+    _C.check(_C.lib().dy_nms(C.byref(d), _C.stream_ptr(pred.device)), "dy_nms")
+    return bufs.out, bufs.counts, bufs.kept
+
+
+def selftest_umma(n: int, k: int) -> float:
+    err = C.c_float(float("nan"))
+    _C.check(_C.lib().dy_selftest_umma(n, k, C.byref(err), _C.stream_ptr()), "dy_selftest_umma")
+    return float(err.value)

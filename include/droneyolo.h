@@ -1,0 +1,175 @@
+/*
+ * droneyolo.h — C-ABI of libdroneyolo.so: the B200 (sm_100a) kernels behind the Drone-YOLO
+ * inference hot path (conv stack -> Detect decode -> NMS).
+ *
+ * The reference (331658260/Drone-YOLO, a fork of ultralytics 8.3.82) has no FFI of its own: the
+ * path sits behind Python modules that dispatch into aten/cuDNN and torchvision.  Each entry point
+ * below names the reference interface it replaces (file:line under the reference tree).  Calling
+ * convention for all of them:
+ *   - plain pointers and sizes; the caller (PyTorch, or any host) owns every buffer;
+ *   - device pointers unless the name says "host"; asynchronous on the given cudaStream_t
+ *     (passed as void* so this header needs no CUDA include);
+ *   - returns DY_OK (0) or a negative dy_status; never throws; dy_last_error() gives the text
+ *     of the last failure on the calling thread.
+ *   - activations are NHWC ("channels last"); a tensor may be a channel slice of a wider buffer,
+ *     described by its pixel stride `ld` (in elements).
+ */
+#ifndef DRONEYOLO_H_
+#define DRONEYOLO_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dy_status {
+  DY_OK = 0,
+  DY_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer)            */
+  DY_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed                       */
+  DY_ERR_UNSUPPORTED = -3, /* valid request the kernels do not implement              */
+  DY_ERR_NOMEM = -4
+} dy_status;
+
+typedef enum dy_dtype { DY_BF16 = 0, DY_F32 = 1 } dy_dtype;
+typedef enum dy_act { DY_ACT_NONE = 0, DY_ACT_SILU = 1 } dy_act;
+typedef enum dy_layout { DY_NHWC = 0, DY_NCHW = 1 } dy_layout;
+
+/* Version / capability ------------------------------------------------------------------- */
+int dy_version(void);                       /* 10000*major + 100*minor + patch           */
+const char* dy_last_error(void);            /* thread-local text of the last error       */
+int dy_device_check(int device);            /* DY_OK iff `device` is compute capability 10.x */
+
+/* ----------------------------------------------------------------------------------------
+ * Conv + folded-BN bias + SiLU (+ residual) as an implicit GEMM on tcgen05 tensor cores.
+ * Replaces: Conv.forward_fuse  ultralytics/nn/modules/conv.py:53-55  (act(conv(x)) after
+ *           fuse_conv_and_bn, utils/torch_utils.py:242-269), the deploy form of RepVGGBlock
+ *           (nn/modules/block.py:1421-1438,1480-1482), RepConv.forward_fuse (conv.py:198-200),
+ *           Bottleneck's residual add (block.py:348-350: x + cv2(cv1(x))), the bare nn.Conv2d
+ *           1x1 outputs of Detect (head.py:44,47) and the concat writes of C2f / Concat
+ *           (block.py:240-242, conv.py:331-333) via out/out_ld channel slices.
+ * in      : bf16 NHWC [B,H,W,Cin] slice, pixel stride in_ld elements (in_ld % 8 == 0, 16B aligned)
+ * weight  : bf16 packed [k*k][Cout_pad][Cin_pad] (tap-major, K contiguous), Cin_pad = ceil64(Cin),
+ *           Cout_pad = ceil16(Cout); BN already folded in fp32 by the host before the bf16 cast
+ * bias    : fp32 [Cout_pad]
+ * out     : bf16 or fp32 NHWC [B,Ho,Wo,Cout] slice, pixel stride out_ld; Ho=(H+2p-k)/s+1, p=k/2
+ * residual: optional bf16 NHWC [B,Ho,Wo,Cout] slice added AFTER the activation, or NULL
+ * ksize in {1,3}; stride in {1,2} (stride 2 needs even H and W); no dilation, no groups.
+ */
+typedef struct dy_conv_desc {
+  const void* in;      int32_t in_ld;
+  int32_t B, H, W, Cin;
+  const void* weight;  const float* bias;
+  int32_t Cout, ksize, stride;
+  void* out;           int32_t out_ld;  int32_t out_dtype;   /* dy_dtype */
+  const void* residual; int32_t res_ld;
+  int32_t act;                                               /* dy_act   */
+} dy_conv_desc;
+
+int dy_conv2d(const dy_conv_desc* d, void* stream);
+
+/* Stem conv: 3x3 stride-2 pad-1 Conv(3->Cout)+bias+SiLU reading the predictor's input tensor.
+ * Replaces: model.0 Conv of the YAMLs (cfg/models/v8/yolov8-p2-repvgg.yaml:17) together with the
+ *           dtype cast of BasePredictor.preprocess (engine/predictor.py:132-135).
+ * in      : NCHW [B,3,H,W] fp32 (values already /255, as LoadTensor supplies, data/loaders.py:516-584)
+ * weight  : fp32 [Cout][27] (cin-major: c*9 + ky*3 + kx), bias fp32 [Cout]; Cout % 8 == 0, <= 128
+ * out     : bf16 NHWC [B,H/2,W/2,Cout] slice with pixel stride out_ld
+ */
+int dy_stem_conv(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout,
+                 void* out, int out_ld, void* stream);
+
+/* SPPF pooling: y1=mp5(x), y2=mp5(y1), y3=mp5(y2) (5x5, stride 1, pad 2, -inf padding) in one pass.
+ * Replaces: SPPF.forward's three chained MaxPool2d + cat  nn/modules/block.py:185-191.
+ * buf     : bf16 NHWC [B,H,W,ld]; reads channels [0,C), writes [C,2C), [2C,3C), [3C,4C).
+ */
+int dy_sppf_pool(void* buf, int B, int H, int W, int C, int ld, void* stream);
+
+/* 2x nearest upsample into a channel slice of a concat buffer.
+ * Replaces: nn.Upsample(None,2,'nearest') + Concat  (yaml :30-31; conv.py:331-333).
+ */
+int dy_upsample2x(const void* in, int in_ld, int B, int H, int W, int C, void* out, int out_ld, void* stream);
+
+/* Depthwise-style grouped conv of the "-sf" graph: 3x3 stride 2, groups = Cout, Cin = 2*Cout.
+ * Replaces: DWConv(c1,c2,3,2) nn/modules/conv.py:102-107 (g = gcd(c1,c2)) of
+ *           cfg/models/v8/yolov8-p2-repvgg-sf.yaml:32,38,44.  weight fp32 [Cout][2][9], bias fp32 [Cout].
+ */
+int dy_dwconv3x3s2(const void* in, int in_ld, int B, int H, int W, int Cin, const float* weight,
+                   const float* bias, int Cout, void* out, int out_ld, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Detect decode: DFL softmax-expectation + dist2bbox(xywh) + stride scaling + class sigmoid.
+ * Replaces: Detect._inference  nn/modules/head.py:100-131, DFL.forward block.py:73-76,
+ *           make_anchors utils/tal.py:333-345, dist2bbox utils/tal.py:348-357.
+ * lvl[l]  : raw head map of level l, `no = 64 + nc` channels (box side*16+bin first, then classes):
+ *           DY_NHWC: [B,H_l,W_l,ld[l]] (bf16 or fp32);  DY_NCHW: [B,no,H_l,W_l] (ld ignored)
+ * out     : fp32 [B, 4+nc, A], A = sum H_l*W_l, rows cx,cy,w,h (input pixels), p_0..p_{nc-1};
+ *           anchors level-major, row-major (y,x) inside a level — the reference's order.
+ */
+typedef struct dy_decode_desc {
+  const void* lvl[4]; int32_t ld[4]; int32_t H[4]; int32_t W[4]; float stride[4];
+  int32_t nl, B, nc, dtype /* dy_dtype */, layout /* dy_layout */;
+  float* out;
+} dy_decode_desc;
+
+int dy_detect_decode(const dy_decode_desc* d, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Batched NMS.  Replaces: ops.non_max_suppression  utils/ops.py:181-332 (confidence filter :250,
+ * xywh2xyxy :259-260/:432-449, best-class / multi-label candidates :284-291, class filter :294-295,
+ * max_nms truncation :301-302, class-offset boxes :305-311) and torchvision.ops.nms (:312),
+ * [:max_det] (:313) and the row gather (:327).
+ * pred    : fp32 [B, 4+nc, A]  rows cx,cy,w,h,p_0..p_{nc-1}
+ * out     : fp32 [B, max_det, 6] rows x1,y1,x2,y2,conf,cls (only the first counts[b] rows are written)
+ * counts  : int32 [B]
+ * kept    : optional int64 [B, max_det]: index of each kept box in the reference's compacted candidate
+ *           list `x` (ops.py:269-302) i.e. what torchvision.ops.nms returned; NULL to skip
+ * classes_host : optional HOST int32 [n_classes] class filter (ops.py:294-295) or NULL
+ * workspace: device scratch of dy_nms_workspace_bytes(B, nc, A, multi_label) bytes (16B aligned)
+ * Ties: equal scores keep the lower candidate index first (stable order), also in the max_nms cut.
+ */
+typedef struct dy_nms_desc {
+  const float* pred; int32_t B, nc, A;
+  float conf_thres;          /* compared in fp32, as torch compares a float32 tensor with a Python scalar */
+  double iou_thres;          /* torchvision's CPU kernel compares the fp32 IoU against this double        */
+  int32_t max_det, max_nms; float max_wh;
+  int32_t agnostic, multi_label;
+  const int32_t* classes_host; int32_t n_classes;   /* HOST array (ops.py:294-295) or NULL              */
+  int32_t xyxy_in_place;     /* 1: also overwrite pred rows 0..3 with x1,y1,x2,y2 (ops.py:259-260) */
+  float* out; int32_t* counts; int64_t* kept;
+  void* workspace; size_t workspace_bytes;
+} dy_nms_desc;
+
+size_t dy_nms_workspace_bytes(int B, int nc, int A, int multi_label);
+int dy_nms(const dy_nms_desc* d, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Program: a recorded sequence of the ops above with tensor maps encoded once, replayed per batch.
+ * Replaces: the Python layer loop BaseModel._predict_once  nn/tasks.py:134-161 for a fixed
+ *           (batch, H, W).  `dy_program_run` only enqueues kernels (capturable in a CUDA graph).
+ */
+typedef struct dy_program dy_program;
+int dy_program_create(dy_program** out);
+void dy_program_destroy(dy_program* p);
+int dy_program_add_conv(dy_program* p, const dy_conv_desc* d);
+int dy_program_add_stem(dy_program* p, const float* in, int B, int H, int W, const float* weight,
+                        const float* bias, int Cout, void* out, int out_ld);
+int dy_program_add_sppf_pool(dy_program* p, void* buf, int B, int H, int W, int C, int ld);
+int dy_program_add_upsample2x(dy_program* p, const void* in, int in_ld, int B, int H, int W, int C,
+                              void* out, int out_ld);
+int dy_program_add_dwconv3x3s2(dy_program* p, const void* in, int in_ld, int B, int H, int W, int Cin,
+                               const float* weight, const float* bias, int Cout, void* out, int out_ld);
+int dy_program_add_decode(dy_program* p, const dy_decode_desc* d);
+int dy_program_add_nms(dy_program* p, const dy_nms_desc* d);
+/* in_offset_bytes / out_offset_bytes are added to the stem input pointer and to the decode output
+ * pointer: the same program serves successive micro-batches of one large resident batch. */
+int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream);
+int dy_program_num_launches(const dy_program* p);   /* kernels enqueued by one dy_program_run */
+
+/* Self-test of the tcgen05 / TMA descriptor encodings (one 128xN tile), used by tests and smoke. */
+int dy_selftest_umma(int N, int K, float* max_abs_err_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DRONEYOLO_H_ */

@@ -1,0 +1,110 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors produced by the real reference (tools/make_golden.py),
+and the host-side model construction against the reference's state_dict digest."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_np, nms_np, recipe, torch_ref
+
+NMS_CASES = {
+    "default": dict(conf_thres=0.001, iou_thres=0.7, max_det=300),
+    "multilabel": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, multi_label=True),
+    "agnostic": dict(conf_thres=0.001, iou_thres=0.5, max_det=100, agnostic=True),
+    "classes": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, classes=[1, 3, 7]),
+    "maxnms": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=200),
+    "predict": dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+}
+REGIMES = ("sparse", "vallike", "dense")
+CONV_FIXTURES = ("n_repvgg_128", "n_repvgg_sf_64", "n_p2_64", "s_repvgg_64")
+
+
+def build_model(g):
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(int(g["model_seed"]))
+    m = DetectionModel(str(g["yaml"]), nc=int(g["nc"]), verbose=False)
+    recipe.apply_recipe(m, int(g["bn_seed"]), float(g["cls_delta"]))
+    return m.eval()
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+def test_decode_oracle_matches_reference(golden_dir, regime):
+    g = np.load(golden_dir / f"decode_nms_{regime}.npz")
+    raw = recipe.synthetic_raw_maps(int(g["B"]), int(g["imgsz"]), int(g["nc"]), float(g["mu"]), int(g["raw_seed"]))
+    y = decode_np.decode([r.numpy() for r in raw], [4.0, 8.0, 16.0, 32.0], int(g["nc"]))
+    assert y.shape == g["y"].shape
+    # boxes in pixels, probabilities in [0,1]: the numpy restatement tracks the reference's aten ops to float rounding
+    np.testing.assert_allclose(y[:, :4], g["y"][:, :4], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(y[:, 4:], g["y"][:, 4:], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+@pytest.mark.parametrize("case", sorted(NMS_CASES))
+def test_nms_oracle_bit_exact_vs_reference(golden_dir, regime, case):
+    g = np.load(golden_dir / f"decode_nms_{regime}.npz")
+    out, kept = nms_np.non_max_suppression(g["y"], return_kept=True, **NMS_CASES[case])
+    for b in range(int(g["B"])):
+        ref_rows, ref_kept = g[f"{case}_out{b}"], g[f"{case}_kept{b}"]
+        assert out[b].shape == ref_rows.shape, (regime, case, b)
+        assert np.array_equal(out[b].view(np.uint32), ref_rows.view(np.uint32)), (regime, case, b)   # bit-exact rows
+        assert np.array_equal(kept[b], ref_kept), (regime, case, b)                                   # and kept indices
+
+
+def test_nms_restatement_equals_installed_torchvision(golden_dir):
+    import torchvision
+
+    g = np.load(golden_dir / "decode_nms_vallike.npz")
+
+    def tv(boxes, scores, thr):
+        return torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
+
+    a = nms_np.non_max_suppression(g["y"], conf_thres=0.001, iou_thres=0.7, return_kept=True)
+    b = nms_np.non_max_suppression(g["y"], conf_thres=0.001, iou_thres=0.7, return_kept=True, nms_fn=tv)
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x, y)
+
+
+def test_nms_tie_and_threshold_rules():
+    # identical boxes, tied scores: the lower index survives; IoU == thr is NOT suppressed (strict >)
+    boxes = np.array([[0, 0, 10, 10], [0, 0, 10, 10], [0, 0, 10, 7]], np.float32)
+    scores = np.array([0.5, 0.5, 0.4], np.float32)
+    assert nms_np.nms_greedy(boxes, scores, 0.7).tolist() == [0, 2]      # IoU(0,2) = 0.7 exactly -> kept
+    assert nms_np.nms_greedy(boxes, scores, 0.69).tolist() == [0]
+    assert nms_np.nms_greedy(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5).size == 0
+
+
+@pytest.mark.parametrize("tag", CONV_FIXTURES)
+def test_seeded_construction_matches_reference_state(golden_dir, tag):
+    g = np.load(golden_dir / f"convstack_{tag}.npz")
+    m = build_model(g)
+    assert len(m.state_dict()) == int(g["n_keys"])
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"])
+    assert np.array_equal(m.stride.numpy(), g["stride"])
+    assert recipe.state_digest(m) == str(g["state_digest"])
+
+
+@pytest.mark.parametrize("tag", CONV_FIXTURES)
+def test_convstack_oracle_matches_reference(golden_dir, tag):
+    g = np.load(golden_dir / f"convstack_{tag}.npz")
+    m = build_model(g)
+    x = recipe.images(int(g["B"]), int(g["imgsz"]), int(g["imgsz"]), int(g["image_seed"]))
+    y, raw = torch_ref.forward(m, x)
+    for i, r in enumerate(raw):
+        np.testing.assert_allclose(r.numpy(), g[f"raw{i}"].astype(np.float32), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(y[:, :4], g["y"][:, :4], rtol=0, atol=1e-2)
+    np.testing.assert_allclose(y[:, 4:], g["y"][:, 4:], rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ("n_repvgg_128", "n_repvgg_sf_64"))
+def test_fuse_reparameterisation_is_exact_enough(golden_dir, tag):
+    """fuse() (BN fold + RepVGG merge) must not change the oracle's outputs beyond fp32 noise."""
+    g = np.load(golden_dir / f"convstack_{tag}.npz")
+    m = build_model(g)
+    x = recipe.images(int(g["B"]), int(g["imgsz"]), int(g["imgsz"]), int(g["image_seed"]))
+    y0, raw0 = torch_ref.forward(m, x)
+    m.fuse(verbose=False)
+    assert m.is_fused() and not any(isinstance(k, torch.nn.BatchNorm2d) for k in m.modules())
+    y1, raw1 = torch_ref.forward(m, x)
+    for a, b in zip(raw0, raw1):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose(y0[:, :4], y1[:, :4], atol=2e-2)
