@@ -30,6 +30,7 @@ static constexpr int kABytes = kBlockM * 128; // one A stage
 static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 256;
 static constexpr int kTmemCols = 512;
+static constexpr int kMaxDynSmem = 227 * 1024 - 1024;
 static constexpr int kAccStride = 256;        // TMEM column offset between the two accumulator stages
 
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
@@ -363,7 +364,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   }
 
   const int stage_bytes = kABytes + p->BN * 128;
-  int stages = (227 * 1024 - 2048) / stage_bytes;
+  int stages = (kMaxDynSmem - 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p->stages = stages;
@@ -377,8 +378,9 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
 int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   static int max_smem_set = 0;
   if (max_smem_set < l->smem_bytes) {
-    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    max_smem_set = 227 * 1024;
+    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 1 KB
+    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    max_smem_set = kMaxDynSmem;
   }
   conv_igemm_kernel<<<l->grid, kThreads, l->smem_bytes, stream>>>(*p);
   return launch_status("conv_igemm_kernel");

@@ -1,0 +1,296 @@
+"""Layer plan: compile a DetectionModel into a recorded dy_program for a fixed (micro-batch, H, W).
+
+Replaces the reference's Python layer loop `BaseModel._predict_once` (ultralytics/nn/tasks.py:134-161) and the
+chunk/cat/upsample copies around it:
+  * every Concat (conv.py:331-333), C2f's chunk+cat (block.py:240-242) and SPPF's cat (block.py:191) disappear:
+    producers write straight into channel slices of one NHWC buffer;
+  * Detect's two first 3x3 convs per level run as one GEMM (N = c2 + c3);
+  * activations live in one arena with lifetime-based reuse, sized for a MICRO-batch so that a layer's output is
+    still in the 126 MB L2 when the next layer reads it; the program is replayed per micro-batch over the resident
+    batch (stem input / decode output pointers are offset per replay);
+  * the whole step (all replays + NMS) is captured in one CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _C
+from .. import kernels as K
+from ..nn.modules import C2f, Concat, Conv, Detect, DWConv, RepConv, RepVGGBlock, SPPF
+from ..nn.tasks import Upsample
+
+Ref = namedtuple("Ref", "buf c0 c H W")     # channel slice [c0, c0+c) of buffer `buf` at resolution HxW
+
+
+class _Buf:
+    __slots__ = ("C", "H", "W", "esz", "first", "last", "offset", "nbytes", "pinned")
+
+    def __init__(self, Cc, H, W, esz, first):
+        self.C, self.H, self.W, self.esz, self.first, self.last = Cc, H, W, esz, first, first
+        self.offset, self.nbytes, self.pinned = -1, 0, False
+
+
+class LayerPlan:
+    """Symbolic pass -> arena assignment -> dy_program."""
+
+    def __init__(self, model, mb: int, H: int, W: int, device, images: torch.Tensor, y: torch.Tensor):
+        if H % 32 or W % 32:
+            raise _C.DroneYoloError(f"input {H}x{W} must be a multiple of the maximum stride 32")
+        self.model, self.mb, self.H, self.W, self.device = model, mb, H, W, device
+        self.bufs: list[_Buf] = []
+        self.ops: list[dict] = []
+        self.keep = []                      # packed weights etc. that must outlive the program
+        self._build_symbolic()
+        self._assign_arena()
+        self._emit(images, y)
+
+    # ---------------------------------------------------------------------------------------------
+    def _new_buf(self, Cc, H, W, esz=2):
+        self.bufs.append(_Buf(Cc, H, W, esz, len(self.ops)))
+        return len(self.bufs) - 1
+
+    def _touch(self, *refs):
+        t = len(self.ops)
+        for r in refs:
+            if r is not None:
+                self.bufs[r.buf].last = max(self.bufs[r.buf].last, t)
+
+    def _op(self, **kw):
+        self._touch(kw.get("inp"), kw.get("out"), kw.get("res"))
+        for r in kw.get("levels", ()):
+            self._touch(r)
+        self.ops.append(kw)
+
+    def _build_symbolic(self):
+        layers = list(self.model.model)
+        n = len(layers)
+        # homes: a layer output that feeds a Concat is produced directly inside that Concat's buffer
+        home: dict[int, tuple[int, int]] = {}          # producer layer index -> (concat layer index, channel offset)
+        cat_ch: dict[int, int] = {}
+        out_ch: list[int] = []
+        for i, m in enumerate(layers):
+            if isinstance(m, Concat):
+                srcs = [(j if j >= 0 else i + j) for j in m.f]
+                c0 = 0
+                for j in srcs:
+                    if j in home or isinstance(layers[j], Concat):
+                        raise _C.DroneYoloError(f"layer {j} feeds two Concats: plan would need a copy op (not in Drone-YOLO graphs)")
+                    home[j] = (i, c0)
+                    c0 += out_ch[j]
+                cat_ch[i] = c0
+                out_ch.append(c0)
+            elif isinstance(m, Detect):
+                out_ch.append(0)
+            elif isinstance(m, Upsample):
+                out_ch.append(out_ch[i - 1 if m.f == -1 else m.f])
+            else:
+                out_ch.append(self._module_cout(m))
+        self.layer_ref: list[Optional[Ref]] = [None] * n
+        cat_buf: dict[int, int] = {}
+        res = {"H": self.H, "W": self.W}
+
+        def dest(i, c, H, W):
+            """Where layer i writes its output."""
+            if i in home:
+                ci, c0 = home[i]
+                if ci not in cat_buf:
+                    cat_buf[ci] = self._new_buf(cat_ch[ci], H, W)
+                b = self.bufs[cat_buf[ci]]
+                if (b.H, b.W) != (H, W):
+                    raise _C.DroneYoloError(f"Concat {ci}: resolution mismatch")
+                return Ref(cat_buf[ci], c0, c, H, W)
+            return Ref(self._new_buf(c, H, W), 0, c, H, W)
+
+        for i, m in enumerate(layers):
+            f = m.f
+            src = None
+            if isinstance(f, int):
+                src = self.layer_ref[i - 1 if f == -1 else f] if i > 0 else None
+            if isinstance(m, Conv) and m.is_stem:
+                Ho, Wo = self.H // 2, self.W // 2
+                out = dest(i, m.conv.out_channels, Ho, Wo)
+                self._op(kind="stem", mod=m, out=out)
+            elif isinstance(m, DWConv):
+                out = dest(i, m.conv.out_channels, src.H // 2, src.W // 2)
+                self._op(kind="dwconv", mod=m, inp=src, out=out)
+            elif isinstance(m, (Conv, RepVGGBlock, RepConv)):
+                cout, k, s = self._conv_geom(m)
+                out = dest(i, cout, src.H // s, src.W // s)
+                self._op(kind="conv", mod=m, inp=src, out=out)
+            elif isinstance(m, C2f):
+                out = dest(i, m.cv2.conv.out_channels, src.H, src.W)
+                self._emit_c2f(m, src, out)
+            elif isinstance(m, SPPF):
+                out = dest(i, m.cv2.conv.out_channels, src.H, src.W)
+                c_ = m.cv1.conv.out_channels
+                cat = self._new_buf(4 * c_, src.H, src.W)
+                self._op(kind="conv", mod=m.cv1, inp=src, out=Ref(cat, 0, c_, src.H, src.W))
+                self._op(kind="pool", inp=Ref(cat, 0, 4 * c_, src.H, src.W), c=c_)
+                self._op(kind="conv", mod=m.cv2, inp=Ref(cat, 0, 4 * c_, src.H, src.W), out=out)
+            elif isinstance(m, Upsample):
+                out = dest(i, src.c, src.H * 2, src.W * 2)
+                self._op(kind="upsample", inp=src, out=out)
+            elif isinstance(m, Concat):
+                b = self.bufs[cat_buf[i]]
+                out = Ref(cat_buf[i], 0, b.C, b.H, b.W)
+            elif isinstance(m, Detect):
+                srcs = [self.layer_ref[j] for j in f]
+                self._emit_detect(m, srcs)
+                out = None
+            else:
+                raise _C.DroneYoloError(f"layer {i}: {type(m).__name__} has no plan lowering")
+            self.layer_ref[i] = out
+        del res
+
+    @staticmethod
+    def _module_cout(m):
+        if isinstance(m, (Conv, DWConv)):
+            return m.conv.out_channels
+        if isinstance(m, (RepVGGBlock, RepConv)):
+            return m._geom()[0]
+        if isinstance(m, (C2f, SPPF)):
+            return m.cv2.conv.out_channels
+        raise _C.DroneYoloError(f"{type(m).__name__}: unknown output width")
+
+    @staticmethod
+    def _conv_geom(m):
+        if isinstance(m, Conv):
+            return m.conv.out_channels, m.conv.kernel_size[0], m.conv.stride[0]
+        cout, s = m._geom()
+        return cout, 3, s
+
+    def _emit_c2f(self, m: C2f, src: Ref, out: Ref):
+        c, n = m.c, len(m.m)
+        H, W = src.H, src.W
+        cat = self._new_buf((2 + n) * c, H, W)
+        self._op(kind="conv", mod=m.cv1, inp=src, out=Ref(cat, 0, 2 * c, H, W))
+        for i, b in enumerate(m.m):
+            xin = Ref(cat, (1 + i) * c, c, H, W)
+            tmp = Ref(self._new_buf(b.cv1.conv.out_channels, H, W), 0, b.cv1.conv.out_channels, H, W)
+            self._op(kind="conv", mod=b.cv1, inp=xin, out=tmp)
+            self._op(kind="conv", mod=b.cv2, inp=tmp, out=Ref(cat, (2 + i) * c, c, H, W), res=xin if b.add else None)
+        self._op(kind="conv", mod=m.cv2, inp=Ref(cat, 0, (2 + n) * c, H, W), out=out)
+
+    def _emit_detect(self, m: Detect, srcs):
+        packed = m.packed()
+        levels = []
+        for i, src in enumerate(srcs):
+            H, W = src.H, src.W
+            c2, c3 = m.cv2[i][0].conv.out_channels, m.cv3[i][0].conv.out_channels
+            (wf, bf), (wbx, bbx), (wcl, bcl) = packed[i]
+            t1 = self._new_buf(c2 + c3, H, W)
+            t2 = self._new_buf(c2 + c3, H, W)
+            raw = self._new_buf(m.raw_ld, H, W, esz=4)
+            self._op(kind="conv", w=(wf, bf), cout=c2 + c3, k=3, s=1, act=True, inp=src, out=Ref(t1, 0, c2 + c3, H, W))
+            self._op(kind="conv", mod=m.cv2[i][1], inp=Ref(t1, 0, c2, H, W), out=Ref(t2, 0, c2, H, W))
+            self._op(kind="conv", mod=m.cv3[i][1], inp=Ref(t1, c2, c3, H, W), out=Ref(t2, c2, c3, H, W))
+            self._op(kind="conv", w=(wbx, bbx), cout=4 * m.reg_max, k=1, s=1, act=False, inp=Ref(t2, 0, c2, H, W),
+                     out=Ref(raw, 0, 4 * m.reg_max, H, W))
+            self._op(kind="conv", w=(wcl, bcl), cout=m.nc, k=1, s=1, act=False, inp=Ref(t2, c2, c3, H, W),
+                     out=Ref(raw, 4 * m.reg_max, m.nc, H, W))
+            levels.append(Ref(raw, 0, m.no, H, W))
+        self._op(kind="decode", levels=levels, det=m)
+        self.raw_refs = levels
+
+    # ---------------------------------------------------------------------------------------------
+    def _assign_arena(self):
+        """First-fit offsets with lifetime reuse (buffers are free after their last reader)."""
+        live: list[tuple[int, int, int]] = []      # (offset, nbytes, last)
+        total = 0
+        order = sorted(range(len(self.bufs)), key=lambda i: self.bufs[i].first)
+        for bi in order:
+            b = self.bufs[bi]
+            b.nbytes = (self.mb * b.H * b.W * b.C * b.esz + 1023) // 1024 * 1024
+            live = [x for x in live if x[2] >= b.first]
+            live.sort()
+            off = 0
+            for o, nb, _ in live:
+                if off + b.nbytes <= o:
+                    break
+                off = max(off, o + nb)
+            b.offset = off
+            live.append((off, b.nbytes, b.last))
+            total = max(total, off + b.nbytes)
+        self.arena_bytes = total
+        self.arena = torch.empty((max(total, 1024),), device=self.device, dtype=torch.uint8)
+
+    def tensor(self, r: Ref) -> torch.Tensor:
+        """(mb, c, H, W) channels-last view of a Ref inside the arena."""
+        b = self.bufs[r.buf]
+        dt = torch.float32 if b.esz == 4 else torch.bfloat16
+        flat = self.arena[b.offset: b.offset + self.mb * b.H * b.W * b.C * b.esz].view(dt)
+        return flat.view(self.mb, b.H, b.W, b.C).permute(0, 3, 1, 2)[:, r.c0: r.c0 + r.c]
+
+    # ---------------------------------------------------------------------------------------------
+    def _emit(self, images: torch.Tensor, y: torch.Tensor):
+        lib = _C.lib()
+        h = C.c_void_p()
+        _C.check(lib.dy_program_create(C.byref(h)), "dy_program_create")
+        self.handle = h
+        mb = self.mb
+        for op in self.ops:
+            kind = op["kind"]
+            if kind == "stem":
+                w, b = op["mod"].packed()
+                self.keep.append((w, b))
+                out = self.tensor(op["out"])
+                optr, old, *_ = K.nhwc_view(out)
+                _C.check(lib.dy_program_add_stem(h, images.data_ptr(), mb, self.H, self.W, w.data_ptr(), b.data_ptr(),
+                                                 w.shape[0], optr, old), "add_stem")
+            elif kind == "conv":
+                if "mod" in op:
+                    w, b = op["mod"].packed()
+                    cout, k, s = self._conv_geom(op["mod"])
+                    act = isinstance(getattr(op["mod"], "act", getattr(op["mod"], "nonlinearity", None)), nn.SiLU)
+                else:
+                    (w, b), cout, k, s, act = op["w"], op["cout"], op["k"], op["s"], op["act"]
+                self.keep.append((w, b))
+                res = self.tensor(op["res"]) if op.get("res") is not None else None
+                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, self.tensor(op["out"]), res)
+                _C.check(lib.dy_program_add_conv(h, C.byref(d)), "add_conv")
+            elif kind == "pool":
+                t = self.tensor(op["inp"])
+                p, ld, B, H, W, _ = K.nhwc_view(t)
+                _C.check(lib.dy_program_add_sppf_pool(h, p, B, H, W, op["c"], ld), "add_sppf_pool")
+            elif kind == "upsample":
+                ti, to = self.tensor(op["inp"]), self.tensor(op["out"])
+                ip, ild, B, H, W, Cc = K.nhwc_view(ti)
+                op_, old, *_ = K.nhwc_view(to)
+                _C.check(lib.dy_program_add_upsample2x(h, ip, ild, B, H, W, Cc, op_, old), "add_upsample2x")
+            elif kind == "dwconv":
+                w, b = op["mod"].packed()
+                w = w.reshape(w.shape[0], 18).contiguous()
+                self.keep.append((w, b))
+                ti, to = self.tensor(op["inp"]), self.tensor(op["out"])
+                ip, ild, B, H, W, Cin = K.nhwc_view(ti)
+                op_, old, *_ = K.nhwc_view(to)
+                _C.check(lib.dy_program_add_dwconv3x3s2(h, ip, ild, B, H, W, Cin, w.data_ptr(), b.data_ptr(), w.shape[0],
+                                                        op_, old), "add_dwconv")
+            elif kind == "decode":
+                det = op["det"]
+                levels = [self.tensor(r) for r in op["levels"]]
+                d = K.decode_desc(levels, [float(s) for s in det.stride.tolist()], det.nc, y)
+                d.B = mb
+                _C.check(lib.dy_program_add_decode(h, C.byref(d)), "add_decode")
+            else:
+                raise AssertionError(kind)
+        self.launches = lib.dy_program_num_launches(h)
+
+    def run(self, in_offset_bytes: int, out_offset_bytes: int, stream: int):
+        _C.check(_C.lib().dy_program_run(self.handle, in_offset_bytes, out_offset_bytes, stream), "dy_program_run")
+
+    def raw_maps(self):
+        """The raw head maps of the LAST replayed micro-batch, as the reference's (mb, no, H, W) views."""
+        return [self.tensor(r) for r in self.raw_refs]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _C.lib().dy_program_destroy(self.handle)
+        except Exception:  # noqa: BLE001
+            pass
