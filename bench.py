@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the Drone-YOLO inference hot path (conv stack + decode + NMS) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--scale s] [--imgsz 640] [--batch 64] [--micro-batch 0]
+
+One "step" = one pass of the hot path over one synthetic batch (`--batch` images PER GPU: weak scaling).
+Default workload = BASELINE.json configs[1]: Drone-YOLO-s, 640x640, batch 64, bf16 conv stack, 1xB200.
+Prints ONE JSON line (see the task contract): `value` is device-timed throughput with inputs resident in HBM,
+`e2e` includes the pinned-host -> device copy of every batch and the device -> host read of the detections.
+`--impl reference` times the CPU port of the reference path (oracle/, torch fp32 + numpy NMS) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GFLOP_PER_IMAGE_640 = {"n": 12.193, "s": 36.655, "l": 204.80, "x": 316.160, "m": 97.97}   # SURVEY.md §8(d), deploy form
+METRIC = "images/sec at 640px (conv+decode+NMS)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", default="s")
+    ap.add_argument("--imgsz", type=int, default=640)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--conf", type=float, default=0.001)
+    ap.add_argument("--iou", type=float, default=0.7)
+    ap.add_argument("--max-det", type=int, default=300)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a, n):
+    return (f"Drone-YOLO-{a.scale} {a.imgsz}x{a.imgsz} batch {a.batch} per GPU bf16 end-to-end inference "
+            f"(conv+decode+NMS) on {n}xB200, nc=10, conf {a.conf}, iou {a.iou}, max_det {a.max_det}")
+
+
+def build_model(scale):
+    import torch
+    from drone_yolo_b200.nn.tasks import DetectionModel
+    from oracle import recipe      # seeded test weights only (bench may use oracle/ for inputs + the CPU baseline)
+
+    torch.manual_seed(0)
+    m = DetectionModel(f"yolov8{scale}-p2-repvgg.yaml", nc=10, verbose=False)
+    recipe.apply_recipe(m)
+    return m.eval()
+
+
+def algorithmic_gflop(scale, imgsz):
+    return GFLOP_PER_IMAGE_640[scale] * (imgsz / 640.0) ** 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_port_images_per_sec(a, n_images, passes=1, threads=None):
+    """Time the CPU port of the reference path (oracle/torch_ref + decode_np + nms_np) on `n_images` synthetic images."""
+    import torch
+    from oracle import nms_np, recipe, torch_ref
+
+    if threads:
+        torch.set_num_threads(threads)
+    m = build_model(a.scale)
+    torch_ref.fuse_like_reference(m)              # Conv+BN folded, RepVGG left un-merged
+    x = recipe.images(n_images, a.imgsz, a.imgsz)
+    best = None
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        y, _ = torch_ref.forward(m, x)
+        t1 = time.perf_counter()
+        nms_np.non_max_suppression(y, conf_thres=a.conf, iou_thres=a.iou, max_det=a.max_det)
+        t2 = time.perf_counter()
+        dt = t2 - t0
+        if best is None or dt < best[0]:
+            best = (dt, t1 - t0, t2 - t1)
+    return n_images / best[0], best, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = max(1, a.cpu_sample)
+    for _ in range(max(0, min(a.warmup, 1))):
+        cpu_port_images_per_sec(a, 1)
+    t0 = time.perf_counter()
+    vals = []
+    steps = max(1, min(a.steps, 5))             # each step is a bounded sample; keep the whole run within minutes
+    for _ in range(steps):
+        v, _, _ = cpu_port_images_per_sec(a, n)
+        vals.append(v)
+        if time.perf_counter() - t0 > 150:
+            break
+    value = sum(vals) / len(vals)
+    sample = f"{n} images per step x {len(vals)} steps of the same workload, torch fp32 CPU conv stack + numpy decode/NMS"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": a.gpus, "steps": len(vals),
+        "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, a.gpus), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from drone_yolo_b200.engine.engine import Engine
+    from drone_yolo_b200.parallel import DetectionGather
+    from oracle import recipe
+
+    model = build_model(a.scale).to(dev).fuse(verbose=False)
+    eng = Engine(model, a.batch, a.imgsz, dev, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou, max_det=a.max_det,
+                 cuda_graph=not a.no_graph)
+    host = recipe.images(a.batch, a.imgsz, a.imgsz, seed=2 + rank).pin_memory()
+    eng.images.copy_(host)
+    gather = DetectionGather(a.batch, a.max_det, dev)
+    out_host = torch.empty((world * a.batch, a.max_det, 6), dtype=torch.float32).pin_memory()
+    cnt_host = torch.empty((world * a.batch,), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        out, counts = eng.step()
+        if world > 1:
+            gather.gather(out, counts)
+
+    def step_e2e():
+        eng.images.copy_(host, non_blocking=True)                 # H2D of this step's inputs (pinned)
+        out, counts = eng.step()
+        oa, ca = gather.gather(out, counts)
+        if rank == 0:                                             # D2H of the step's result
+            out_host.copy_(oa, non_blocking=True)
+            cnt_host.copy_(ca, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    # per-stage device times for the roofline: conv-stack plan alone, NMS alone (same buffers, separate graphs)
+    def graph_of(fn):
+        fn(); torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    g_plan = graph_of(lambda: eng.enqueue(nms=False))
+    from drone_yolo_b200 import _C
+    g_nms = graph_of(lambda: _C.check(_C.lib().dy_program_run(eng._nms_prog, 0, 0, _C.stream_ptr(dev)), "nms"))
+    for g in (g_plan, g_nms):
+        for _ in range(3):
+            g.replay()
+    ms_plan = timed(g_plan.replay, a.steps) / a.steps
+    ms_nms = timed(g_nms.replay, a.steps) / a.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback (B200_PROFILING.md)"
+
+    imgs = a.batch * world
+    ms_step = ms_total / a.steps
+    value = imgs / (ms_step / 1e3)
+    e2e_value = imgs / (ms_e2e / a.steps / 1e3)
+    gf = algorithmic_gflop(a.scale, a.imgsz)
+    conv_tflops = gf * a.batch / ms_plan                       # GFLOP / ms == TFLOP/s
+    nms_bytes = a.batch * (eng.A * (4 + eng.nc) * 4 + a.max_det * 24 + 4)
+    dec_bytes = a.batch * eng.A * (eng.model.model[-1].no * 4 + (4 + eng.nc) * 4)   # fp32 raw maps in this build
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a, world), "global_batch": imgs, "micro_batch": eng.mb, "parallelism": f"dp{world}",
+                   "cuda_graph": not a.no_graph, "weights": "random-init (seed 0) + seeded BN/cls-bias recipe",
+                   "l2": f"inputs larger than L2: {a.batch * 3 * a.imgsz * a.imgsz * 4 / 1e6:.0f} MB of images per step, "
+                         f"arena {eng.plan.arena_bytes / 1e6:.0f} MB per micro-batch"},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host.numel() * 4 * world,
+                "d2h_bytes_per_step": out_host.numel() * 4 + cnt_host.numel() * 4},
+        "gpu_launches": eng.launches_per_step * a.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv stack plan: stem + 78 tcgen05 convs + pool/upsample + decode)",
+                     "achieved": conv_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": conv_tflops / tf_peak,
+                     "traffic": None, "peak_source": peak_src, "ms_per_launch_group": ms_plan,
+                     "algorithmic_gflop_per_image": gf},
+        "stages": {"conv_stack_decode_ms": ms_plan, "nms_ms": ms_nms,
+                   "nms_hbm_gbs": nms_bytes / ms_nms / 1e6, "nms_frac_of_hbm": nms_bytes / ms_nms / 1e6 / hbm_peak,
+                   "decode_algorithmic_bytes": dec_bytes},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            v, (dt, t_conv, t_nms), cores = cpu_port_images_per_sec(a, a.cpu_sample, passes=2, threads=os.cpu_count())
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{a.cpu_sample} images of the same workload, best of 2 passes "
+                                              f"(conv+decode {t_conv:.2f}s, NMS {t_nms:.2f}s)"}
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

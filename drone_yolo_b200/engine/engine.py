@@ -1,0 +1,104 @@
+"""Engine: the device-side runtime of one (model, batch, H, W) configuration.
+
+Plays the role of the reference's AutoBackend (ultralytics/nn/autobackend.py:149-159,548-556: fuse, dtype, forward)
+plus DetectionPredictor.postprocess's NMS call (models/yolo/detect/predict.py:25-35) for the PyTorch branch only.
+Owns: the static input batch, the layer plan (engine/plan.py), the (B, 4+nc, A) prediction, the NMS buffers and
+one CUDA graph that replays [plan x micro-batches, NMS].
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from .. import _C
+from .. import kernels as K
+from .plan import LayerPlan
+
+
+def pick_micro_batch(model, batch: int, H: int, W: int, budget_mb: float = 48.0) -> int:
+    """Largest divisor of `batch` whose widest P2-level tensor pair (input + output of one conv) fits `budget_mb`:
+    keeps a layer's output L2-resident (126 MB) until its consumer runs."""
+    det = model.model[-1]
+    p2_ch = max(int(m.conv.in_channels) for m in (det.cv2[0][0], det.cv3[0][0]))
+    per_image = (H // 4) * (W // 4) * p2_ch * 3 * 2 * 2.0      # widest P2 concat is 3x the P2 width; in + out
+    best = 1
+    for d in range(1, batch + 1):
+        if batch % d == 0 and d * per_image <= budget_mb * 1e6:
+            best = d
+    return best
+
+
+class Engine:
+    def __init__(self, model, batch: int, imgsz, device, micro_batch: int = 0, conf: float = 0.25, iou: float = 0.7,
+                 max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
+                 max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+        _C.check(_C.lib().dy_device_check(device.index or 0), "dy_device_check")
+        H, W = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        self.model, self.device, self.batch, self.H, self.W = model, device, batch, H, W
+        det = model.model[-1]
+        self.nc = det.nc
+        self.A = sum((H // int(s)) * (W // int(s)) for s in det.stride.tolist())
+        self.mb = micro_batch if micro_batch and batch % micro_batch == 0 else pick_micro_batch(model, batch, H, W)
+        with torch.cuda.device(device):
+            self.images = torch.zeros((batch, 3, H, W), device=device, dtype=torch.float32)
+            self.y = torch.empty((batch, 4 + self.nc, self.A), device=device, dtype=torch.float32)
+            self.plan = LayerPlan(model, self.mb, H, W, device, self.images, self.y)
+            ml = bool(multi_label) and self.nc > 1
+            self.nms_bufs = K.NmsBuffers(batch, self.nc, self.A, max_det, ml, device)
+            self.nms_cfg = dict(conf=conf, iou=iou, max_det=max_det, classes=classes, agnostic=agnostic, multi_label=ml,
+                                max_nms=max_nms, max_wh=max_wh)
+            d = K.nms_desc(self.y, self.nms_bufs, conf, iou, max_det, max_nms, max_wh, agnostic, ml, classes,
+                           in_place=False, want_kept=True)
+            h = C.c_void_p()
+            _C.check(_C.lib().dy_program_create(C.byref(h)), "dy_program_create")
+            self._nms_prog = h
+            _C.check(_C.lib().dy_program_add_nms(h, C.byref(d)), "dy_program_add_nms")
+            self.launches_per_step = self.plan.launches * (batch // self.mb) + _C.lib().dy_program_num_launches(h)
+            self.graph: Optional[torch.cuda.CUDAGraph] = None
+            self.enqueue()                       # eager warm-up (sets kernel attributes, pages in code)
+            torch.cuda.synchronize(device)
+            if cuda_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.enqueue()
+                self.graph = g
+
+    def enqueue(self, stream: Optional[int] = None, nms: bool = True):
+        """Enqueue the whole step on `stream` (default: torch's current stream)."""
+        s = _C.stream_ptr(self.device) if stream is None else stream
+        in_bytes = self.mb * 3 * self.H * self.W * 4
+        out_bytes = self.mb * (4 + self.nc) * self.A * 4
+        for m in range(self.batch // self.mb):
+            self.plan.run(m * in_bytes, m * out_bytes, s)
+        if nms:
+            _C.check(_C.lib().dy_program_run(self._nms_prog, 0, 0, s), "dy_program_run(nms)")
+
+    def step(self):
+        """Run conv stack + decode + NMS on the resident `images`; results in y / nms_bufs (no host sync)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.enqueue()
+        return self.nms_bufs.out, self.nms_bufs.counts
+
+    def __call__(self, images: Optional[torch.Tensor] = None):
+        if images is not None:
+            if images.shape != self.images.shape:
+                raise _C.DroneYoloError(f"engine built for {tuple(self.images.shape)}, got {tuple(images.shape)}")
+            self.images.copy_(images, non_blocking=True)
+        return self.step()
+
+    def raw_maps(self):
+        return self.plan.raw_maps()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_nms_prog", None):
+                _C.lib().dy_program_destroy(self._nms_prog)
+        except Exception:  # noqa: BLE001
+            pass

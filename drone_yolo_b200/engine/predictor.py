@@ -1,0 +1,224 @@
+"""DetectionPredictor: source -> preprocess -> Engine (conv stack + decode + NMS) -> Results.
+
+Mirror of the reference's BasePredictor / DetectionPredictor (ultralytics/engine/predictor.py:66-410,
+models/yolo/detect/predict.py:23-73) for the inference hot path: same constructor (`overrides`, `_callbacks`),
+`setup_model`, `__call__(source, stream)`, `preprocess`, `inference`, `postprocess`, the five `on_predict_*`
+callback events and `Results.speed`.  Differences: one batched D2H of the padded detections instead of per-image
+boolean-mask syncs; `orig_img` of tensor sources is produced lazily; boxes are rescaled on the host (<= max_det rows).
+"""
+from __future__ import annotations
+
+import threading
+import time
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import _C
+from ..utils import ops
+from .engine import Engine
+from .results import Results
+
+DEFAULTS = dict(task="detect", mode="predict", imgsz=640, batch=1, device=None, conf=0.25, iou=0.7, max_det=300,
+                half=False, classes=None, agnostic_nms=False, augment=False, stream=False, verbose=False,
+                micro_batch=0, cuda_graph=True, multi_label=False)
+EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end", "on_predict_end")
+
+
+def letterbox(im: np.ndarray, new_shape, stride=32, auto=False, color=(114, 114, 114)):
+    """Resize + pad to `new_shape` keeping the aspect ratio (reference data/augment.py:1544-1610, centre padding)."""
+    import cv2
+
+    shape = im.shape[:2]
+    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+    new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+    dw /= 2
+    dh /= 2
+    if shape[::-1] != new_unpad:
+        im = cv2.resize(im, new_unpad, interpolation=cv2.INTER_LINEAR)
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return cv2.copyMakeBorder(im, top, bottom, left, right, cv2.BORDER_CONSTANT, value=color)
+
+
+class DetectionPredictor:
+    def __init__(self, cfg=None, overrides=None, _callbacks=None):
+        args = dict(DEFAULTS)
+        args.update(cfg or {})
+        args.update(overrides or {})
+        if args.get("conf") is None:
+            args["conf"] = 0.25
+        if args.get("augment"):
+            raise _C.DroneYoloError("augment=True (TTA) is outside the inference hot path")
+        self.args = SimpleNamespace(**args)
+        self.model = None
+        self.device = None
+        self.engines: dict = {}
+        self.callbacks = {e: [] for e in EVENTS}
+        for k, v in (_callbacks or {}).items():
+            self.callbacks.setdefault(k, []).extend(v if isinstance(v, (list, tuple)) else [v])
+        self.results = None
+        self.batch = None
+        self.save_dir = None
+        self.seen = 0
+        self._lock = threading.Lock()
+        self._pinned: dict = {}
+
+    # ---- setup ---------------------------------------------------------------------------------
+    def setup_model(self, model, verbose=False):
+        """Move to the device, fold BN + re-parameterise (AutoBackend: autobackend.py:149-159)."""
+        dev = self.args.device
+        if dev is None or dev == "":
+            dev = "cuda:0"
+        if isinstance(dev, int) or (isinstance(dev, str) and dev.isdigit()):
+            dev = f"cuda:{dev}"
+        self.device = torch.device(dev)
+        if self.device.type != "cuda":
+            raise _C.DroneYoloError(f"device '{dev}': drone_yolo_b200 has no CPU path (use the reference for CPU inference)")
+        self.model = model.to(self.device).eval().fuse(verbose=False)
+        self.engines.clear()
+
+    def add_callback(self, event, func):
+        self.callbacks[event].append(func)
+
+    def run_callbacks(self, event):
+        for cb in self.callbacks.get(event, []):
+            cb(self)
+
+    def engine_for(self, B, H, W) -> Engine:
+        a = self.args
+        key = (B, H, W, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes else None, a.agnostic_nms, a.multi_label,
+               a.micro_batch, a.cuda_graph)
+        if key not in self.engines:
+            if len(self.engines) >= 4:
+                self.engines.clear()
+            self.engines[key] = Engine(self.model, B, (H, W), self.device, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou,
+                                       max_det=a.max_det, classes=a.classes, agnostic=a.agnostic_nms,
+                                       multi_label=a.multi_label, cuda_graph=a.cuda_graph)
+        return self.engines[key]
+
+    # ---- source handling (reference data/build.py:186-219, data/loaders.py) ---------------------
+    def _batches(self, source):
+        """Yield (paths, im0s, tensor_or_None): a Tensor source is ONE batch (loaders.py:575-580); a list / ndarray /
+        path source is grouped by args.batch."""
+        if isinstance(source, torch.Tensor):
+            im = source[None] if source.dim() == 3 else source
+            if im.shape[2] % 32 or im.shape[3] % 32:
+                raise ValueError(f"tensor source {tuple(im.shape)} must have H, W divisible by stride 32 (loaders.py:559)")
+            if im.dtype.is_floating_point and im.numel() and float(im.max()) > 1.0 + 1e-5:
+                print("WARNING: torch.Tensor inputs should be normalized 0.0-1.0; dividing by 255 (loaders.py:565-571)")
+                im = im.float() / 255.0
+            yield [f"image{i}.jpg" for i in range(im.shape[0])], None, im
+            return
+        items = source if isinstance(source, (list, tuple)) else [source]
+        imgs, paths = [], []
+        for i, s in enumerate(items):
+            if isinstance(s, (str, Path)):
+                import cv2
+
+                im = cv2.imread(str(s))
+                if im is None:
+                    raise FileNotFoundError(f"image not found or unreadable: {s}")
+                imgs.append(im)
+                paths.append(str(s))
+            elif isinstance(s, np.ndarray):
+                imgs.append(s)
+                paths.append(f"image{i}.jpg")
+            else:  # PIL
+                imgs.append(np.asarray(s)[:, :, ::-1] if np.asarray(s).ndim == 3 else np.asarray(s))
+                paths.append(getattr(s, "filename", "") or f"image{i}.jpg")
+        bs = len(imgs) if not isinstance(items[0], (str, Path)) else max(int(self.args.batch), 1)
+        for i in range(0, len(imgs), bs):
+            yield paths[i:i + bs], imgs[i:i + bs], None
+
+    def preprocess(self, im0s):
+        """uint8 HWC BGR list -> pinned float32 (B,3,H,W) RGB in [0,1] (predictor.py:118-136, 147-163)."""
+        a = self.args
+        shape = (a.imgsz, a.imgsz) if isinstance(a.imgsz, int) else tuple(a.imgsz)
+        same = len({x.shape for x in im0s}) == 1
+        lb = [letterbox(x, shape, auto=same) for x in im0s]
+        arr = np.ascontiguousarray(np.stack(lb)[..., ::-1].transpose(0, 3, 1, 2))
+        key = arr.shape
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(key, dtype=torch.float32).pin_memory()
+        buf = self._pinned[key]
+        torch.div(torch.from_numpy(arr), 255.0, out=buf)
+        return buf
+
+    # ---- the loop --------------------------------------------------------------------------------
+    def __call__(self, source=None, model=None, stream=False):
+        gen = self.stream_inference(source, model)
+        return gen if stream else list(gen)
+
+    def stream_inference(self, source=None, model=None):
+        if self.model is None:
+            self.setup_model(model)
+        with self._lock, torch.inference_mode():
+            self.run_callbacks("on_predict_start")
+            for paths, im0s, tensor in self._batches(source):
+                self.run_callbacks("on_predict_batch_start")
+                self.batch = (paths, im0s, None)
+                t0 = time.perf_counter()
+                im = tensor if tensor is not None else self.preprocess(im0s)
+                B, _, H, W = im.shape
+                eng = self.engine_for(B, H, W)
+                eng.images.copy_(im, non_blocking=True)            # H2D (or D2D) into the static input
+                torch.cuda.synchronize(self.device)
+                t1 = time.perf_counter()
+                out, counts = self.inference(eng)
+                torch.cuda.synchronize(self.device)
+                t2 = time.perf_counter()
+                self.results = self.postprocess((out, counts), im, im0s if im0s is not None else tensor, paths)
+                t3 = time.perf_counter()
+                self.run_callbacks("on_predict_postprocess_end")
+                n = len(self.results)
+                speed = {"preprocess": (t1 - t0) * 1e3 / n, "inference": (t2 - t1) * 1e3 / n, "postprocess": (t3 - t2) * 1e3 / n}
+                for r in self.results:
+                    r.speed = speed
+                self.seen += n
+                if self.args.verbose:
+                    for p, r in zip(paths, self.results):
+                        print(f"{p}: {H}x{W} {r.verbose()}{speed['inference']:.2f}ms")
+                self.run_callbacks("on_predict_batch_end")
+                yield from self.results
+            self.run_callbacks("on_predict_end")
+
+    def inference(self, eng: Engine):
+        """conv stack + decode + NMS, one CUDA-graph replay (predictor.py:138-145 + detect/predict.py:25-35)."""
+        return eng.step()
+
+    def postprocess(self, preds, img, orig_imgs, paths):
+        """Padded detections -> Results; boxes rescaled to the original image (detect/predict.py:37-73)."""
+        out, counts = preds
+        k = int(self.args.max_det)
+        host = torch.empty((out.shape[0], k * 6 + 1), dtype=torch.float32)
+        host[:, : k * 6] = out.reshape(out.shape[0], -1).cpu()     # one D2H of (B, max_det, 6)
+        n = counts.cpu().tolist()
+        names = self.model.names
+        results = []
+        in_shape = tuple(img.shape[2:])
+        for i in range(out.shape[0]):
+            rows = host[i, : n[i] * 6].reshape(n[i], 6).clone()
+            if isinstance(orig_imgs, torch.Tensor):
+                src = orig_imgs
+                oshape = in_shape
+
+                def lazy(j=i, t=src):
+                    return ops.convert_torch2numpy_batch(t[j:j + 1])[0]
+
+                orig = lazy
+            else:
+                orig = orig_imgs[i]
+                oshape = orig.shape[:2]
+            rows[:, :4] = ops.scale_boxes(in_shape, rows[:, :4], oshape)
+            results.append(Results(orig, path=paths[i], names=names, boxes=rows, orig_shape=oshape))
+        return results
+
+    def predict_cli(self, source=None, model=None):
+        for _ in self.stream_inference(source, model):
+            pass

@@ -135,3 +135,12 @@ def forward(model, x, return_features=False):
         if return_features:
             feats[m.i] = x
     raise RuntimeError("model has no Detect head")
+
+
+def fuse_like_reference(model):
+    """What the reference's BaseModel.fuse does on this graph (nn/tasks.py:193-221): Conv+BN folded, RepVGGBlock left
+    as two conv+BN branches (it never calls switch_to_deploy).  Used by the CPU baseline timing."""
+    for m in model.modules():
+        if type(m).__name__ in ("Conv", "DWConv") and hasattr(m, "bn"):
+            m.fuse()
+    return model

@@ -1,0 +1,361 @@
+"""GPU parity tests (run with `-m gpu` on a B200): every kernel family through the C-ABI against the oracle, the
+golden vectors of the real reference, and size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): raw head outputs rtol 2e-2 (bf16 conv stack vs the reference's fp32), decoded boxes 0.5 px,
+NMS rows and kept indices bit-exact given identical pre-NMS tensors.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import decode_np, nms_np, recipe, torch_ref  # noqa: E402
+
+NMS_CASES = {
+    "default": dict(conf_thres=0.001, iou_thres=0.7, max_det=300),
+    "multilabel": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, multi_label=True),
+    "agnostic": dict(conf_thres=0.001, iou_thres=0.5, max_det=100, agnostic=True),
+    "classes": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, classes=[1, 3, 7]),
+    "maxnms": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=200),
+    "predict": dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+}
+STRIDES = [4.0, 8.0, 16.0, 32.0]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def K():
+    from drone_yolo_b200 import kernels
+
+    return kernels
+
+
+def close(got, ref, rtol, atol):
+    torch.testing.assert_close(got.float().cpu(), ref.float().cpu(), rtol=rtol, atol=atol)
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 conv
+@pytest.mark.parametrize("n,k", [(16, 64), (64, 64), (256, 64), (32, 32), (80, 96), (512, 256), (64, 576), (160, 1024)])
+def test_umma_selftest(K, n, k):
+    assert K.selftest_umma(n, k) < 5e-3
+
+
+CONV_CASES = [
+    # B, cin, cout, H, W, k, s, act, res, f32, in_pad, out_pad, tail_pad
+    (1, 64, 64, 16, 16, 1, 1, True, False, False, 0, 0, 0),
+    (2, 64, 64, 16, 16, 3, 1, True, False, False, 0, 0, 0),
+    (2, 64, 128, 16, 16, 3, 2, True, False, False, 0, 0, 0),
+    (2, 32, 32, 40, 40, 3, 1, True, True, False, 0, 0, 0),          # Bottleneck residual, K padded 32 -> 64
+    (3, 128, 256, 20, 20, 3, 1, True, False, False, 0, 0, 0),       # 20x20 map: tile spans images
+    (2, 96, 64, 32, 32, 1, 1, True, False, False, 32, 64, 0),       # reads / writes channel slices of concat buffers
+    (2, 64, 10, 20, 20, 1, 1, False, False, True, 0, 64, 6),        # Detect cls logits: Cout 10, fp32, no activation
+    (1, 512, 512, 20, 20, 3, 1, True, False, False, 0, 0, 0),       # two N tiles of 256
+    (2, 256, 512, 40, 40, 3, 2, True, False, False, 0, 0, 0),       # RepVGG-style downsample
+    (1, 16, 16, 32, 32, 3, 1, True, True, False, 0, 0, 0),
+    (1, 8, 8, 32, 32, 3, 1, True, False, False, 0, 0, 0),           # n-scale bottleneck (Cin 8)
+    (2, 80, 160, 24, 24, 3, 2, True, False, False, 0, 0, 0),        # x-scale widths (N = 160)
+    (1, 160, 320, 13, 17, 3, 1, True, False, False, 0, 0, 0),       # odd, ragged map
+    (1, 48, 96, 15, 15, 3, 2, True, False, False, 0, 0, 0),         # odd map, stride 2
+    (1, 64, 64, 1, 1, 3, 1, True, False, False, 0, 0, 0),           # single pixel
+    (2, 1024, 512, 20, 20, 1, 1, True, False, False, 0, 0, 0),      # SPPF cv2 (K = 1024)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(str(int(v)) for v in c))
+def test_conv_vs_fp32_reference(K, dev, case):
+    B, cin, cout, H, W, k, s, act, res, f32, in_pad, out_pad, tail_pad = case
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    x = torch.randn(B, cin, H, W, generator=g).to(dev)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    xb = torch.zeros(B, H, W, cin + in_pad, device=dev, dtype=torch.bfloat16)
+    xb[..., in_pad:] = x.permute(0, 2, 3, 1)
+    xin = xb.permute(0, 3, 1, 2)[:, in_pad:]
+    wp, bp = K.pack_conv_weight(w, b)
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    ob = torch.full((B, Ho, Wo, out_pad + cout + tail_pad), 7.0, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    out = ob.permute(0, 3, 1, 2)[:, out_pad:out_pad + cout]
+    r = None
+    if res:
+        r = torch.randn(B, cout, Ho, Wo, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    K.conv2d(xin, wp, bp, cout, k, s, act, residual=r, out=out)
+    ref = F.conv2d(xin.float(), w.to(torch.bfloat16).float(), b, stride=s, padding=k // 2)   # plain PyTorch fp32 reference
+    ref = F.silu(ref) if act else ref
+    ref = ref + r.float() if res else ref
+    close(out, ref, 2e-2, 2e-2)
+    assert bool((ob[..., :out_pad] == 7.0).all()) and bool((ob[..., out_pad + cout:] == 7.0).all()), "wrote outside its slice"
+
+
+def test_conv_rejects_bad_arguments(K, dev):
+    from drone_yolo_b200._C import DroneYoloError
+
+    x = torch.zeros(1, 4, 4, 12, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2)      # Cin = 12: not 16B rows
+    w, b = K.pack_conv_weight(torch.zeros(16, 12, 1, 1, device=dev), None)
+    with pytest.raises(DroneYoloError):
+        K.conv2d(x, w, b, 16, 1, 1)
+    with pytest.raises(DroneYoloError):
+        K.conv2d(torch.zeros(1, 16, 4, 4), w, b, 16, 1, 1)                                  # CPU tensor
+
+
+# ---------------------------------------------------------------------------------------------- aux kernels
+def test_stem_pool_upsample_dwconv(K, dev):
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 64, 96, generator=g).to(dev)
+    w = (torch.randn(32, 3, 3, 3, generator=g) * 0.3).to(dev)
+    b = torch.randn(32, generator=g).to(dev)
+    close(K.stem_conv(x, w.reshape(32, 27).contiguous(), b), F.silu(F.conv2d(x, w, b, stride=2, padding=1)), 2e-2, 2e-2)
+
+    for hw, c in ((20, 64), (40, 8), (7, 16)):
+        buf = torch.zeros(2, hw, hw, 4 * c, device=dev, dtype=torch.bfloat16)
+        buf[..., :c] = torch.randn(2, hw, hw, c, generator=g).to(dev)
+        v = buf.permute(0, 3, 1, 2)
+        K.sppf_pool(v, c)
+        y0 = v[:, :c].float()
+        y1 = F.max_pool2d(y0, 5, 1, 2); y2 = F.max_pool2d(y1, 5, 1, 2); y3 = F.max_pool2d(y2, 5, 1, 2)
+        assert torch.equal(v[:, c:].float(), torch.cat((y1, y2, y3), 1))                  # max is exact in bf16
+
+    xi = torch.randn(2, 10, 12, 128, generator=g).to(dev).to(torch.bfloat16).permute(0, 3, 1, 2)
+    ob = torch.zeros(2, 20, 24, 192, device=dev, dtype=torch.bfloat16)
+    K.upsample2x(xi, out=ob.permute(0, 3, 1, 2)[:, 64:])
+    assert torch.equal(ob.permute(0, 3, 1, 2)[:, 64:].float(), F.interpolate(xi.float(), scale_factor=2.0))
+    assert float(ob[..., :64].abs().sum()) == 0
+
+    xi = torch.randn(2, 16, 16, 64, generator=g).to(dev).to(torch.bfloat16).permute(0, 3, 1, 2)
+    w = (torch.randn(32, 2, 3, 3, generator=g) * 0.3).to(dev)
+    b = torch.randn(32, generator=g).to(dev)
+    close(K.dwconv3x3s2(xi, w, b), F.silu(F.conv2d(xi.float(), w, b, stride=2, padding=1, groups=32)), 2e-2, 2e-2)
+
+
+# ---------------------------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("regime", ["sparse", "vallike", "dense"])
+def test_decode_vs_reference_golden(K, dev, golden_dir, regime):
+    g = np.load(golden_dir / f"decode_nms_{regime}.npz")
+    raw = recipe.synthetic_raw_maps(int(g["B"]), int(g["imgsz"]), int(g["nc"]), float(g["mu"]), int(g["raw_seed"]))
+    y = K.detect_decode([r.to(dev) for r in raw], STRIDES, int(g["nc"])).cpu().numpy()
+    assert np.abs(y[:, :4] - g["y"][:, :4]).max() < 1e-2            # pixels (budget: 0.5 px)
+    np.testing.assert_allclose(y[:, 4:], g["y"][:, 4:], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("imgsz", [64, 640])
+def test_decode_nhwc_vs_oracle(K, dev, dtype, imgsz):
+    raw = recipe.synthetic_raw_maps(2, imgsz, 10, -10.0)
+    lv, lv_ref = [], []
+    for r in raw:
+        B, no, H, W = r.shape
+        buf = torch.zeros(B, H, W, 80, device=dev, dtype=dtype)
+        buf[..., :no] = r.to(dev).permute(0, 2, 3, 1).to(dtype)
+        lv.append(buf.permute(0, 3, 1, 2)[:, :no])
+        lv_ref.append(buf[..., :no].permute(0, 3, 1, 2).float().cpu().numpy())
+    ref = decode_np.decode(lv_ref, STRIDES, 10)
+    y = K.detect_decode(lv, STRIDES, 10).cpu().numpy()
+    assert np.abs(y[:, :4] - ref[:, :4]).max() < 1e-2
+    np.testing.assert_allclose(y[:, 4:], ref[:, 4:], rtol=1e-4, atol=1e-7)
+
+
+def test_decode_properties_at_full_size(K, dev):
+    """136k anchors (1280 px): boxes are inside [-15*stride, imgsz + 15*stride], w,h in [0, 30*stride], probabilities in (0,1);
+    decode is per-anchor, so permuting images permutes outputs."""
+    raw = [r.to(dev) for r in recipe.synthetic_raw_maps(4, 1280, 10, -10.0)]
+    y = K.detect_decode(raw, STRIDES, 10)
+    assert y.shape == (4, 14, 136000)
+    assert bool((y[:, 4:] > 0).all()) and bool((y[:, 4:] < 1).all())
+    assert bool((y[:, 2:4] >= 0).all()) and float(y[:, 2:4].max()) <= 30 * 32
+    perm = [2, 0, 3, 1]
+    y2 = K.detect_decode([r[perm].contiguous() for r in raw], STRIDES, 10)
+    assert torch.equal(y2, y[perm])
+
+
+# ---------------------------------------------------------------------------------------------- NMS
+def run_nms(K, dev, y, kw):
+    out, counts, kept = K.nms(torch.as_tensor(y).to(dev), kw["conf_thres"], kw["iou_thres"], max_det=kw["max_det"],
+                              max_nms=kw.get("max_nms", 30000), agnostic=kw.get("agnostic", False),
+                              multi_label=kw.get("multi_label", False), classes=kw.get("classes"))
+    return out.cpu().numpy(), counts.cpu().numpy(), kept.cpu().numpy()
+
+
+def assert_nms_equal(out, counts, kept, ref_out, ref_kept):
+    for b in range(len(ref_out)):
+        n = int(counts[b])
+        assert n == ref_out[b].shape[0], f"image {b}: {n} rows vs {ref_out[b].shape[0]}"
+        assert np.array_equal(out[b, :n].view(np.uint32), ref_out[b].view(np.uint32)), f"image {b}: rows differ"
+        assert np.array_equal(kept[b, :n], ref_kept[b]), f"image {b}: kept indices differ"
+
+
+@pytest.mark.parametrize("regime", ["sparse", "vallike", "dense"])
+@pytest.mark.parametrize("case", sorted(NMS_CASES))
+def test_nms_bit_exact_vs_reference_golden(K, dev, golden_dir, regime, case):
+    g = np.load(golden_dir / f"decode_nms_{regime}.npz")
+    out, counts, kept = run_nms(K, dev, g["y"], NMS_CASES[case])
+    B = int(g["B"])
+    assert_nms_equal(out, counts, kept, [g[f"{case}_out{b}"] for b in range(B)], [g[f"{case}_kept{b}"] for b in range(B)])
+
+
+@pytest.mark.parametrize("mu", [-11.0, -10.0, -7.5])
+@pytest.mark.parametrize("case", ["default", "multilabel"])
+def test_nms_bit_exact_vs_oracle_34k(K, dev, mu, case):
+    raw = recipe.synthetic_raw_maps(2, 640, 10, mu)
+    y = decode_np.decode([r.numpy() for r in raw], STRIDES, 10)
+    ref_out, ref_kept = nms_np.non_max_suppression(y, return_kept=True, **NMS_CASES[case])
+    assert_nms_equal(*run_nms(K, dev, y, NMS_CASES[case]), ref_out, ref_kept)
+
+
+def test_nms_max_nms_truncation_136k(K, dev):
+    """136k anchors, dense: n > max_nms = 30000 exercises the truncation (ops.py:301-302) with the stable tie rule."""
+    raw = recipe.synthetic_raw_maps(1, 1280, 10, -7.5)
+    y = decode_np.decode([r.numpy() for r in raw], STRIDES, 10)
+    ref_out, ref_kept = nms_np.non_max_suppression(y, return_kept=True, **NMS_CASES["default"])
+    assert_nms_equal(*run_nms(K, dev, y, NMS_CASES["default"]), ref_out, ref_kept)
+
+
+def test_nms_edge_cases(K, dev):
+    kw = dict(conf_thres=0.25, iou_thres=0.45, max_det=300)
+    # no candidates at all; A not a multiple of 4 (scalar load path); a single anchor
+    for A in (100, 37, 1):
+        y = np.zeros((2, 14, A), np.float32)
+        out, counts, kept = run_nms(K, dev, y, kw)
+        assert counts.tolist() == [0, 0]
+    # all-identical boxes with tied scores: the lowest index survives, others are suppressed
+    y = np.zeros((1, 14, 64), np.float32)
+    y[0, :4] = np.array([50, 50, 20, 20], np.float32)[:, None]
+    y[0, 4] = 0.9
+    out, counts, kept = run_nms(K, dev, y, kw)
+    ref_out, ref_kept = nms_np.non_max_suppression(y, return_kept=True, **kw)
+    assert_nms_equal(out, counts, kept, ref_out, ref_kept)
+    assert counts.tolist() == [1] and kept[0, 0] == 0
+    # many heavily overlapping boxes: several 512-candidate rounds, few kept
+    rng = np.random.default_rng(0)
+    A = 4096
+    y = np.zeros((1, 14, A), np.float32)
+    y[0, 0] = 100 + rng.random(A) * 3; y[0, 1] = 100 + rng.random(A) * 3; y[0, 2:4] = 50
+    y[0, 4:] = rng.random((10, A)).astype(np.float32)
+    kw2 = dict(conf_thres=0.001, iou_thres=0.7, max_det=300)
+    ref_out, ref_kept = nms_np.non_max_suppression(y, return_kept=True, **kw2)
+    assert_nms_equal(*run_nms(K, dev, y, kw2), ref_out, ref_kept)
+    # max_det smaller than one round
+    kw3 = dict(conf_thres=0.001, iou_thres=0.7, max_det=5)
+    ref_out, ref_kept = nms_np.non_max_suppression(y, return_kept=True, **kw3)
+    assert_nms_equal(*run_nms(K, dev, y, kw3), ref_out, ref_kept)
+
+
+def test_nms_properties_full_batch(K, dev):
+    """BASELINE config 4 size (B=256 x 34k anchors): rows are score-sorted, counts <= max_det, idempotent under image
+    permutation, and image b of the batch equals the same image run alone."""
+    raw = recipe.synthetic_raw_maps(8, 640, 10, -10.0)
+    y8 = torch.from_numpy(decode_np.decode([r.numpy() for r in raw], STRIDES, 10)).to(dev)
+    y = y8.repeat(32, 1, 1)                                        # 256 images
+    out, counts, _ = K.nms(y, 0.001, 0.7)
+    out, counts = out.clone(), counts.clone()
+    assert int(counts.max()) <= 300
+    o = out.cpu().numpy(); c = counts.cpu().numpy()
+    for b in (0, 100, 255):
+        s = o[b, : c[b], 4]
+        assert np.all(s[:-1] >= s[1:])
+    assert np.array_equal(c.reshape(32, 8), np.tile(c[:8], (32, 1)))
+    assert np.array_equal(o[:8], o[248:256])
+    single, c1, _ = K.nms(y8[3:4].contiguous(), 0.001, 0.7)
+    assert int(c1[0]) == c[3] and np.array_equal(single.cpu().numpy()[0, : c[3]], o[3, : c[3]])
+
+
+def test_ops_non_max_suppression_signature_and_side_effects(dev, golden_dir):
+    from drone_yolo_b200.utils import ops
+
+    g = np.load(golden_dir / "decode_nms_vallike.npz")
+    pred = torch.from_numpy(g["y"]).to(dev)
+    before = pred.clone()
+    res = ops.non_max_suppression((pred, None), 0.001, 0.7, None, False, max_det=300, nc=10)     # tuple input, in_place default
+    for b, r in enumerate(res):
+        assert np.array_equal(r.cpu().numpy().view(np.uint32), g[f"default_out{b}"].view(np.uint32))
+    # in_place=True rewrote rows 0..3 of the caller's tensor as xyxy (ops.py:259-260)
+    exp = nms_np.xywh2xyxy(before[:, :4].permute(0, 2, 1).cpu().numpy()).transpose(0, 2, 1)
+    assert np.array_equal(pred[:, :4].cpu().numpy(), exp) and torch.equal(pred[:, 4:], before[:, 4:])
+    res2 = ops.non_max_suppression(before.clone(), 0.001, 0.7, in_place=False, max_time_img=0.0)
+    assert all(torch.equal(a, b) for a, b in zip(res, res2))
+
+
+# ---------------------------------------------------------------------------------------------- whole model
+def build(g, dev):
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(int(g["model_seed"]))
+    m = DetectionModel(str(g["yaml"]), nc=int(g["nc"]), verbose=False)
+    recipe.apply_recipe(m, int(g["bn_seed"]), float(g["cls_delta"]))
+    return m.eval()
+
+
+@pytest.mark.parametrize("tag", ["n_repvgg_128", "n_repvgg_sf_64", "n_p2_64", "s_repvgg_64"])
+@pytest.mark.parametrize("path", ["modules", "plan"])
+def test_model_vs_reference_golden(dev, golden_dir, tag, path):
+    from drone_yolo_b200.engine.engine import Engine
+
+    g = np.load(golden_dir / f"convstack_{tag}.npz")
+    m = build(g, dev).to(dev)
+    x = recipe.images(int(g["B"]), int(g["imgsz"]), int(g["imgsz"]), int(g["image_seed"])).to(dev)
+    if path == "modules":                      # layer-by-layer drop-in modules (un-fused: BN folded on the fly)
+        y, raw = m(x)
+    else:                                      # fused model through the compiled layer plan + CUDA graph
+        eng = Engine(m.fuse(verbose=False), int(g["B"]), int(g["imgsz"]), dev, conf=0.001, iou=0.7)
+        eng(x)
+        y, raw = eng.y, eng.raw_maps()
+    for i, r in enumerate(raw):
+        close(r, torch.from_numpy(g[f"raw{i}"].astype(np.float32)), 2e-2, 2e-2)      # north_star: rtol 2e-2
+    assert float((y[:, :4].cpu() - torch.from_numpy(g["y"][:, :4])).abs().max()) < 0.5   # north_star: 0.5 px
+    close(y[:, 4:], torch.from_numpy(g["y"][:, 4:]), 2e-2, 1e-4)
+
+
+@pytest.mark.parametrize("scale,imgsz,B,mb", [("s", 640, 4, 2), ("n", 320, 3, 1), ("x", 320, 2, 2), ("m", 256, 2, 1)])
+def test_engine_vs_cpu_oracle(dev, scale, imgsz, B, mb):
+    """Full path at real resolutions vs the CPU oracle (fp32): raw maps, boxes, and NMS bit-exact on the engine's own
+    pre-NMS tensor.  Micro-batched replays must not leak state between micro-batches."""
+    from drone_yolo_b200.engine.engine import Engine
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    cpu = DetectionModel(f"yolov8{scale}-p2-repvgg.yaml", nc=10, verbose=False)
+    recipe.apply_recipe(cpu)
+    cpu.eval()
+    x = recipe.images(B, imgsz, imgsz)
+    y_ref, raw_ref = torch_ref.forward(cpu, x)
+    eng = Engine(copy.deepcopy(cpu).to(dev).fuse(verbose=False), B, imgsz, dev, micro_batch=mb, conf=0.001, iou=0.7)
+    out, counts = eng(x.to(dev))
+    y = eng.y.cpu().numpy()
+    for r, rr in zip(eng.raw_maps(), raw_ref):                      # raw maps of the LAST micro-batch
+        close(r, rr[B - mb:], 2e-2, 3e-2)
+    assert np.abs(y[:, :4] - y_ref[:, :4]).max() < 0.5
+    ref_out, ref_kept = nms_np.non_max_suppression(y, return_kept=True, conf_thres=0.001, iou_thres=0.7, max_det=300)
+    assert_nms_equal(out.cpu().numpy(), counts.cpu().numpy(), eng.nms_bufs.kept.cpu().numpy(), ref_out, ref_kept)
+    out2, counts2 = eng(x.to(dev))                                  # graph replay is deterministic
+    assert torch.equal(out2, out) and torch.equal(counts2, counts)
+
+
+def test_predict_api_matches_engine(dev):
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200._C import DroneYoloError
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    x = recipe.images(2, 128, 160).to(dev)
+    events = []
+    res = model.predict(x, conf=0.001, iou=0.7, max_det=50, device="cuda:0")
+    assert len(res) == 2 and all(r.boxes.data.shape[1] == 6 and len(r) <= 50 for r in res)
+    assert res[0].orig_shape == (128, 160) and res[0].orig_img.shape == (128, 160, 3)
+    b = res[0].boxes
+    assert b.xyxy.shape == (len(b), 4) and bool((b.conf[:-1] >= b.conf[1:]).all()) and float(b.xyxy.min()) >= 0
+    model.predictor.add_callback("on_predict_batch_end", lambda p: events.append(len(p.results)))
+    imgs = [(np.random.default_rng(1).random((90, 120, 3)) * 255).astype(np.uint8)] * 3      # list source: letterboxed
+    res2 = model.predict(imgs, conf=0.001, iou=0.7, max_det=50, device="cuda:0", imgsz=128)
+    assert len(res2) == 3 and events == [3] and res2[0].orig_shape == (90, 120)
+    assert float(res2[0].boxes.xyxy[:, [0, 2]].max()) <= 120 and float(res2[0].boxes.xyxy[:, [1, 3]].max()) <= 90
+    with pytest.raises(ValueError):
+        model.predict(torch.rand(1, 3, 100, 100, device=dev), device="cuda:0")
+    with pytest.raises(DroneYoloError):
+        model.predict(x, device="cuda:0", augment=True)

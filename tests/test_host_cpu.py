@@ -1,0 +1,191 @@
+"""CPU tests of the host side: C-ABI symbol table, model construction for every scale / graph, re-parameterisation
+algebra, box helpers, the loud failure without CUDA, and the 2-rank (gloo) shard + gather logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+PARAMS = {  # BASELINE.md §2 (nc = 10)
+    "yolov8n-p2-repvgg.yaml": 2972360, "yolov8s-p2-repvgg.yaml": 10815576, "yolov8m-p2-repvgg.yaml": 25375784,
+    "yolov8l-p2-repvgg.yaml": 43288952, "yolov8x-p2-repvgg.yaml": 67274376,
+    "yolov8n-p2-repvgg-sf.yaml": 2978856, "yolov8s-p2-repvgg-sf.yaml": 10839320, "yolov8x-p2-repvgg-sf.yaml": 67414376,
+}
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    from drone_yolo_b200 import _C
+
+    g.build()
+    header = (ROOT / "include" / "droneyolo.h").read_text()
+    declared = set(re.findall(r"\b(dy_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dy_status"}
+    lib = ctypes.CDLL(str(_C.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in droneyolo.h but not exported"
+    assert declared <= set(_C.SYMBOLS), f"ctypes table misses {declared - set(_C.SYMBOLS)}"
+    assert lib.dy_version() >= 100
+    assert _C.lib().dy_nms_workspace_bytes(256, 10, 34000, 0) >= 256 * 34000 * 8
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the C structs: sizes must equal what gcc computes from the header."""
+    src = '#include "droneyolo.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(dy_conv_desc), sizeof(dy_decode_desc), sizeof(dy_nms_desc));return 0;}'
+    exe = ROOT / "gpurun_out" / "_sizes"
+    exe.parent.mkdir(exist_ok=True)
+    subprocess.run(["gcc", "-x", "c", "-", "-I", str(ROOT / "include"), "-o", str(exe)], input=src, text=True, check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    from drone_yolo_b200 import _C
+
+    assert sizes == [ctypes.sizeof(_C.ConvDesc), ctypes.sizeof(_C.DecodeDesc), ctypes.sizeof(_C.NmsDesc)]
+
+
+@pytest.mark.parametrize("cfg,n_params", sorted(PARAMS.items()))
+def test_model_builds_with_reference_param_count(cfg, n_params):
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    m = DetectionModel(cfg, nc=10, verbose=False)
+    assert sum(p.numel() for p in m.parameters()) == n_params
+    assert m.stride.tolist() == [4.0, 8.0, 16.0, 32.0]
+    assert sorted(set(m.save)) == ([2, 4, 6, 9, 12, 15, 18, 21, 24, 27] if "sf" not in cfg else [0, 2, 4, 6, 9, 10, 13, 14, 17, 18, 21, 24, 27, 30])
+    assert len(m.model) == (29 if "sf" not in cfg else 32)
+
+
+def test_unknown_module_and_missing_yaml_fail():
+    from drone_yolo_b200.nn.tasks import DetectionModel, parse_model
+
+    with pytest.raises(FileNotFoundError):
+        DetectionModel("yolov8n-nope.yaml", verbose=False)
+    with pytest.raises(KeyError):
+        parse_model({"nc": 3, "backbone": [[-1, 1, "GhostConv", [8, 3, 2]]], "head": []}, 3, verbose=False)
+
+
+def test_repvgg_and_repconv_reparameterisation_algebra():
+    """K3 + pad(K1) (+ identity) with BN folded equals the multi-branch forward (reference conv.py:206-247,
+    block.py:1440-1478) — checked with the oracle's plain torch ops."""
+    from drone_yolo_b200.nn.modules import RepConv, RepVGGBlock
+    from oracle import recipe, torch_ref
+
+    torch.manual_seed(3)
+    for blk in (RepVGGBlock(16, 32, 3, 2), RepVGGBlock(16, 16, 3, 1), RepConv(16, 16, 3, 1, bn=True), RepConv(8, 24, 3, 2)):
+        recipe.randomize_bn(blk, 5)
+        blk.eval()
+        x = torch.randn(2, blk.in_channels if hasattr(blk, "in_channels") else blk.c1, 12, 12)
+        ref = torch_ref.module_forward(blk, x)
+        w, b = blk.get_equivalent_kernel_bias()
+        s = blk._geom()[1]
+        got = torch.nn.functional.silu(torch.nn.functional.conv2d(x, w, b, stride=s, padding=1))
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+        (blk.switch_to_deploy if isinstance(blk, RepVGGBlock) else blk.fuse_convs)()
+        torch.testing.assert_close(torch_ref.module_forward(blk, x), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_conv_fuse_matches_bn_forward():
+    from drone_yolo_b200.nn.modules import Conv
+    from oracle import recipe, torch_ref
+
+    torch.manual_seed(4)
+    c = Conv(8, 16, 3, 2)
+    recipe.randomize_bn(c, 9)
+    c.eval()
+    x = torch.randn(1, 8, 10, 10)
+    ref = torch_ref.conv_forward(c, x)
+    c.fuse()
+    assert not hasattr(c, "bn")
+    torch.testing.assert_close(torch_ref.conv_forward(c, x), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_pack_conv_weight_layout():
+    from drone_yolo_b200 import kernels as K
+
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    packed, bias = K.pack_conv_weight(w, torch.tensor([1.0, 2.0]))
+    assert packed.shape == (9, 16, 64) and bias.shape == (16,)
+    assert packed.dtype == torch.bfloat16
+    # tap (r, s) row co, column ci  ==  w[co, ci, r, s]
+    assert float(packed[1 * 3 + 2, 1, 2]) == float(w[1, 2, 1, 2].to(torch.bfloat16))
+    assert float(packed[:, 2:].abs().sum()) == 0 and float(packed[:, :, 3:].abs().sum()) == 0
+    assert bias[:2].tolist() == [1.0, 2.0] and float(bias[2:].abs().sum()) == 0
+
+
+def test_box_helpers_match_reference_formulas():
+    from drone_yolo_b200.utils import ops
+
+    b = torch.tensor([[50.0, 60.0, 20.0, 10.0]])
+    assert ops.xywh2xyxy(b).tolist() == [[40.0, 55.0, 60.0, 65.0]]
+    boxes = torch.tensor([[100.0, 120.0, 300.0, 400.0], [-5.0, 10.0, 700.0, 500.0]])
+    out = ops.scale_boxes((640, 640), boxes.clone(), (480, 640))      # letterboxed 480x640 image: pad (0, 80), gain 1
+    assert out.tolist() == [[100.0, 40.0, 300.0, 320.0], [0.0, 0.0, 640.0, 420.0]]
+    assert ops.make_divisible(33, 8) == 40
+
+
+def test_cpu_tensors_fail_loudly():
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200._C import DroneYoloError
+    from drone_yolo_b200.nn.tasks import DetectionModel
+    from drone_yolo_b200.utils import ops
+
+    with pytest.raises(DroneYoloError):
+        ops.non_max_suppression(torch.rand(1, 14, 100), 0.25, 0.45)
+    with pytest.raises(AssertionError):
+        ops.non_max_suppression(torch.rand(1, 14, 100), 1.5, 0.45)
+    m = DetectionModel("yolov8n-p2-repvgg.yaml", nc=10, verbose=False).eval()
+    with pytest.raises(DroneYoloError):
+        m(torch.rand(1, 3, 64, 64))
+    with pytest.raises(DroneYoloError):
+        YOLO(m).predict(torch.rand(1, 3, 64, 64), device="cpu")
+
+
+def test_shard_bounds_cover_the_batch():
+    from drone_yolo_b200.parallel import shard_bounds
+
+    for n in (0, 1, 7, 64, 513):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from drone_yolo_b200.parallel import DetectionGather, shard_batch, split_detections
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['PORT']}", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+batch = torch.arange(6 * 3, dtype=torch.float32).reshape(6, 3)
+mine = shard_batch(batch, 2, rank)
+assert mine.shape[0] == 3 and float(mine[0, 0]) == rank * 9
+out = torch.full((3, 4, 6), float(rank + 1)); counts = torch.tensor([1 + rank, 2, 0], dtype=torch.int32)
+g = DetectionGather(3, 4, "cpu")
+oa, ca = g.gather(out, counts)
+assert ca.tolist() == [1, 2, 0, 2, 2, 0], ca
+dets = split_detections(oa, ca)
+assert [d.shape[0] for d in dets] == [1, 2, 0, 2, 2, 0] and float(dets[3][0, 0]) == 2.0 and float(dets[0][0, 0]) == 1.0
+dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+"""
+
+
+def test_two_rank_gather_over_gloo(tmp_path):
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port), REPO=str(ROOT), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
