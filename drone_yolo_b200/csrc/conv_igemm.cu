@@ -19,6 +19,7 @@
 #include "dy_ptx.cuh"
 #include "conv_igemm.h"
 #include <cstring>
+#include <cstdlib>
 
 namespace dy {
 
@@ -28,7 +29,7 @@ static constexpr int kBlockM = 128;           // UMMA M
 static constexpr int kBlockK = 64;            // bf16 per 128B swizzle row
 static constexpr int kABytes = kBlockM * 128; // one A stage
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxDynSmem = 227 * 1024 - 1024;
 static constexpr int kAccStride = 256;        // TMEM column offset between the two accumulator stages
@@ -52,10 +53,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < p.nmaps; ++i) prefetch_tmap(&p.tmA[i]);
     prefetch_tmap(&p.tmB);
+    if (p.use_tma_store) prefetch_tmap(&p.tmO);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
@@ -63,6 +65,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we touch
+  // memory it produced.  Let our own dependents start their prologue right away.
+  grid_dep_wait();
+  grid_dep_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -117,21 +123,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> regs -> bias/SiLU/residual -> global =====================
-    const int q = warp - 4;                         // TMEM lane quarter this warp may access
+    // ===================== epilogue: TMEM -> regs -> bias/SiLU/residual -> (smem -> TMA store | global) ==========
+    // 8 warps: warp pair (q, half) owns TMEM lanes [32q, 32q+32) and columns [32*half, 32*half+32) of every 64-column chunk.
+    const int ew = warp - 4;
+    const int q = ew & 3;                           // TMEM lane quarter this warp may access (== warp % 4)
+    const int half = ew >> 2;
     const int row = q * 32 + lane;                  // accumulator row == pixel of the tile
     const int rows_valid = p.TW * p.TH * p.TB;
+    const bool issuer = (threadIdx.x == 4 * 32);    // issues the TMA stores and owns their bulk groups
+    uint8_t* stage_base = smem + static_cast<size_t>(p.stages) * stage_bytes;   // 2 x 16 KB output staging tiles
     int acc = 0; uint32_t acc_phase = 0;
+    int store_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m_tile = tile / p.n_tiles;
       const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th_i = m_tile % p.tiles_h;
       const int tb_i = m_tile / p.tiles_h;
+      const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.TB;
       const int wl = row % p.TW;
       const int hl = (row / p.TW) % p.TH;
       const int bl = row / (p.TW * p.TH);
-      const int w = tw_i * p.TW + wl, h = th_i * p.TH + hl, b = tb_i * p.TB + bl;
+      const int w = w0 + wl, h = h0 + hl, b = b0 + bl;
       const bool valid = (row < rows_valid) && (w < p.Wo) && (h < p.Ho) && (b < p.B);
       const size_t pix = (static_cast<size_t>(b) * p.Ho + h) * p.Wo + w;
       const int n0 = n_tile * p.BN;
@@ -139,69 +152,105 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccStride);
-      for (int c = 0; c < p.BN / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(taddr + c * 16, r);
+      const int nchunks = (p.BN + 63) >> 6;
+      for (int c = 0; c < nchunks; ++c) {
+        const int col0 = c * 64 + half * 32;        // first accumulator column of this warp's 32-column group
+        const int ncols = min(32, p.BN - col0);     // 32, 16 or <= 0 (BN is a multiple of 16)
+        uint32_t r[32];
+        if (ncols >= 32) tmem_ld_32x32b_x32(taddr + col0, r);
+        else if (ncols > 0) tmem_ld_32x32b_x16(taddr + col0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
         tmem_ld_wait();
-        const int n = n0 + c * 16;
-        if (valid && n < p.Cout) {
-          float v[16];
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+        if (c == nchunks - 1) {                     // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const bool via_tma = p.use_tma_store && (c * 64 + 64 <= p.BN);   // uniform over the 8 warps
+        const int n = n0 + col0;
+        float v[32];
+        if (ncols > 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bb = __ldg(bp + j);
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+          for (int j = 0; j < 8; ++j) {
+            if (j * 4 < ncols) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
           }
           if (p.act == DY_ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
           }
-          const bool full16 = (n + 16 <= p.Cout);
-          if (p.res != nullptr) {
+          if (p.res != nullptr && valid) {
             const __nv_bfloat16* rp = p.res + pix * p.res_ld + n;
-            if (full16) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { v[2 * j] += bf16_lo(rw[j]); v[2 * j + 1] += bf16_hi(rw[j]); }
-            } else {
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) v[j] += __bfloat162float(rp[j]);
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncols && n + g * 8 + 8 <= p.Cout) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rp + g * 8);
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[g * 8 + 2 * j] += bf16_lo(rw[j]); v[g * 8 + 2 * j + 1] += bf16_hi(rw[j]); }
+              } else if (g * 8 < ncols) {
+                for (int j = 0; j < 8; ++j) if (n + g * 8 + j < p.Cout) v[g * 8 + j] += __bfloat162float(rp[g * 8 + j]);
+              }
             }
           }
+        }
+        if (via_tma) {
+          // stage the [128 px x 64 ch] bf16 chunk in the 128B-swizzled layout the output tensor map expects
+          uint8_t* st = stage_base + (store_ctr & 1) * kABytes;
+          if (issuer) bulk_wait_group_read<1>();     // the store that last used this buffer has finished reading it
+          named_bar_sync(1, 256);
+          uint8_t* rowp = st + row * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+            o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+            const int chunk16 = half * 4 + g;
+            *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (issuer) {
+            tma_store_4d(&p.tmO, st, n0 + c * 64, w0, h0, b0);
+            bulk_commit_group();
+          }
+          ++store_ctr;
+        } else if (ncols > 0 && valid && n < p.Cout) {
+          // direct register -> global path: fp32 outputs, narrow (non multiple of 64) tails
           if (p.out_f32) {
             float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n;
-            if (full16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) op[j] = v[j];
+            for (int j = 0; j < 8; ++j) {
+              if (j * 4 < ncols) {
+                if (n + j * 4 + 4 <= p.Cout) reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                else for (int e = 0; e < 4; ++e) if (n + j * 4 + e < p.Cout) op[j * 4 + e] = v[j * 4 + e];
+              }
             }
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
-            if (full16) {
-              uint4 o0, o1;
-              o0.x = pack_bf16(v[0], v[1]);   o0.y = pack_bf16(v[2], v[3]);
-              o0.z = pack_bf16(v[4], v[5]);   o0.w = pack_bf16(v[6], v[7]);
-              o1.x = pack_bf16(v[8], v[9]);   o1.y = pack_bf16(v[10], v[11]);
-              o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
-              reinterpret_cast<uint4*>(op)[0] = o0;
-              reinterpret_cast<uint4*>(op)[1] = o1;
-            } else {
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) op[j] = __float2bfloat16(v[j]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncols) {
+                if (n + g * 8 + 8 <= p.Cout) {
+                  uint4 o;
+                  o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+                  o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+                  reinterpret_cast<uint4*>(op)[g] = o;
+                } else {
+                  for (int e = 0; e < 8; ++e) if (n + g * 8 + e < p.Cout) op[g * 8 + e] = __float2bfloat16(v[g * 8 + e]);
+                }
+              }
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (issuer) bulk_wait_group<0>();               // all bulk stores complete before the CTA retires its smem
   }
 
   tc_fence_before();
@@ -363,12 +412,32 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (rc) return rc;
   }
 
+  // output tensor map for the TMA-store epilogue (bf16 outputs; same pixel box as A, 64 channels wide)
+  p->use_tma_store = 0;
+  if (d->out_dtype == DY_BF16 && p->BN >= 64) {
+    const uint64_t old = d->out_ld;
+    const uint32_t obox[4] = {64, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+    int rc;
+    if (k == 1) {
+      const uint64_t M = uint64_t(d->B) * d->H * d->W;
+      const uint64_t dims[4] = {uint64_t(d->Cout), M, 1, 1};
+      const uint64_t strides[3] = {old * esz, M * old * esz, M * old * esz};
+      rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox);
+    } else {
+      const uint64_t dims[4] = {uint64_t(d->Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
+      const uint64_t strides[3] = {old * esz, uint64_t(Wo) * old * esz, uint64_t(Ho) * Wo * old * esz};
+      rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox);
+    }
+    if (rc) return rc;
+    p->use_tma_store = 1;
+  }
+
   const int stage_bytes = kABytes + p->BN * 128;
-  int stages = (kMaxDynSmem - 1024) / stage_bytes;
+  int stages = (kMaxDynSmem - 1024 - 2 * kABytes) / stage_bytes;      // 2 x 16 KB output staging tiles behind the ring
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p->stages = stages;
-  l->smem_bytes = stages * stage_bytes + 1024;
+  l->smem_bytes = stages * stage_bytes + 2 * kABytes + 1024;
   const int total = p->m_tiles * p->n_tiles;
   const int sms = num_sms();
   l->grid = total < sms ? total : sms;
@@ -382,7 +451,18 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     max_smem_set = kMaxDynSmem;
   }
-  conv_igemm_kernel<<<l->grid, kThreads, l->smem_bytes, stream>>>(*p);
+  static const bool use_pdl = (getenv("DY_NO_PDL") == nullptr);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(l->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = l->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, *p));
   return launch_status("conv_igemm_kernel");
 }
 

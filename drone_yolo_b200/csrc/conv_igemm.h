@@ -13,12 +13,14 @@ struct ConvTap { int16_t map, dx, dy, pad; };   // which A tensor map, and the b
 struct ConvParams {
   CUtensorMap tmA[4];      // activation views (1 for stride 1, 4 parity views for stride 2)
   CUtensorMap tmB;         // packed weights [tap][Cout_pad][Cin_pad]
+  CUtensorMap tmO;         // bf16 output slice (TMA-store epilogue)
   ConvTap taps[9];
   int nmaps, ntaps, kblocks;
   int BN, n_tiles;
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
   int B, Ho, Wo, Cout;
   int stages;
+  int use_tma_store;
   void* out; int out_ld; int out_f32;
   const __nv_bfloat16* res; int res_ld;
   const float* bias; int act;
