@@ -186,7 +186,7 @@ struct SelShared {
   int scan_tmp[kSelThreads / 32];
   int sel_count;
   int kept;
-  int found_bin; unsigned int found_below;
+  int found_bin; unsigned int found_below; unsigned int found_count;
 };
 
 static constexpr size_t kSelSharedBytes = (sizeof(SelShared) + 15) & ~size_t(15);
@@ -239,16 +239,25 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
         const unsigned int dmask = (1u << p.pass_bits[ps]) - 1u;
         for (int i = tid; i < kBins; i += kSelThreads) s.hist[i] = 0u;
         __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += kSelThreads) {
-          const int i = i0 + tid;
-          unsigned int digit = 0xffffffffu;
-          if (i < n) {
-            const unsigned long long key = keys[i];
-            const bool live = first ? true : (key > prev_T);
-            if (live && (key & prefix_mask) == prefix_val) digit = static_cast<unsigned>(key >> shift) & dmask;
+        // 4 keys per thread per trip: the loads are independent, so their L2 latency overlaps
+        for (int i0 = 0; i0 < n; i0 += kSelThreads * 4) {
+          unsigned long long key[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kSelThreads + tid;
+            key[u] = (i < n) ? keys[i] : 0ull;
           }
-          const unsigned peers = __match_any_sync(0xffffffffu, digit);
-          if (digit != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&s.hist[digit], __popc(peers));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kSelThreads + tid;
+            unsigned int digit = 0xffffffffu;
+            if (i < n) {
+              const bool live = first ? true : (key[u] > prev_T);
+              if (live && (key[u] & prefix_mask) == prefix_val) digit = static_cast<unsigned>(key[u] >> shift) & dmask;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (digit != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&s.hist[digit], __popc(peers));
+          }
         }
         __syncthreads();
         // locate the bin holding the k_rem-th element: each thread owns 4 consecutive bins
@@ -263,17 +272,24 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
         for (int w = 0; w < warp; ++w) wbase += s.scan_tmp[w];
         const unsigned int excl = static_cast<unsigned>(wbase + incl - mine);
         if (k_rem > excl && k_rem <= excl + static_cast<unsigned>(mine)) {
-          unsigned int below = excl; int bin = tid * 4;
-          if (k_rem > below + h0) { below += h0; bin++;
-            if (k_rem > below + h1) { below += h1; bin++;
-              if (k_rem > below + h2) { below += h2; bin++; } } }
-          s.found_bin = bin; s.found_below = below;
+          unsigned int below = excl; int bin = tid * 4; unsigned int cnt = h0;
+          if (k_rem > below + h0) { below += h0; bin++; cnt = h1;
+            if (k_rem > below + h1) { below += h1; bin++; cnt = h2;
+              if (k_rem > below + h2) { below += h2; bin++; cnt = h3; } } }
+          s.found_bin = bin; s.found_below = below; s.found_count = cnt;
         }
         __syncthreads();
         prefix_val |= static_cast<unsigned long long>(static_cast<unsigned>(s.found_bin)) << shift;
         prefix_mask |= static_cast<unsigned long long>(dmask) << shift;
         k_rem -= s.found_below;
+        const bool takes_whole_bin = (k_rem == s.found_count);
         __syncthreads();
+        if (takes_whole_bin) {
+          // every key sharing this prefix is wanted: the remaining (lower) digits need no selection.
+          // Typical case: after the three score passes the K-th score is unique, so the two id passes are skipped.
+          prefix_val |= (shift > 0) ? ((1ull << shift) - 1ull) : 0ull;   // only bits BELOW this digit (bits between the id and score fields are always 0)
+          break;
+        }
       }
     }
     const unsigned long long T = take_all ? ~0ull : prefix_val;
@@ -282,12 +298,21 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
     if (tid == 0) s.sel_count = 0;
     s.sel_key[tid] = ~0ull;
     __syncthreads();
-    for (int i = tid; i < n; i += kSelThreads) {
-      const unsigned long long key = keys[i];
-      const bool live = first ? true : (key > prev_T);
-      if (live && key <= T) {
-        const int slot = atomicAdd(&s.sel_count, 1);
-        if (slot < kK) s.sel_key[slot] = key;
+    for (int i0 = 0; i0 < n; i0 += kSelThreads * 4) {
+      unsigned long long key[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSelThreads + tid;
+        key[u] = (i < n) ? keys[i] : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSelThreads + tid;
+        const bool live = first ? true : (key[u] > prev_T);
+        if (i < n && live && key[u] <= T) {
+          const int slot = atomicAdd(&s.sel_count, 1);
+          if (slot < kK) s.sel_key[slot] = key[u];
+        }
       }
     }
     __syncthreads();
