@@ -31,33 +31,88 @@ static constexpr int kABytes = kBlockM * 128; // one A stage
 static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
 static constexpr int kTmemCols = 512;
-static constexpr int kMaxDynSmem = 227 * 1024 - 1024;
-static constexpr int kAccStride = 256;        // TMEM column offset between the two accumulator stages
+static constexpr int kMaxDynSmem = 227 * 1024 - 2048;
+static constexpr int kMaxAcc = 8;              // accumulator stages in TMEM: min(8, 512 / BN), BN columns apart
 
+// Contiguous tile range per CTA: coordinates advance by carry instead of by integer division (the single-thread
+// producer / MMA loops are latency-bound, a div/mod chain per tile was ~600 cycles of pure overhead).
+struct TileIter {
+  int n_tile, tw_i, th_i, tb_i, remaining;
+  __device__ __forceinline__ TileIter(const ConvParams& p, int cta, int ncta) {
+    const int total = p.m_tiles * p.n_tiles;
+    const int base = total / ncta, rem = total % ncta;
+    const int begin = cta * base + min(cta, rem);
+    remaining = base + (cta < rem ? 1 : 0);
+    n_tile = begin % p.n_tiles;
+    int m = begin / p.n_tiles;
+    tw_i = m % p.tiles_w; m /= p.tiles_w;
+    th_i = m % p.tiles_h;
+    tb_i = m / p.tiles_h;
+  }
+  __device__ __forceinline__ bool valid() const { return remaining > 0; }
+  __device__ __forceinline__ void next(int n_tiles, int tiles_w, int tiles_h) {
+    --remaining;
+    if (++n_tile == n_tiles) {
+      n_tile = 0;
+      if (++tw_i == tiles_w) {
+        tw_i = 0;
+        if (++th_i == tiles_h) { th_i = 0; ++tb_i; }
+      }
+    }
+  }
+};
+
+// MODE = tap geometry, known at compile time so the single-thread loops carry no table look-ups:
+//   0: 1x1 (one tap), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (four parity views).
+// CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true): 128-byte or
+// 64-byte staging rows.  CW = 0 selects the generic register->global epilogue (odd widths).
+//
+// Warp roles: 0 = A producer (TMA), 1 = MMA issuer, 2 = TMEM allocator, 3 = B producer (TMA), 4..11 = epilogue.
+// Shared memory: [resident weights (b_resident)] [stages x (A 16 KB [+ B BN*128])] [2 x 16 KB output staging].
+template <int MODE, int CW, bool F32>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tfull_bar[2];
-  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
+  __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[256];
 
+  constexpr int NTAPS = MODE == 0 ? 1 : 9;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const bool bres = p.b_resident != 0;
+  const uint32_t bres_bytes = bres ? static_cast<uint32_t>(NTAPS * p.kblocks) * b_bytes : 0u;
+  const uint32_t stage_bytes = kABytes + (bres ? 0u : b_bytes);
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int kiters = p.ntaps * p.kblocks;
+#ifdef DY_CONV_DEBUG
+  const int dbg = p.dbg;   // DY_CONV_DBG knock-outs for bottleneck hunting: 1 = no epilogue work, 2 = no MMA, 4 = no A loads, 8 = no B loads
+#else
+  constexpr int dbg = 0;   // knock-outs compile away unless built with -DDY_CONV_DEBUG
+#endif
+  // `opaque` pins loop invariants in registers: without it the compiler re-derives the shared-window addresses
+  // (S2UR SR_CgaCtaId + ULEA) and re-reads kernel parameters inside the single-thread loops, whose cost is pure latency.
+  const uint32_t smem_base = opaque(smem_u32(smem));
+  const uint32_t stage0 = opaque(smem_base + bres_bytes);  // first pipeline stage (1024-aligned: bres_bytes is a multiple of 2048)
+  const uint32_t full0 = opaque(smem_u32(&full_bar[0])), empty0 = opaque(smem_u32(&empty_bar[0]));
+  const uint32_t tfull0 = opaque(smem_u32(&tfull_bar[0])), tempty0 = opaque(smem_u32(&tempty_bar[0]));
+  const uint32_t bres_b = opaque(smem_u32(&bres_bar));
+  const int nstages = opaque(p.stages), nacc = opaque(p.nacc);
 
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < p.nmaps; ++i) prefetch_tmap(&p.tmA[i]);
     prefetch_tmap(&p.tmB);
-    if (p.use_tma_store) prefetch_tmap(&p.tmO);
+    if (CW > 0) prefetch_tmap(&p.tmO);
   }
   if (warp == 1 && elect_one()) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    const uint32_t producers = bres ? 1u : 2u;             // A thread (+ B thread) arrive on every full barrier
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    mbar_init(&bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, kTmemCols);
@@ -71,26 +126,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   grid_dep_launch();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== A producer: one TMA box per (tap, 64-channel block) =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH * p.TB) * 128u + b_bytes;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        int m_tile = tile / p.n_tiles;
-        const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
-        const int th_i = m_tile % p.tiles_h;
-        const int tb_i = m_tile / p.tiles_h;
-        const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.TB, n0 = n_tile * p.BN;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const ConvTap tap = p.taps[t];
-          for (int kc = 0; kc < p.kblocks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(sa, &p.tmA[tap.map], &full_bar[stage], kc * kBlockK, w0 + tap.dx, h0 + tap.dy, b0);
-            tma_load_3d(sa + kABytes, &p.tmB, &full_bar[stage], kc * kBlockK, n0, t);
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      const uint32_t a_tx = (dbg & 4) ? 0u : static_cast<uint32_t>(p.TW * p.TH * p.TB) * 128u;
+      const int kblocks = opaque(p.kblocks);
+      const int n_tiles = opaque(p.n_tiles), tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h);
+      const int TW = opaque(p.TW), TH = opaque(p.TH), TB = opaque(p.TB);
+      for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(n_tiles, tiles_w, tiles_h)) {
+        const int w0 = it.tw_i * TW, h0 = it.th_i * TH, b0 = it.tb_i * TB;
+#pragma unroll
+        for (int t = 0; t < NTAPS; ++t) {
+          // compile-time tap geometry
+          const int oy = MODE == 0 ? 0 : t / 3 - 1, ox = MODE == 0 ? 0 : t % 3 - 1;
+          const int map = MODE == 2 ? ((oy & 1) * 2 + (ox & 1)) : 0;
+          const int dx = MODE == 2 ? (ox < 0 ? -1 : 0) : ox, dy = MODE == 2 ? (oy < 0 ? -1 : 0) : oy;
+          const CUtensorMap* tm = &p.tmA[map];
+          for (int kc = 0; kc < kblocks; ++kc) {
+            const uint32_t fb = full0 + stage * 8;
+            mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
+            mbar_arrive_expect_tx_a(fb, a_tx);
+            if (!(dbg & 4)) tma_load_4d_a(stage0 + stage * stage_bytes, tm, fb, kc * kBlockK, w0 + dx, h0 + dy, b0);
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: weights, either once (resident) or per stage =====================
+    if (elect_one()) {
+      const int kblocks = opaque(p.kblocks);
+      if (bres) {
+        mbar_arrive_expect_tx_a(bres_b, (dbg & 8) ? 0u : bres_bytes);
+        if (!(dbg & 8)) {
+          for (int t = 0; t < NTAPS; ++t)
+            for (int kc = 0; kc < kblocks; ++kc)
+              tma_load_3d_a(smem_base + static_cast<uint32_t>(t * kblocks + kc) * b_bytes, &p.tmB, bres_b, kc * kBlockK, 0, t);
+        }
+      } else {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t b_tx = (dbg & 8) ? 0u : b_bytes;
+        const int n_tiles = opaque(p.n_tiles), tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h), BN = opaque(p.BN);
+        for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(n_tiles, tiles_w, tiles_h)) {
+          const int n0 = it.n_tile * BN;
+#pragma unroll
+          for (int t = 0; t < NTAPS; ++t) {
+            for (int kc = 0; kc < kblocks; ++kc) {
+              const uint32_t fb = full0 + stage * 8;
+              mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
+              mbar_arrive_expect_tx_a(fb, b_tx);
+              if (!(dbg & 8)) tma_load_3d_a(stage0 + stage * stage_bytes + kABytes, &p.tmB, fb, kc * kBlockK, n0, t);
+              if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -101,156 +188,207 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16(kBlockM, p.BN);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      const int kiters = opaque(NTAPS * p.kblocks);
+      const uint32_t sbytes = opaque(stage_bytes), bbytes = opaque(b_bytes);
+      // descriptor = constant high word | (address >> 4): only the low word changes
+      const uint64_t desc_hi = umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
+      const uint32_t desc_lo_const = static_cast<uint32_t>(umma_desc_sw128(0, 1024) & 0xffffffffull);   // LBO field
+      if (bres) mbar_wait_a(bres_b, 0);
+      const uint32_t BNu = opaque(static_cast<uint32_t>(p.BN));
+      int my_tiles = total_tiles / static_cast<int>(gridDim.x) + (static_cast<int>(blockIdx.x) < total_tiles % static_cast<int>(gridDim.x) ? 1 : 0);
+      for (; my_tiles > 0; --my_tiles) {
+        mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * BNu;
         for (int kb = 0; kb < kiters; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_a(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t a_addr = stage0 + stage * sbytes;
+          const uint32_t b_addr = bres ? smem_base + static_cast<uint32_t>(kb) * bbytes : a_addr + kABytes;
+          const uint32_t a_lo = desc_lo_const | ((a_addr & 0x3ffffu) >> 4), b_lo = desc_lo_const | ((b_addr & 0x3ffffu) >> 4);
+          if (!(dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_bf16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32, 1024), umma_desc_sw128(b_addr + k * 32, 1024),
-                         idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_ss(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          umma_commit_a(empty0 + stage * 8);          // frees the smem slot when these MMAs retire
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        umma_commit_a(tfull0 + acc * 8);              // accumulator complete -> epilogue
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> bias/SiLU/residual -> (smem -> TMA store | global) ==========
-    // 8 warps: warp pair (q, half) owns TMEM lanes [32q, 32q+32) and columns [32*half, 32*half+32) of every 64-column chunk.
+    // 8 warps: warp pair (q, half) owns TMEM lanes [32q, 32q+32) and one half of every CW-column chunk.
     const int ew = warp - 4;
     const int q = ew & 3;                           // TMEM lane quarter this warp may access (== warp % 4)
     const int half = ew >> 2;
     const int row = q * 32 + lane;                  // accumulator row == pixel of the tile
+    const int etid = threadIdx.x - 4 * 32;          // 0..255
     const int rows_valid = p.TW * p.TH * p.TB;
-    const bool issuer = (threadIdx.x == 4 * 32);    // issues the TMA stores and owns their bulk groups
-    uint8_t* stage_base = smem + static_cast<size_t>(p.stages) * stage_bytes;   // 2 x 16 KB output staging tiles
+    const bool issuer = (etid == 0);                // issues the TMA stores and owns their bulk groups
+    uint8_t* stage_base = smem + bres_bytes + static_cast<size_t>(p.stages) * stage_bytes;   // 2 x 16 KB output staging tiles
+    const bool silu = (p.act == DY_ACT_SILU);
+    const float bscale = silu ? 0.5f : 1.0f;        // SiLU path keeps 0.5*bias: h = 0.5*acc + 0.5*b in one FFMA
     int acc = 0; uint32_t acc_phase = 0;
     int store_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      int m_tile = tile / p.n_tiles;
-      const int tw_i = m_tile % p.tiles_w; m_tile /= p.tiles_w;
-      const int th_i = m_tile % p.tiles_h;
-      const int tb_i = m_tile / p.tiles_h;
-      const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tb_i * p.TB;
-      const int wl = row % p.TW;
-      const int hl = (row / p.TW) % p.TH;
-      const int bl = row / (p.TW * p.TH);
+    const int wl = row % p.TW;                      // this thread's pixel inside the tile never changes
+    const int hl = (row / p.TW) % p.TH;
+    const int bl = row / (p.TW * p.TH);
+    for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(p.n_tiles, p.tiles_w, p.tiles_h)) {
+      const int w0 = it.tw_i * p.TW, h0 = it.th_i * p.TH, b0 = it.tb_i * p.TB;
       const int w = w0 + wl, h = h0 + hl, b = b0 + bl;
       const bool valid = (row < rows_valid) && (w < p.Wo) && (h < p.Ho) && (b < p.B);
       const size_t pix = (static_cast<size_t>(b) * p.Ho + h) * p.Wo + w;
-      const int n0 = n_tile * p.BN;
+      const int n0 = it.n_tile * p.BN;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccStride);
-      const int nchunks = (p.BN + 63) >> 6;
-      for (int c = 0; c < nchunks; ++c) {
-        const int col0 = c * 64 + half * 32;        // first accumulator column of this warp's 32-column group
-        const int ncols = min(32, p.BN - col0);     // 32, 16 or <= 0 (BN is a multiple of 16)
-        uint32_t r[32];
-        if (ncols >= 32) tmem_ld_32x32b_x32(taddr + col0, r);
-        else if (ncols > 0) tmem_ld_32x32b_x16(taddr + col0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-        tmem_ld_wait();
-        if (c == nchunks - 1) {                     // accumulator fully read: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        const bool via_tma = p.use_tma_store && (c * 64 + 64 <= p.BN);   // uniform over the 8 warps
-        const int n = n0 + col0;
-        float v[32];
-        if (ncols > 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j * 4 < ncols) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-            }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
+
+      if constexpr (CW > 0) {
+        // ---------------- fast path: every chunk is CW columns wide and leaves through a TMA store ----------------
+        constexpr int WC = CW / 2;                  // columns per warp
+        s_bias[etid] = (etid < p.BN) ? bscale * __ldg(p.bias + n0 + etid) : 0.f;   // visible after the chunk's first barrier
+        const int nchunks = (p.BN + CW - 1) / CW;   // a ragged last chunk only exists when n_tiles == 1: TMA clips columns >= Cout
+        for (int c = 0; c < nchunks; ++c) {
+          const int col0 = c * CW + half * WC;
+          uint32_t r[WC];
+          if constexpr (WC == 32) tmem_ld_32x32b_x32(taddr + col0, r);
+          else tmem_ld_32x32b_x16(taddr + col0, r);
+          uint8_t* st = stage_base + (store_ctr & 1) * kABytes;
+          if (dbg & 1) {                             // knock-out: read the accumulator, release it, do nothing else
+            tmem_ld_wait();
+            if (c == nchunks - 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty_bar[acc]); }
+            continue;
           }
-          if (p.act == DY_ACT_SILU) {
+          if (issuer) bulk_wait_group_read<1>();     // the store that last used this staging buffer has read it
+          named_bar_sync(1, 256);                    // ... and s_bias of this tile is complete
+          tmem_ld_wait();
+          if (c == nchunks - 1) {                    // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          float v[WC];
+          const float4* bs = reinterpret_cast<const float4*>(s_bias + col0);
+          if (silu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
+            for (int j = 0; j < WC / 4; ++j) {
+              const float4 hb = bs[j];
+              const float h0_ = fmaf(__uint_as_float(r[4 * j + 0]), 0.5f, hb.x), h1_ = fmaf(__uint_as_float(r[4 * j + 1]), 0.5f, hb.y);
+              const float h2_ = fmaf(__uint_as_float(r[4 * j + 2]), 0.5f, hb.z), h3_ = fmaf(__uint_as_float(r[4 * j + 3]), 0.5f, hb.w);
+              v[4 * j + 0] = fmaf(h0_, tanh_fast(h0_), h0_); v[4 * j + 1] = fmaf(h1_, tanh_fast(h1_), h1_);
+              v[4 * j + 2] = fmaf(h2_, tanh_fast(h2_), h2_); v[4 * j + 3] = fmaf(h3_, tanh_fast(h3_), h3_);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < WC / 4; ++j) {
+              const float4 bb = bs[j];
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
           }
           if (p.res != nullptr && valid) {
-            const __nv_bfloat16* rp = p.res + pix * p.res_ld + n;
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_ld + n0 + col0);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncols && n + g * 8 + 8 <= p.Cout) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rp + g * 8);
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { v[g * 8 + 2 * j] += bf16_lo(rw[j]); v[g * 8 + 2 * j + 1] += bf16_hi(rw[j]); }
-              } else if (g * 8 < ncols) {
-                for (int j = 0; j < 8; ++j) if (n + g * 8 + j < p.Cout) v[g * 8 + j] += __bfloat162float(rp[g * 8 + j]);
-              }
+            for (int g = 0; g < WC / 8; ++g) {
+              if (n0 + col0 + 8 * g + 8 > p.Cout) break;     // ragged last chunk: stay inside the residual slice
+              const uint4 rr = __ldg(rp + g);
+              v[8 * g + 0] += bf16_lo(rr.x); v[8 * g + 1] += bf16_hi(rr.x); v[8 * g + 2] += bf16_lo(rr.y); v[8 * g + 3] += bf16_hi(rr.y);
+              v[8 * g + 4] += bf16_lo(rr.z); v[8 * g + 5] += bf16_hi(rr.z); v[8 * g + 6] += bf16_lo(rr.w); v[8 * g + 7] += bf16_hi(rr.w);
             }
           }
-        }
-        if (via_tma) {
-          // stage the [128 px x 64 ch] bf16 chunk in the 128B-swizzled layout the output tensor map expects
-          uint8_t* st = stage_base + (store_ctr & 1) * kABytes;
-          if (issuer) bulk_wait_group_read<1>();     // the store that last used this buffer has finished reading it
-          named_bar_sync(1, 256);
-          uint8_t* rowp = st + row * 128;
+          // stage the [128 px x CW ch] chunk: 128-byte rows are 128B-swizzled (CW == 64 bf16, CW == 32 fp32),
+          // 64-byte rows (CW == 32 bf16) are linear
+          if constexpr (F32) {
+            uint8_t* rowp = st + row * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-            o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-            const int chunk16 = half * 4 + g;
-            *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = o;
+            for (int g = 0; g < WC / 4; ++g) {
+              const int chunk16 = half * (WC / 4) + g;
+              *reinterpret_cast<float4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+          } else {
+            uint8_t* rowp = st + row * (CW * 2);
+#pragma unroll
+            for (int g = 0; g < WC / 8; ++g) {
+              uint4 o;
+              o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+              o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+              const int chunk16 = half * (WC / 8) + g;
+              if constexpr (CW == 64) *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = o;
+              else *reinterpret_cast<uint4*>(rowp + (chunk16 << 4)) = o;
+            }
           }
           fence_proxy_async_smem();
           named_bar_sync(1, 256);
           if (issuer) {
-            tma_store_4d(&p.tmO, st, n0 + c * 64, w0, h0, b0);
+            tma_store_4d(&p.tmO, st, n0 + c * CW, w0, h0, b0);
             bulk_commit_group();
           }
           ++store_ctr;
-        } else if (ncols > 0 && valid && n < p.Cout) {
-          // direct register -> global path: fp32 outputs, narrow (non multiple of 64) tails
-          if (p.out_f32) {
-            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j * 4 < ncols) {
-                if (n + j * 4 + 4 <= p.Cout) reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                else for (int e = 0; e < 4; ++e) if (n + j * 4 + e < p.Cout) op[j * 4 + e] = v[j * 4 + e];
-              }
+        }
+      } else {
+        // ---------------- generic path: fp32 outputs and odd widths, registers -> global ----------------
+        const int nchunks = (p.BN + 63) >> 6;
+        for (int c = 0; c < nchunks; ++c) {
+          const int col0 = c * 64 + half * 32;
+          const int ncols = min(32, p.BN - col0);    // 32, 16 or <= 0 (BN is a multiple of 16)
+          uint32_t r[32];
+          if (ncols >= 32) tmem_ld_32x32b_x32(taddr + col0, r);
+          else if (ncols > 0) tmem_ld_32x32b_x16(taddr + col0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          tmem_ld_wait();
+          if (c == nchunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          const int n = n0 + col0;
+          if (ncols > 0 && valid && n < p.Cout) {
+            for (int j = 0; j < ncols; ++j) {
+              if (n + j >= p.Cout) break;
+              float x = __uint_as_float(r[j]) + __ldg(p.bias + n + j);
+              if (silu) x = silu_fast(x);
+              if (p.res != nullptr) x += __bfloat162float(p.res[pix * p.res_ld + n + j]);
+              r[j] = __float_as_uint(x);
             }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
+            if (p.out_f32) {
+              float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncols) {
-                if (n + g * 8 + 8 <= p.Cout) {
-                  uint4 o;
-                  o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-                  o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-                  reinterpret_cast<uint4*>(op)[g] = o;
-                } else {
-                  for (int e = 0; e < 8; ++e) if (n + g * 8 + e < p.Cout) op[g * 8 + e] = __float2bfloat16(v[g * 8 + e]);
+              for (int j = 0; j < 8; ++j) {
+                if (j * 4 < ncols) {
+                  if (n + j * 4 + 4 <= p.Cout)
+                    reinterpret_cast<float4*>(op)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                  else
+                    for (int e = 0; e < 4; ++e) if (n + j * 4 + e < p.Cout) op[j * 4 + e] = __uint_as_float(r[j * 4 + e]);
+                }
+              }
+            } else {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (g * 8 < ncols) {
+                  if (n + g * 8 + 8 <= p.Cout) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+                    o.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+                    o.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                    o.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                    reinterpret_cast<uint4*>(op)[g] = o;
+                  } else {
+                    for (int e = 0; e < 8; ++e) if (n + g * 8 + e < p.Cout) op[g * 8 + e] = __float2bfloat16(__uint_as_float(r[g * 8 + e]));
+                  }
                 }
               }
             }
           }
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
-    if (issuer) bulk_wait_group<0>();               // all bulk stores complete before the CTA retires its smem
+    if (CW > 0 && issuer) bulk_wait_group<0>();     // all bulk stores complete before the CTA retires its smem
   }
 
   tc_fence_before();
@@ -278,14 +416,15 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return fail(DY_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, dtype, rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(DY_ERR_CUDA,
@@ -412,43 +551,69 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (rc) return rc;
   }
 
-  // output tensor map for the TMA-store epilogue (bf16 outputs; same pixel box as A, 64 channels wide)
+  // output tensor map for the TMA-store epilogue (same pixel box as A, CW channels wide).  A ragged last chunk is only
+  // allowed with a single N tile, where every column >= BN is also >= Cout and is clipped by the tensor map.
   p->use_tma_store = 0;
-  if (d->out_dtype == DY_BF16 && p->BN >= 64) {
-    const uint64_t old = d->out_ld;
-    const uint32_t obox[4] = {64, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
-    int rc;
-    if (k == 1) {
-      const uint64_t M = uint64_t(d->B) * d->H * d->W;
-      const uint64_t dims[4] = {uint64_t(d->Cout), M, 1, 1};
-      const uint64_t strides[3] = {old * esz, M * old * esz, M * old * esz};
-      rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox);
-    } else {
-      const uint64_t dims[4] = {uint64_t(d->Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
-      const uint64_t strides[3] = {old * esz, uint64_t(Wo) * old * esz, uint64_t(Ho) * Wo * old * esz};
-      rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox);
+  {
+    const bool f32 = d->out_dtype == DY_F32;
+    int cw = 0;
+    // (TMA clips the innermost dimension at 16-byte granularity: the slice width must be a multiple of 16 bytes)
+    if (f32) { if ((p->BN % 32 == 0 || p->n_tiles == 1) && d->Cout % 4 == 0) cw = 32; }
+    else if (d->Cout % 8 == 0) {
+      if (p->BN % 64 == 0) cw = 64;
+      else if (p->BN % 32 == 0) cw = 32;
+      else if (p->n_tiles == 1) cw = p->BN > 32 ? 64 : 32;
     }
-    if (rc) return rc;
-    p->use_tma_store = 1;
+    if (cw) {
+      const uint64_t oes = out_esz;
+      const uint64_t old = d->out_ld;
+      const uint32_t obox[4] = {uint32_t(cw), uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+      const CUtensorMapSwizzle sw = (cw * out_esz == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+      const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      int rc;
+      if (k == 1) {
+        const uint64_t M = uint64_t(d->B) * d->H * d->W;
+        const uint64_t dims[4] = {uint64_t(d->Cout), M, 1, 1};
+        const uint64_t strides[3] = {old * oes, M * old * oes, M * old * oes};
+        rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox, sw, dt);
+      } else {
+        const uint64_t dims[4] = {uint64_t(d->Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
+        const uint64_t strides[3] = {old * oes, uint64_t(Wo) * old * oes, uint64_t(Ho) * Wo * old * oes};
+        rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox, sw, dt);
+      }
+      if (rc) return rc;
+      p->use_tma_store = cw;
+    }
   }
 
-  const int stage_bytes = kABytes + p->BN * 128;
-  int stages = (kMaxDynSmem - 1024 - 2 * kABytes) / stage_bytes;      // 2 x 16 KB output staging tiles behind the ring
+  // Shared-memory plan.  Small layers keep ALL their weights resident (loaded once per CTA): the per-stage traffic and the
+  // per-stage TMA issue then only cover the activation tile.  Everything else streams B next to A.
+  const int b_tile = p->BN * 128;
+  const int b_all = p->ntaps * p->kblocks * b_tile;
+  const int budget = kMaxDynSmem - 1024 - 2 * kABytes;                  // minus alignment slack and the output staging tiles
+  p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes) ? 1 : 0;   // leave room for >= 4 activation stages
+  if (getenv("DY_NO_BRES")) p->b_resident = 0;
+  const int stage_bytes = kABytes + (p->b_resident ? 0 : b_tile);
+  int stages = (budget - (p->b_resident ? b_all : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p->stages = stages;
-  l->smem_bytes = stages * stage_bytes + 2 * kABytes + 1024;
+  p->nacc = 512 / p->BN < kMaxAcc ? 512 / p->BN : kMaxAcc;
+  l->smem_bytes = (p->b_resident ? b_all : 0) + stages * stage_bytes + 2 * kABytes + 1024;
+  p->mode = (k == 1) ? 0 : (s == 1 ? 1 : 2);
   const int total = p->m_tiles * p->n_tiles;
   const int sms = num_sms();
   l->grid = total < sms ? total : sms;
+  { const char* e = getenv("DY_CONV_DBG"); p->dbg = e ? atoi(e) : 0; }
   return DY_OK;
 }
 
-int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
+template <int MODE, int CW, bool F32>
+static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   static int max_smem_set = 0;
   if (max_smem_set < l->smem_bytes) {
-    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 1 KB
-    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 2 KB
+    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     max_smem_set = kMaxDynSmem;
   }
   static const bool use_pdl = (getenv("DY_NO_PDL") == nullptr);
@@ -462,8 +627,22 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, *p));
+  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<MODE, CW, F32>, *p));
   return launch_status("conv_igemm_kernel");
+}
+
+template <int MODE>
+static int conv_launch_m(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
+  if (p->use_tma_store == 64) return conv_launch_t<MODE, 64, false>(p, l, stream);
+  if (p->use_tma_store == 32 && !p->out_f32) return conv_launch_t<MODE, 32, false>(p, l, stream);
+  if (p->use_tma_store == 32 && p->out_f32) return conv_launch_t<MODE, 32, true>(p, l, stream);
+  return conv_launch_t<MODE, 0, false>(p, l, stream);
+}
+
+int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
+  if (p->mode == 0) return conv_launch_m<0>(p, l, stream);
+  if (p->mode == 1) return conv_launch_m<1>(p, l, stream);
+  return conv_launch_m<2>(p, l, stream);
 }
 
 }  // namespace dy

@@ -19,8 +19,9 @@ struct ConvParams {
   int BN, n_tiles;
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
   int B, Ho, Wo, Cout;
-  int stages;
+  int stages, nacc, b_resident, mode;
   int use_tma_store;
+  int dbg;
   void* out; int out_ld; int out_f32;
   const __nv_bfloat16* res; int res_ld;
   const float* bias; int act;

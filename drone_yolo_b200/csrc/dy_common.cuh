@@ -44,6 +44,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);   // a -> low half, b -> high half
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// Identity the optimiser cannot see through: keeps a loop invariant in a register.
+__device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ int opaque(int x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ float tanh_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
 // SiLU with one MUFU: x*sigmoid(x) = h + h*tanh(h), h = x/2
 __device__ __forceinline__ float silu_fast(float x) {
   float h = 0.5f * x, t;

@@ -191,8 +191,9 @@ class LayerPlan:
             self._op(kind="conv", mod=m.cv3[i][1], inp=Ref(t1, c2, c3, H, W), out=Ref(t2, c2, c3, H, W))
             self._op(kind="conv", w=(wbx, bbx), cout=4 * m.reg_max, k=1, s=1, act=False, inp=Ref(t2, 0, c2, H, W),
                      out=Ref(raw, 0, 4 * m.reg_max, H, W))
-            self._op(kind="conv", w=(wcl, bcl), cout=m.nc, k=1, s=1, act=False, inp=Ref(t2, c2, c3, H, W),
-                     out=Ref(raw, 4 * m.reg_max, m.nc, H, W))
+            ncp = m.raw_ld - 4 * m.reg_max          # class logits padded to 16 channels (zero weights) -> TMA-store path
+            self._op(kind="conv", w=(wcl, bcl), cout=ncp, k=1, s=1, act=False, inp=Ref(t2, c2, c3, H, W),
+                     out=Ref(raw, 4 * m.reg_max, ncp, H, W))
             levels.append(Ref(raw, 0, m.no, H, W))
         self._op(kind="decode", levels=levels, det=m)
         self.raw_refs = levels

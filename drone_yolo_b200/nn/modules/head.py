@@ -94,7 +94,8 @@ class Detect(nn.Module):
             self.cv3[i][1].run(t1[:, c2:], out=t2[:, c2:])
             raw = K.empty_nhwc(B, self.raw_ld, H, W, xi.device, torch.float32)
             K.conv2d(t2[:, :c2], wbx, bbx, 4 * self.reg_max, 1, 1, False, out=raw[:, :4 * self.reg_max])
-            K.conv2d(t2[:, c2:], wcl, bcl, self.nc, 1, 1, False, out=raw[:, 4 * self.reg_max:self.no])
+            ncp = self.raw_ld - 4 * self.reg_max           # padded class rows are zero weights: pad channels become 0
+            K.conv2d(t2[:, c2:], wcl, bcl, ncp, 1, 1, False, out=raw[:, 4 * self.reg_max:])
             outs.append(raw[:, :self.no])
         return outs
 
