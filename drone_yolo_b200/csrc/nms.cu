@@ -27,6 +27,7 @@ static constexpr int kSelThreads = 512;
 static constexpr int kK = 512;                 // candidates per greedy round (== kSelThreads)
 static constexpr int kWords = kK / 32;
 static constexpr int kBins = 2048;
+static constexpr int kBig = 4096;               // keys selected + sorted per super-round
 static constexpr int kMaxPasses = 8;
 static constexpr int kMaxClassWords = 32;      // class filter bitmask: nc <= 1024
 
@@ -177,7 +178,6 @@ __device__ __forceinline__ bool iou_suppresses(const float4& a, float area_a, co
 }
 
 struct SelShared {
-  unsigned long long sel_key[kK];
   float4 box[kK];
   float area[kK];
   unsigned int hist[kBins];
@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   unsigned long long* kkey = reinterpret_cast<unsigned long long*>(kbox + p.max_det);
   float* karea = reinterpret_cast<float*>(kkey + p.max_det);
   int* krank = reinterpret_cast<int*>(karea + p.max_det);
+  unsigned long long* big = reinterpret_cast<unsigned long long*>(smem_raw + kSelSharedBytes + ((static_cast<size_t>(p.max_det) * 32 + 15) & ~size_t(15)));
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.img_count[b];
@@ -225,14 +226,15 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   __syncthreads();
 
   int processed = 0;
-  unsigned long long prev_T = 0ull;            // every key is > 0 (scores are finite, so ~bits != 0 ... and id part)
+  unsigned long long prev_T = 0ull;            // keys taken so far are exactly the keys <= prev_T
   bool first = true;
-  while (processed < limit) {
-    const int K = min(kK, limit - processed);
-    // ---- (a) radix select: T = K-th smallest key among keys > prev_T (or >= for the first round) ----
+  bool done = false;
+  while (processed < limit && !done) {
+    // =============== super-round: the next SK (<= 4096) smallest keys, selected once and sorted in shared memory ===============
+    const int SK = min(kBig, limit - processed);
     unsigned long long prefix_val = 0ull, prefix_mask = 0ull;
-    unsigned int k_rem = static_cast<unsigned>(K);
-    const bool take_all = (n - processed) <= K;          // everything left fits in this round: skip the select
+    unsigned int k_rem = static_cast<unsigned>(SK);
+    const bool take_all = (n - processed) <= SK;          // everything left fits: no selection needed
     if (!take_all) {
       for (int ps = 0; ps < p.npasses; ++ps) {
         const int shift = p.pass_shift[ps];
@@ -294,9 +296,11 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
     }
     const unsigned long long T = take_all ? ~0ull : prefix_val;
 
-    // ---- (b) gather keys in (prev_T, T] and sort them ascending (bitonic, 512 slots) ----
+    // ---- gather keys in (prev_T, T] into big[] and bitonic-sort them ascending ----
+    int npow = kK;                                   // sort size: next power of two >= SK (>= 512)
+    while (npow < SK) npow <<= 1;
     if (tid == 0) s.sel_count = 0;
-    s.sel_key[tid] = ~0ull;
+    for (int i = tid; i < npow; i += kSelThreads) big[i] = ~0ull;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += kSelThreads * 4) {
       unsigned long long key[4];
@@ -311,79 +315,85 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
         const bool live = first ? true : (key[u] > prev_T);
         if (i < n && live && key[u] <= T) {
           const int slot = atomicAdd(&s.sel_count, 1);
-          if (slot < kK) s.sel_key[slot] = key[u];
+          if (slot < kBig) big[slot] = key[u];
         }
       }
     }
     __syncthreads();
-    for (int size = 2; size <= kK; size <<= 1) {
+    for (int size = 2; size <= npow; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        const int partner = tid ^ stride;
-        if (partner > tid) {
-          const unsigned long long x = s.sel_key[tid], y = s.sel_key[partner];
-          const bool up = (tid & size) == 0;
-          if ((x > y) == up) { s.sel_key[tid] = y; s.sel_key[partner] = x; }
+        for (int t = tid; t < (npow >> 1); t += kSelThreads) {
+          const int lo = 2 * t - (t & (stride - 1));
+          const int hi = lo + stride;
+          const unsigned long long x = big[lo], y = big[hi];
+          const bool up = (lo & size) == 0;
+          if ((x > y) == up) { big[lo] = y; big[hi] = x; }
         }
         __syncthreads();
       }
     }
 
-    // ---- (c) class-offset boxes ----
-    const bool have = tid < K;
-    float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f); float myarea = 0.f;
-    if (have) { load_offset_box(p, img, s.sel_key[tid], &mybox, &myarea); s.box[tid] = mybox; s.area[tid] = myarea; }
-    // ---- (d) suppress against boxes kept in earlier rounds ----
-    bool dead = !have;
-    const int kept0 = s.kept;
-    if (have) {
-      for (int i = 0; i < kept0 && !dead; ++i) dead = iou_suppresses(kbox[i], karea[i], mybox, myarea, p.iou_f, p.iou_inclusive);
-    }
-    const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
-    if (lane == 0) s.remv[warp] = dead_bits;
-    __syncthreads();
-    // ---- (e) upper-triangular suppression bitmask: thread i owns row i; mask[w][i] covers j in [32w, 32w+32) ----
-    if (have) {
-      for (int w = 0; w < kWords; ++w) {
-        unsigned int bits = 0u;
-        const int j0 = w * 32;
-        if (j0 + 31 > tid && j0 < K && !dead) {
-          const int jend = min(32, K - j0);
-          for (int jj = 0; jj < jend; ++jj) {
-            const int j = j0 + jj;
-            if (j > tid && iou_suppresses(mybox, myarea, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+    // =============== greedy rounds of 512 candidates in sorted order ===============
+    for (int off = 0; off < SK; off += kK) {
+      const int K = min(kK, SK - off);
+      // ---- (c) class-offset boxes ----
+      const bool have = tid < K;
+      const unsigned long long mykey = have ? big[off + tid] : ~0ull;
+      float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f); float myarea = 0.f;
+      if (have) { load_offset_box(p, img, mykey, &mybox, &myarea); s.box[tid] = mybox; s.area[tid] = myarea; }
+      // ---- (d) suppress against boxes kept in earlier rounds ----
+      bool dead = !have;
+      const int kept0 = s.kept;
+      if (have) {
+        for (int i = 0; i < kept0 && !dead; ++i) dead = iou_suppresses(kbox[i], karea[i], mybox, myarea, p.iou_f, p.iou_inclusive);
+      }
+      const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
+      if (lane == 0) s.remv[warp] = dead_bits;
+      __syncthreads();
+      // ---- (e) upper-triangular suppression bitmask: thread i owns row i; mask[w][i] covers j in [32w, 32w+32) ----
+      if (have) {
+        for (int w = 0; w < kWords; ++w) {
+          unsigned int bits = 0u;
+          const int j0 = w * 32;
+          if (j0 + 31 > tid && j0 < K && !dead) {
+            const int jend = min(32, K - j0);
+            for (int jj = 0; jj < jend; ++jj) {
+              const int j = j0 + jj;
+              if (j > tid && iou_suppresses(mybox, myarea, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+            }
+          }
+          s.mask[w * (kK + 1) + tid] = bits;
+        }
+      }
+      __syncthreads();
+      // ---- (f) greedy scan by warp 0: lane w holds remv word w ----
+      if (warp == 0) {
+        unsigned int remv = lane < kWords ? s.remv[lane] : 0xffffffffu;
+        int kept = kept0;
+        const int nwords = (K + 31) / 32;
+        for (int wi = 0; wi < nwords && kept < p.max_det; ++wi) {
+          unsigned int cur = __shfl_sync(0xffffffffu, remv, wi);
+          const int nb = min(32, K - wi * 32);
+          unsigned int avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+          while (avail && kept < p.max_det) {
+            const int bit = __ffs(avail) - 1;
+            const int i = wi * 32 + bit;
+            if (lane == 0) { kbox[kept] = s.box[i]; karea[kept] = s.area[i]; kkey[kept] = big[off + i]; krank[kept] = processed + off + i; }
+            kept++;
+            if (lane < kWords) remv |= s.mask[lane * (kK + 1) + i];
+            cur = __shfl_sync(0xffffffffu, remv, wi);
+            avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+            avail &= ~((2u << bit) - 1u);          // only bits above the one just taken
           }
         }
-        s.mask[w * (kK + 1) + tid] = bits;
+        if (lane == 0) s.kept = kept;
       }
+      __syncthreads();
+      if (s.kept >= p.max_det) { done = true; break; }
     }
-    __syncthreads();
-    // ---- (f) greedy scan by warp 0: lane w holds remv word w ----
-    if (warp == 0) {
-      unsigned int remv = lane < kWords ? s.remv[lane] : 0xffffffffu;
-      int kept = kept0;
-      const int nwords = (K + 31) / 32;
-      for (int wi = 0; wi < nwords && kept < p.max_det; ++wi) {
-        unsigned int cur = __shfl_sync(0xffffffffu, remv, wi);
-        const int nb = min(32, K - wi * 32);
-        unsigned int avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-        while (avail && kept < p.max_det) {
-          const int bit = __ffs(avail) - 1;
-          const int i = wi * 32 + bit;
-          if (lane == 0) { kbox[kept] = s.box[i]; karea[kept] = s.area[i]; kkey[kept] = s.sel_key[i]; krank[kept] = processed + i; }
-          kept++;
-          if (lane < kWords) remv |= s.mask[lane * (kK + 1) + i];
-          cur = __shfl_sync(0xffffffffu, remv, wi);
-          avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          avail &= ~((2u << bit) - 1u);          // only bits above the one just taken
-        }
-      }
-      if (lane == 0) s.kept = kept;
-    }
-    __syncthreads();
-    processed += K;
+    processed += SK;
     prev_T = T;
     first = false;
-    if (s.kept >= p.max_det) break;
   }
 
   // ---- output rows x[i] = (x1,y1,x2,y2,conf,cls) (ops.py:327) ----
@@ -495,7 +505,7 @@ int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
   nms_filter_kernel<<<fgrid, kFilterThreads, 0, stream>>>(p);
   int rc = launch_status("nms_filter_kernel");
   if (rc) return rc;
-  const size_t smem = kSelSharedBytes + static_cast<size_t>(d->max_det) * (16 + 8 + 4 + 4);
+  const size_t smem = kSelSharedBytes + ((static_cast<size_t>(d->max_det) * (16 + 8 + 4 + 4) + 15) & ~size_t(15)) + static_cast<size_t>(kBig) * 8;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     DY_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
