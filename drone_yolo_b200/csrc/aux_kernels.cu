@@ -15,6 +15,7 @@ namespace dy {
 // ------------------------------------------------------------------------------------------------
 static constexpr int kStemThreads = 128;
 static constexpr int kStemMaxC = 128;
+static constexpr int kStemPix = 4;              // output pixels per thread (consecutive along W): weights are fetched once per 4 pixels
 
 __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __restrict__ in, int B, int H, int W,
                                                                  const float* __restrict__ weight,
@@ -30,15 +31,17 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
   __syncthreads();
 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo;
-  const long long pix = static_cast<long long>(blockIdx.x) * kStemThreads + threadIdx.x;
-  if (pix >= total) return;
-  const int wo = static_cast<int>(pix % Wo);
-  const int ho = static_cast<int>((pix / Wo) % Ho);
-  const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const int Wq = (Wo + kStemPix - 1) / kStemPix;          // pixel quads per output row
+  const long long total = static_cast<long long>(B) * Ho * Wq;
+  const long long item = static_cast<long long>(blockIdx.x) * kStemThreads + threadIdx.x;
+  if (item >= total) return;
+  const int wq = static_cast<int>(item % Wq);
+  const int ho = static_cast<int>((item / Wq) % Ho);
+  const int b = static_cast<int>(item / (static_cast<long long>(Wq) * Ho));
+  const int wo0 = wq * kStemPix;
 
-  float x[28];
-  x[27] = 0.f;
+  // 3 channels x 3 rows x 9 columns of input feed the 4 output pixels
+  float x[3][3][2 * kStemPix + 1];
   const size_t plane = static_cast<size_t>(H) * W;
   const float* img = in + static_cast<size_t>(b) * 3 * plane;
 #pragma unroll
@@ -46,35 +49,45 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int y = 2 * ho - 1 + ky;
+      const bool yok = (y >= 0) && (y < H);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = 2 * wo - 1 + kx;
-        const bool ok = (y >= 0) && (y < H) && (xx >= 0) && (xx < W);
-        x[c * 9 + ky * 3 + kx] = ok ? __ldg(img + c * plane + static_cast<size_t>(y) * W + xx) : 0.f;
+      for (int j = 0; j < 2 * kStemPix + 1; ++j) {
+        const int xx = 2 * wo0 - 1 + j;
+        x[c][ky][j] = (yok && xx >= 0 && xx < W) ? __ldg(img + c * plane + static_cast<size_t>(y) * W + xx) : 0.f;
       }
     }
 
-  __nv_bfloat16* op = out + static_cast<size_t>(pix) * out_ld;
+  __nv_bfloat16* op = out + (static_cast<size_t>(b) * Ho + ho) * Wo * out_ld + static_cast<size_t>(wo0) * out_ld;
   for (int co = 0; co < Cout; co += 8) {
-    float acc[8];
+    float acc[kStemPix][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float a = b_s[co + j];
       const float4* wr = reinterpret_cast<const float4*>(w_s + (co + j) * 28);
+      float wv[28];
 #pragma unroll
-      for (int k4 = 0; k4 < 7; ++k4) {
-        const float4 wv = wr[k4];
-        a = fmaf(x[4 * k4 + 0], wv.x, a);
-        a = fmaf(x[4 * k4 + 1], wv.y, a);
-        a = fmaf(x[4 * k4 + 2], wv.z, a);
-        a = fmaf(x[4 * k4 + 3], wv.w, a);
+      for (int k4 = 0; k4 < 7; ++k4) { const float4 t = wr[k4]; wv[4 * k4] = t.x; wv[4 * k4 + 1] = t.y; wv[4 * k4 + 2] = t.z; wv[4 * k4 + 3] = t.w; }
+      const float bj = b_s[co + j];
+#pragma unroll
+      for (int px = 0; px < kStemPix; ++px) {
+        float a = bj;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) a = fmaf(x[c][ky][2 * px + kx], wv[c * 9 + ky * 3 + kx], a);
+        acc[px][j] = silu_fast(a);
       }
-      acc[j] = silu_fast(a);
     }
-    uint4 o;
-    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(op + co) = o;
+#pragma unroll
+    for (int px = 0; px < kStemPix; ++px) {
+      if (wo0 + px < Wo) {
+        uint4 o;
+        o.x = pack_bf16(acc[px][0], acc[px][1]); o.y = pack_bf16(acc[px][2], acc[px][3]);
+        o.z = pack_bf16(acc[px][4], acc[px][5]); o.w = pack_bf16(acc[px][6], acc[px][7]);
+        *reinterpret_cast<uint4*>(op + static_cast<size_t>(px) * out_ld + co) = o;
+      }
+    }
   }
 }
 
@@ -85,7 +98,7 @@ int stem_launch(const float* in, int B, int H, int W, const float* weight, const
   DY_CHECK_ARG(Cout % 8 == 0 && Cout > 0 && Cout <= kStemMaxC, "stem: Cout must be a multiple of 8, <= %d", kStemMaxC);
   DY_CHECK_ARG(out_ld % 8 == 0 && out_ld >= Cout && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem: out slice must be 16B aligned");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const long long total = static_cast<long long>(B) * Ho * ((Wo + kStemPix - 1) / kStemPix);
   const long long blocks = (total + kStemThreads - 1) / kStemThreads;
   DY_CHECK_ARG(blocks < (1ll << 31), "stem: too many pixels");
   stem_conv_kernel<<<static_cast<unsigned>(blocks), kStemThreads, 0, stream>>>(in, B, H, W, weight, bias, Cout,

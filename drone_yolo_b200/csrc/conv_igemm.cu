@@ -32,6 +32,8 @@ static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxDynSmem = 227 * 1024 - 2048;
+static constexpr int kHaloW = 16, kHaloH = 18;   // MODE 3 halo tile: 8x16 output pixels + 1-pixel border, row pitch padded to 16 pixels
+static constexpr int kHaloBytes = kHaloW * kHaloH * 128;
 static constexpr int kMaxAcc = 8;              // accumulator stages in TMEM: min(8, 512 / BN), BN columns apart
 
 // Contiguous tile range per CTA: coordinates advance by carry instead of by integer division (the single-thread
@@ -63,7 +65,9 @@ struct TileIter {
 };
 
 // MODE = tap geometry, known at compile time so the single-thread loops carry no table look-ups:
-//   0: 1x1 (one tap), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (four parity views).
+//   0: 1x1 (one tap), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (four parity views),
+//   3: 3x3 stride 1 "halo": Cin <= 64, weights resident; ONE TMA box per tile brings the 8x16-pixel tile plus its border
+//      (16 x 18 pixels x 64 ch) and the nine taps are nine shifted UMMA descriptors over that single smem tile.
 // CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true): 128-byte or
 // 64-byte staging rows.  CW = 0 selects the generic register->global epilogue (odd widths).
 //
@@ -82,12 +86,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __shared__ __align__(16) float s_bias[256];
 
   constexpr int NTAPS = MODE == 0 ? 1 : 9;
+  constexpr int LOADS = MODE == 3 ? 1 : NTAPS;    // TMA boxes per (tile, 64-channel block)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
   const bool bres = p.b_resident != 0;
   const uint32_t bres_bytes = bres ? static_cast<uint32_t>(NTAPS * p.kblocks) * b_bytes : 0u;
-  const uint32_t stage_bytes = kABytes + (bres ? 0u : b_bytes);
+  const uint32_t stage_bytes = MODE == 3 ? static_cast<uint32_t>(kHaloBytes) : kABytes + (bres ? 0u : b_bytes);
   const int total_tiles = p.m_tiles * p.n_tiles;
 #ifdef DY_CONV_DEBUG
   const int dbg = p.dbg;   // DY_CONV_DBG knock-outs for bottleneck hunting: 1 = no epilogue work, 2 = no MMA, 4 = no A loads, 8 = no B loads
@@ -135,8 +140,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int TW = opaque(p.TW), TH = opaque(p.TH), TB = opaque(p.TB);
       for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(n_tiles, tiles_w, tiles_h)) {
         const int w0 = it.tw_i * TW, h0 = it.th_i * TH, b0 = it.tb_i * TB;
+        if constexpr (MODE == 3) {
+          const uint32_t fb = full0 + stage * 8;
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
+          mbar_arrive_expect_tx_a(fb, (dbg & 4) ? 0u : static_cast<uint32_t>(kHaloBytes));
+          if (!(dbg & 4)) tma_load_4d_a(stage0 + stage * stage_bytes, &p.tmA[0], fb, 0, w0 - 1, h0 - 1, b0);
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          continue;
+        }
 #pragma unroll
-        for (int t = 0; t < NTAPS; ++t) {
+        for (int t = 0; t < LOADS; ++t) {
           // compile-time tap geometry
           const int oy = MODE == 0 ? 0 : t / 3 - 1, ox = MODE == 0 ? 0 : t % 3 - 1;
           const int map = MODE == 2 ? ((oy & 1) * 2 + (ox & 1)) : 0;
@@ -193,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       // descriptor = constant high word | (address >> 4): only the low word changes
       const uint64_t desc_hi = umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
       const uint32_t desc_lo_const = static_cast<uint32_t>(umma_desc_sw128(0, 1024) & 0xffffffffull);   // LBO field
+      const uint64_t halo_hi = umma_desc_sw128(0, kHaloW * 128) & 0xffffffff00000000ull;               // SBO = one halo row of 16 pixels
       if (bres) mbar_wait_a(bres_b, 0);
       const uint32_t BNu = opaque(static_cast<uint32_t>(p.BN));
       int my_tiles = total_tiles / static_cast<int>(gridDim.x) + (static_cast<int>(blockIdx.x) < total_tiles % static_cast<int>(gridDim.x) ? 1 : 0);
@@ -200,6 +214,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * BNu;
+        if constexpr (MODE == 3) {
+          mbar_wait_a(full0 + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo_const | (((stage0 + stage * sbytes) & 0x3ffffu) >> 4);
+          const uint32_t b_lo = desc_lo_const | ((smem_base & 0x3ffffu) >> 4);
+          const uint32_t bstep = bbytes >> 4;
+          if (!(dbg & 2)) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              // tap (r, c): rows of the halo tile start (r*16 + c) pixels in; 8-pixel row groups are 16 pixels (2048 B) apart.
+              // The start is c rows into a 1024-byte swizzle atom.  Measured on B200: tcgen05 applies the 128B-swizzle XOR to
+              // ABSOLUTE shared-memory address bits (like TMA), so a row-shifted start needs no base-offset (setting the
+              // descriptor's base-offset field to c gives wrong results; DY_HALO_BASEOFF=1 reproduces that).
+              const uint32_t r = t / 3, c = t % 3;
+              const uint64_t hi = halo_hi | (p.halo_base_offset ? (static_cast<uint64_t>(c) << 49) : 0ull);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16_ss(d_tmem, hi | (a_lo + r * 128 + c * 8 + 2 * k), desc_hi | (b_lo + t * bstep + 2 * k), idesc, (t | k) ? 1u : 0u);
+            }
+          }
+          umma_commit_a(empty0 + stage * 8);
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          umma_commit_a(tfull0 + acc * 8);
+          if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         for (int kb = 0; kb < kiters; ++kb) {
           mbar_wait_a(full0 + stage * 8, phase);
           tc_fence_after();
@@ -480,6 +520,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     DY_CHECK_ARG(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "conv: residual slice must be 16B aligned");
 
   memset(p, 0, sizeof(*p));
+  bool halo = false;
   const int k = d->ksize, s = d->stride;
   const int Ho = (d->H + 2 * (k / 2) - k) / s + 1, Wo = (d->W + 2 * (k / 2) - k) / s + 1;
   const int cin_pad = round_up(d->Cin, kBlockK), cout_pad = round_up(d->Cout, 16);
@@ -511,7 +552,16 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   } else {
     p->Ho = Ho; p->Wo = Wo; p->B = d->B;
     pick_tile(Wo, Ho, d->B, &p->TW, &p->TH, &p->TB);
-    const uint32_t box[4] = {kBlockK, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+    // Halo mode: one activation load per tile instead of nine.  Needs a single 64-channel block, all weights resident and
+    // 8x16-pixel tiles that fill the map well.
+    {
+      const double eff = double(Wo) * Ho / (double(ceil_div(Wo, 8)) * 8 * ceil_div(Ho, 16) * 16);
+      const int b_all9 = 9 * p->BN * 128;
+      halo = (s == 1 && cin_pad == kBlockK && p->n_tiles == 1 && eff >= 0.8 &&
+              b_all9 + 2 * kHaloBytes + 2 * kABytes + 1024 <= kMaxDynSmem && getenv("DY_NO_HALO") == nullptr);
+      if (halo) { p->TW = 8; p->TH = 16; p->TB = 1; }
+    }
+    const uint32_t box[4] = {kBlockK, uint32_t(halo ? kHaloW : p->TW), uint32_t(halo ? kHaloH : p->TH), uint32_t(p->TB)};
     if (s == 1) {
       const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(d->W), uint64_t(d->H), uint64_t(d->B)};
       const uint64_t strides[3] = {ld * esz, uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
@@ -593,14 +643,16 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int budget = kMaxDynSmem - 1024 - 2 * kABytes;                  // minus alignment slack and the output staging tiles
   p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes) ? 1 : 0;   // leave room for >= 4 activation stages
   if (getenv("DY_NO_BRES")) p->b_resident = 0;
-  const int stage_bytes = kABytes + (p->b_resident ? 0 : b_tile);
+  if (halo) p->b_resident = 1;
+  const int stage_bytes = halo ? kHaloBytes : kABytes + (p->b_resident ? 0 : b_tile);
   int stages = (budget - (p->b_resident ? b_all : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p->stages = stages;
   p->nacc = 512 / p->BN < kMaxAcc ? 512 / p->BN : kMaxAcc;
   l->smem_bytes = (p->b_resident ? b_all : 0) + stages * stage_bytes + 2 * kABytes + 1024;
-  p->mode = (k == 1) ? 0 : (s == 1 ? 1 : 2);
+  p->mode = (k == 1) ? 0 : (halo ? 3 : (s == 1 ? 1 : 2));
+  { const char* e = getenv("DY_HALO_BASEOFF"); p->halo_base_offset = e ? atoi(e) : 0; }   // measured on B200: the swizzle XOR uses absolute smem address bits, the field must stay 0
   const int total = p->m_tiles * p->n_tiles;
   const int sms = num_sms();
   l->grid = total < sms ? total : sms;
@@ -642,6 +694,7 @@ static int conv_launch_m(const ConvParams* p, const ConvLaunch* l, cudaStream_t 
 int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   if (p->mode == 0) return conv_launch_m<0>(p, l, stream);
   if (p->mode == 1) return conv_launch_m<1>(p, l, stream);
+  if (p->mode == 3) return conv_launch_m<3>(p, l, stream);
   return conv_launch_m<2>(p, l, stream);
 }
 

@@ -19,7 +19,7 @@ struct ConvParams {
   int BN, n_tiles;
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
   int B, Ho, Wo, Cout;
-  int stages, nacc, b_resident, mode;
+  int stages, nacc, b_resident, mode, halo_base_offset;
   int use_tma_store;
   int dbg;
   void* out; int out_ld; int out_f32;

@@ -184,6 +184,7 @@ struct SelShared {
   unsigned int mask[kWords * (kK + 1)];
   unsigned int remv[kWords];
   int scan_tmp[kSelThreads / 32];
+  unsigned short kidx[kK];
   int sel_count;
   int kept;
   int found_bin; unsigned int found_below; unsigned int found_count;
@@ -350,23 +351,29 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
       if (lane == 0) s.remv[warp] = dead_bits;
       __syncthreads();
-      // ---- (e) upper-triangular suppression bitmask: thread i owns row i; mask[w][i] covers j in [32w, 32w+32) ----
+      // ---- (e) upper-triangular suppression bitmask: thread i owns row i; mask[w][i] covers j in [32w, 32w+32).
+      //      Only candidates that survived (d) matter, as rows and as columns.
       if (have) {
         for (int w = 0; w < kWords; ++w) {
           unsigned int bits = 0u;
           const int j0 = w * 32;
           if (j0 + 31 > tid && j0 < K && !dead) {
-            const int jend = min(32, K - j0);
-            for (int jj = 0; jj < jend; ++jj) {
+            unsigned int todo = ~s.remv[w];                          // columns still alive after (d)
+            if (K - j0 < 32) todo &= (1u << (K - j0)) - 1u;
+            if (tid >= j0) todo &= ~((2u << (tid - j0)) - 1u);       // only j > i
+            while (todo) {
+              const int jj = __ffs(todo) - 1;
+              todo &= todo - 1u;
               const int j = j0 + jj;
-              if (j > tid && iou_suppresses(mybox, myarea, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+              if (iou_suppresses(mybox, myarea, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
             }
           }
           s.mask[w * (kK + 1) + tid] = bits;
         }
       }
       __syncthreads();
-      // ---- (f) greedy scan by warp 0: lane w holds remv word w ----
+      // ---- (f) greedy scan by warp 0: lane w holds remv word w; only the index of each kept candidate is recorded here,
+      //      the box data is copied by all threads afterwards ----
       if (warp == 0) {
         unsigned int remv = lane < kWords ? s.remv[lane] : 0xffffffffu;
         int kept = kept0;
@@ -374,19 +381,28 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
         for (int wi = 0; wi < nwords && kept < p.max_det; ++wi) {
           unsigned int cur = __shfl_sync(0xffffffffu, remv, wi);
           const int nb = min(32, K - wi * 32);
-          unsigned int avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+          const unsigned int range = (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+          unsigned int avail = ~cur & range;
           while (avail && kept < p.max_det) {
             const int bit = __ffs(avail) - 1;
             const int i = wi * 32 + bit;
-            if (lane == 0) { kbox[kept] = s.box[i]; karea[kept] = s.area[i]; kkey[kept] = big[off + i]; krank[kept] = processed + off + i; }
+            if (lane == 0) s.kidx[kept - kept0] = static_cast<unsigned short>(i);
             kept++;
             if (lane < kWords) remv |= s.mask[lane * (kK + 1) + i];
             cur = __shfl_sync(0xffffffffu, remv, wi);
-            avail = ~cur & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-            avail &= ~((2u << bit) - 1u);          // only bits above the one just taken
+            avail = ~cur & range & ~((2u << bit) - 1u);    // only bits above the one just taken
           }
         }
         if (lane == 0) s.kept = kept;
+      }
+      __syncthreads();
+      {
+        const int newly = s.kept - kept0;
+        if (tid < newly) {
+          const int i = s.kidx[tid];
+          kbox[kept0 + tid] = s.box[i]; karea[kept0 + tid] = s.area[i];
+          kkey[kept0 + tid] = big[off + i]; krank[kept0 + tid] = processed + off + i;
+        }
       }
       __syncthreads();
       if (s.kept >= p.max_det) { done = true; break; }

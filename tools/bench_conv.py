@@ -16,7 +16,10 @@ LAYERS = [  # name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32
     ("P2 1x1 64->64", 64, 64, 64, 160, 160, 1, 1, False, 64, 96, False),
     ("P2 1x1 192->64", 64, 192, 64, 160, 160, 1, 1, False, 192, 96, False),
     ("P2 3x3 32->32 +res", 64, 32, 32, 160, 160, 3, 1, True, 96, 96, False),
+    ("P2 3x3 32->32 nores", 64, 32, 32, 160, 160, 3, 1, False, 96, 96, False),
+    ("P2 3x3 32->32 dense", 64, 32, 32, 160, 160, 3, 1, False, 32, 32, False),
     ("P2 3x3 64->64", 64, 64, 64, 160, 160, 3, 1, False, 128, 128, False),
+    ("P3 3x3 64->64", 64, 64, 64, 80, 80, 3, 1, False, 128, 128, False),
     ("P2 3x3 64->128", 64, 64, 128, 160, 160, 3, 1, False, 64, 128, False),
     ("P2 1x1 64->64 f32", 64, 64, 64, 160, 160, 1, 1, False, 128, 80, True),
     ("P1->P2 3x3 s2 32->64", 64, 32, 64, 320, 320, 3, 2, False, 32, 64, False),
