@@ -206,14 +206,43 @@ def run_ours(a):
         if world > 1:
             gather.gather(out, counts)
 
+    # ---- end-to-end arm: the batch crosses PCIe as pinned uint8 NCHW, exactly what the reference's predictor uploads for
+    # image sources (engine/predictor.py:127-135: uint8 -> .to(device) -> .float() -> /255 on the device).  H2D of batch
+    # i+1 runs on a copy stream while batch i computes; each step ends with the D2H read of its padded detections.
+    eng8 = Engine(model, a.batch, a.imgsz, dev, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou, max_det=a.max_det,
+                  cuda_graph=not a.no_graph, input_dtype=torch.uint8)
+    host8 = (host * 255.0).round().to(torch.uint8).pin_memory()
+    staging = [torch.empty_like(host8, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    slot_free = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "primed": False}
+
+    def enqueue_h2d(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot_free[i % 2])
+            staging[i % 2].copy_(host8, non_blocking=True)
+            h2d_done[i % 2].record(copy_stream)
+
     def step_e2e():
-        eng.images.copy_(host, non_blocking=True)                 # H2D of this step's inputs (pinned)
-        out, counts = eng.step()
+        i = e2e_state["i"]
+        cur = torch.cuda.current_stream(dev)
+        if not e2e_state["primed"]:
+            for ev in slot_free:
+                ev.record(cur)
+            enqueue_h2d(i)
+            e2e_state["primed"] = True
+        enqueue_h2d(i + 1)                                         # next batch's H2D overlaps this batch's compute
+        cur.wait_event(h2d_done[i % 2])
+        eng8.images.copy_(staging[i % 2], non_blocking=True)       # device-side hand-over into the graph's static input
+        slot_free[i % 2].record(cur)
+        out, counts = eng8.step()
         oa, ca = gather.gather(out, counts)
         if rank == 0:                                             # D2H of the step's result
             out_host.copy_(oa, non_blocking=True)
             cnt_host.copy_(ca, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        cur.synchronize()
+        e2e_state["i"] = i + 1
 
     def timed(fn, steps):
         barrier()
@@ -285,8 +314,9 @@ def run_ours(a):
                    "cuda_graph": not a.no_graph, "weights": "random-init (seed 0) + seeded BN/cls-bias recipe",
                    "l2": f"inputs larger than L2: {a.batch * 3 * a.imgsz * a.imgsz * 4 / 1e6:.0f} MB of images per step, "
                          f"arena {eng.plan.arena_bytes / 1e6:.0f} MB per micro-batch"},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host.numel() * 4 * world,
-                "d2h_bytes_per_step": out_host.numel() * 4 + cnt_host.numel() * 4},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host8.numel() * world,
+                "d2h_bytes_per_step": out_host.numel() * 4 + cnt_host.numel() * 4,
+                "input": "pinned uint8 NCHW batch (as the reference's predictor uploads image sources), H2D of batch i+1 overlapped with compute of batch i"},
         "gpu_launches": eng.launches_per_step * a.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv stack plan: stem + 78 tcgen05 convs + pool/upsample + decode)",

@@ -12,7 +12,7 @@ import torch
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libdroneyolo.so"
 
-DY_BF16, DY_F32 = 0, 1
+DY_BF16, DY_F32, DY_U8 = 0, 1, 2
 DY_ACT_NONE, DY_ACT_SILU = 0, 1
 DY_NHWC, DY_NCHW = 0, 1
 
@@ -62,7 +62,7 @@ SYMBOLS = {
     "dy_last_error": (C.c_char_p, []),
     "dy_device_check": (C.c_int, [C.c_int]),
     "dy_conv2d": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
-    "dy_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "dy_stem_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dy_sppf_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dy_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dy_dwconv3x3s2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -72,7 +72,7 @@ SYMBOLS = {
     "dy_program_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "dy_program_destroy": (None, [C.c_void_p]),
     "dy_program_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
-    "dy_program_add_stem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "dy_program_add_stem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "dy_program_add_sppf_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dy_program_add_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "dy_program_add_dwconv3x3s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

@@ -12,7 +12,7 @@ namespace dy {
 // forward declarations of the per-op launchers (decode.cu, nms.cu, aux_kernels.cu)
 int decode_launch(const dy_decode_desc* d, size_t out_offset_bytes, cudaStream_t stream);
 int nms_launch(const dy_nms_desc* d, cudaStream_t stream);
-int stem_launch(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
+int stem_launch(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
                 int out_ld, cudaStream_t stream);
 int sppf_pool_launch(void* buf, int B, int H, int W, int C, int ld, cudaStream_t stream);
 int upsample2x_launch(const void* in, int in_ld, int B, int H, int W, int C, void* out, int out_ld, cudaStream_t stream);
@@ -103,11 +103,11 @@ int dy_program_add_conv(dy_program* p, const dy_conv_desc* d) {
   return push(p, o, 1);
 }
 
-int dy_program_add_stem(dy_program* p, const float* in, int B, int H, int W, const float* weight, const float* bias,
+int dy_program_add_stem(dy_program* p, const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias,
                         int Cout, void* out, int out_ld) {
   DY_CHECK_ARG(p && in && weight && bias && out, "program_add_stem: null");
   dy::Op* o = new dy::Op();
-  o->kind = dy::OP_STEM; o->in = in; o->B = B; o->H = H; o->W = W; o->w = weight; o->b = bias; o->C = Cout; o->out = out; o->out_ld = out_ld;
+  o->kind = dy::OP_STEM; o->in = in; o->Cin = in_dtype; o->B = B; o->H = H; o->W = W; o->w = weight; o->b = bias; o->C = Cout; o->out = out; o->out_ld = out_ld;
   return push(p, o, 1);
 }
 
@@ -160,7 +160,7 @@ int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_byte
     switch (o->kind) {
       case dy::OP_CONV: rc = dy::conv_launch(&o->conv, &o->conv_launch, stream); break;
       case dy::OP_STEM:
-        rc = dy::stem_launch(reinterpret_cast<const float*>(static_cast<const char*>(o->in) + in_offset_bytes), o->B, o->H, o->W,
+        rc = dy::stem_launch(static_cast<const char*>(o->in) + in_offset_bytes, o->Cin, o->B, o->H, o->W,
                              o->w, o->b, o->C, o->out, o->out_ld, stream);
         break;
       case dy::OP_POOL: rc = dy::sppf_pool_launch(o->out, o->B, o->H, o->W, o->C, o->out_ld, stream); break;

@@ -17,7 +17,8 @@ static constexpr int kStemThreads = 128;
 static constexpr int kStemMaxC = 128;
 static constexpr int kStemPix = 4;              // output pixels per thread (consecutive along W): weights are fetched once per 4 pixels
 
-__global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __restrict__ in, int B, int H, int W,
+template <typename TIn>
+__global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const TIn* __restrict__ in, float in_scale, int B, int H, int W,
                                                                  const float* __restrict__ weight,
                                                                  const float* __restrict__ bias, int Cout,
                                                                  __nv_bfloat16* __restrict__ out, int out_ld) {
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
   // 3 channels x 3 rows x 9 columns of input feed the 4 output pixels
   float x[3][3][2 * kStemPix + 1];
   const size_t plane = static_cast<size_t>(H) * W;
-  const float* img = in + static_cast<size_t>(b) * 3 * plane;
+  const TIn* img = in + static_cast<size_t>(b) * 3 * plane;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
 #pragma unroll
       for (int j = 0; j < 2 * kStemPix + 1; ++j) {
         const int xx = 2 * wo0 - 1 + j;
-        x[c][ky][j] = (yok && xx >= 0 && xx < W) ? __ldg(img + c * plane + static_cast<size_t>(y) * W + xx) : 0.f;
+        x[c][ky][j] = (yok && xx >= 0 && xx < W) ? static_cast<float>(__ldg(img + c * plane + static_cast<size_t>(y) * W + xx)) * in_scale : 0.f;
       }
     }
 
@@ -91,8 +92,9 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
   }
 }
 
-int stem_launch(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
+int stem_launch(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
                 int out_ld, cudaStream_t stream) {
+  DY_CHECK_ARG(in_dtype == DY_F32 || in_dtype == DY_U8, "stem: input must be fp32 or uint8");
   DY_CHECK_ARG(in && weight && bias && out, "stem: null pointer");
   DY_CHECK_ARG(B > 0 && H > 0 && W > 0, "stem: bad shape");
   DY_CHECK_ARG(Cout % 8 == 0 && Cout > 0 && Cout <= kStemMaxC, "stem: Cout must be a multiple of 8, <= %d", kStemMaxC);
@@ -101,8 +103,12 @@ int stem_launch(const float* in, int B, int H, int W, const float* weight, const
   const long long total = static_cast<long long>(B) * Ho * ((Wo + kStemPix - 1) / kStemPix);
   const long long blocks = (total + kStemThreads - 1) / kStemThreads;
   DY_CHECK_ARG(blocks < (1ll << 31), "stem: too many pixels");
-  stem_conv_kernel<<<static_cast<unsigned>(blocks), kStemThreads, 0, stream>>>(in, B, H, W, weight, bias, Cout,
-                                                                              static_cast<__nv_bfloat16*>(out), out_ld);
+  if (in_dtype == DY_U8)
+    stem_conv_kernel<unsigned char><<<static_cast<unsigned>(blocks), kStemThreads, 0, stream>>>(
+        static_cast<const unsigned char*>(in), 1.f / 255.f, B, H, W, weight, bias, Cout, static_cast<__nv_bfloat16*>(out), out_ld);
+  else
+    stem_conv_kernel<float><<<static_cast<unsigned>(blocks), kStemThreads, 0, stream>>>(
+        static_cast<const float*>(in), 1.f, B, H, W, weight, bias, Cout, static_cast<__nv_bfloat16*>(out), out_ld);
   return launch_status("stem_conv_kernel");
 }
 
@@ -263,9 +269,9 @@ int dwconv_launch(const void* in, int in_ld, int B, int H, int W, int Cin, const
 
 }  // namespace dy
 
-extern "C" int dy_stem_conv(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
-                            int out_ld, void* stream) {
-  return dy::stem_launch(in, B, H, W, weight, bias, Cout, out, out_ld, static_cast<cudaStream_t>(stream));
+extern "C" int dy_stem_conv(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout,
+                            void* out, int out_ld, void* stream) {
+  return dy::stem_launch(in, in_dtype, B, H, W, weight, bias, Cout, out, out_ld, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dy_sppf_pool(void* buf, int B, int H, int W, int C, int ld, void* stream) {
   return dy::sppf_pool_launch(buf, B, H, W, C, ld, static_cast<cudaStream_t>(stream));

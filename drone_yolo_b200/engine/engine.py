@@ -17,15 +17,14 @@ from .. import kernels as K
 from .plan import LayerPlan
 
 
-def pick_micro_batch(model, batch: int, H: int, W: int, budget_mb: float = 48.0) -> int:
-    """Largest divisor of `batch` whose widest P2-level tensor pair (input + output of one conv) fits `budget_mb`:
-    keeps a layer's output L2-resident (126 MB) until its consumer runs."""
-    det = model.model[-1]
-    p2_ch = max(int(m.conv.in_channels) for m in (det.cv2[0][0], det.cv3[0][0]))
-    per_image = (H // 4) * (W // 4) * p2_ch * 3 * 2 * 2.0      # widest P2 concat is 3x the P2 width; in + out
+def pick_micro_batch(model, batch: int, H: int, W: int, cap: int = 64) -> int:
+    """Images per replay of the layer plan.  Measured on B200 (profiles/r01_summary.md): while the small layers are
+    still launch/latency-bound the largest micro-batch wins (s@640: 2 -> 2.0k, 8 -> 4.7k, 32 -> 6.6k, 64 -> 7.0k img/s
+    with the first kernels), so the default is the largest divisor of `batch` up to `cap`; smaller values keep a
+    layer's output L2-resident (126 MB) for its consumer and become interesting once the kernels are memory-bound."""
     best = 1
-    for d in range(1, batch + 1):
-        if batch % d == 0 and d * per_image <= budget_mb * 1e6:
+    for d in range(1, min(batch, cap) + 1):
+        if batch % d == 0:
             best = d
     return best
 
@@ -33,7 +32,8 @@ def pick_micro_batch(model, batch: int, H: int, W: int, budget_mb: float = 48.0)
 class Engine:
     def __init__(self, model, batch: int, imgsz, device, micro_batch: int = 0, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
-                 max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True):
+                 max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True,
+                 input_dtype: torch.dtype = torch.float32):
         device = torch.device(device)
         if device.type != "cuda":
             raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
@@ -45,7 +45,9 @@ class Engine:
         self.A = sum((H // int(s)) * (W // int(s)) for s in det.stride.tolist())
         self.mb = micro_batch if micro_batch and batch % micro_batch == 0 else pick_micro_batch(model, batch, H, W)
         with torch.cuda.device(device):
-            self.images = torch.zeros((batch, 3, H, W), device=device, dtype=torch.float32)
+            if input_dtype not in (torch.float32, torch.uint8):
+                raise _C.DroneYoloError("engine input must be float32 in [0,1] or uint8 0..255")
+            self.images = torch.zeros((batch, 3, H, W), device=device, dtype=input_dtype)
             self.y = torch.empty((batch, 4 + self.nc, self.A), device=device, dtype=torch.float32)
             self.plan = LayerPlan(model, self.mb, H, W, device, self.images, self.y)
             ml = bool(multi_label) and self.nc > 1
@@ -71,7 +73,7 @@ class Engine:
     def enqueue(self, stream: Optional[int] = None, nms: bool = True):
         """Enqueue the whole step on `stream` (default: torch's current stream)."""
         s = _C.stream_ptr(self.device) if stream is None else stream
-        in_bytes = self.mb * 3 * self.H * self.W * 4
+        in_bytes = self.mb * 3 * self.H * self.W * self.images.element_size()
         out_bytes = self.mb * (4 + self.nc) * self.A * 4
         for m in range(self.batch // self.mb):
             self.plan.run(m * in_bytes, m * out_bytes, s)

@@ -241,7 +241,8 @@ class LayerPlan:
                 self.keep.append((w, b))
                 out = self.tensor(op["out"])
                 optr, old, *_ = K.nhwc_view(out)
-                _C.check(lib.dy_program_add_stem(h, images.data_ptr(), mb, self.H, self.W, w.data_ptr(), b.data_ptr(),
+                in_dt = _C.DY_U8 if images.dtype == torch.uint8 else _C.DY_F32
+                _C.check(lib.dy_program_add_stem(h, images.data_ptr(), in_dt, mb, self.H, self.W, w.data_ptr(), b.data_ptr(),
                                                  w.shape[0], optr, old), "add_stem")
             elif kind == "conv":
                 if "mod" in op:

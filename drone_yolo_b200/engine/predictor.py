@@ -90,16 +90,16 @@ class DetectionPredictor:
         for cb in self.callbacks.get(event, []):
             cb(self)
 
-    def engine_for(self, B, H, W) -> Engine:
+    def engine_for(self, B, H, W, dtype=torch.float32) -> Engine:
         a = self.args
-        key = (B, H, W, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes else None, a.agnostic_nms, a.multi_label,
+        key = (B, H, W, dtype, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes else None, a.agnostic_nms, a.multi_label,
                a.micro_batch, a.cuda_graph)
         if key not in self.engines:
             if len(self.engines) >= 4:
                 self.engines.clear()
             self.engines[key] = Engine(self.model, B, (H, W), self.device, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou,
                                        max_det=a.max_det, classes=a.classes, agnostic=a.agnostic_nms,
-                                       multi_label=a.multi_label, cuda_graph=a.cuda_graph)
+                                       multi_label=a.multi_label, cuda_graph=a.cuda_graph, input_dtype=dtype)
         return self.engines[key]
 
     # ---- source handling (reference data/build.py:186-219, data/loaders.py) ---------------------
@@ -137,7 +137,9 @@ class DetectionPredictor:
             yield paths[i:i + bs], imgs[i:i + bs], None
 
     def preprocess(self, im0s):
-        """uint8 HWC BGR list -> pinned float32 (B,3,H,W) RGB in [0,1] (predictor.py:118-136, 147-163)."""
+        """uint8 HWC BGR list -> pinned uint8 (B,3,H,W) RGB (predictor.py:118-131, 147-163).  Like the reference, the
+        batch crosses PCIe as uint8; its `.float()` and `/ 255` (predictor.py:133-135) happen on the device, here inside the
+        stem kernel."""
         a = self.args
         shape = (a.imgsz, a.imgsz) if isinstance(a.imgsz, int) else tuple(a.imgsz)
         same = len({x.shape for x in im0s}) == 1
@@ -145,9 +147,9 @@ class DetectionPredictor:
         arr = np.ascontiguousarray(np.stack(lb)[..., ::-1].transpose(0, 3, 1, 2))
         key = arr.shape
         if key not in self._pinned:
-            self._pinned[key] = torch.empty(key, dtype=torch.float32).pin_memory()
+            self._pinned[key] = torch.empty(key, dtype=torch.uint8).pin_memory()
         buf = self._pinned[key]
-        torch.div(torch.from_numpy(arr), 255.0, out=buf)
+        buf.copy_(torch.from_numpy(arr))
         return buf
 
     # ---- the loop --------------------------------------------------------------------------------
@@ -166,7 +168,9 @@ class DetectionPredictor:
                 t0 = time.perf_counter()
                 im = tensor if tensor is not None else self.preprocess(im0s)
                 B, _, H, W = im.shape
-                eng = self.engine_for(B, H, W)
+                if im.dtype != torch.uint8:
+                    im = im.float()
+                eng = self.engine_for(B, H, W, im.dtype)
                 eng.images.copy_(im, non_blocking=True)            # H2D (or D2D) into the static input
                 torch.cuda.synchronize(self.device)
                 t1 = time.perf_counter()

@@ -107,16 +107,18 @@ def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, resid
 
 
 def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: NCHW fp32 contiguous [B,3,H,W]; w27 fp32 [Cout,27]; returns bf16 NHWC [B,Cout,H/2,W/2] view."""
+    """x: NCHW contiguous [B,3,H,W], fp32 in [0,1] or uint8 0..255 (scaled by 1/255 in the kernel); w27 fp32 [Cout,27];
+    returns bf16 NHWC [B,Cout,H/2,W/2] view."""
     _C.require_cuda(x, w27, bias)
-    if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[1] != 3:
-        raise _C.DroneYoloError("stem_conv expects a contiguous fp32 NCHW tensor with 3 channels")
+    if x.dtype not in (torch.float32, torch.uint8) or not x.is_contiguous() or x.shape[1] != 3:
+        raise _C.DroneYoloError("stem_conv expects a contiguous fp32 or uint8 NCHW tensor with 3 channels")
     B, _, H, W = x.shape
     cout = w27.shape[0]
     if out is None:
         out = empty_nhwc(B, cout, (H - 1) // 2 + 1, (W - 1) // 2 + 1, x.device)
     op, old, *_ = nhwc_view(out, "stem output")
-    _C.check(_C.lib().dy_stem_conv(x.data_ptr(), B, H, W, w27.data_ptr(), bias.data_ptr(), cout, op, old,
+    in_dt = _C.DY_U8 if x.dtype == torch.uint8 else _C.DY_F32
+    _C.check(_C.lib().dy_stem_conv(x.data_ptr(), in_dt, B, H, W, w27.data_ptr(), bias.data_ptr(), cout, op, old,
                                    _C.stream_ptr(x.device)), "dy_stem_conv")
     return out
 

@@ -130,7 +130,8 @@ class Conv(_PackedMixin, nn.Module):
         c = self.conv
         if self.is_stem:
             K._C.require_cuda(x)
-            return K.stem_conv(x.float().contiguous(), w, b, out=out)
+            x = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
+            return K.stem_conv(x, w, b, out=out)
         return K.conv2d(as_input(x), w, b, c.out_channels, c.kernel_size[0], c.stride[0], isinstance(self.act, nn.SiLU),
                         residual=residual, out=out, out_dtype=out_dtype)
 

@@ -32,7 +32,7 @@ typedef enum dy_status {
   DY_ERR_NOMEM = -4
 } dy_status;
 
-typedef enum dy_dtype { DY_BF16 = 0, DY_F32 = 1 } dy_dtype;
+typedef enum dy_dtype { DY_BF16 = 0, DY_F32 = 1, DY_U8 = 2 } dy_dtype;
 typedef enum dy_act { DY_ACT_NONE = 0, DY_ACT_SILU = 1 } dy_act;
 typedef enum dy_layout { DY_NHWC = 0, DY_NCHW = 1 } dy_layout;
 
@@ -72,11 +72,13 @@ int dy_conv2d(const dy_conv_desc* d, void* stream);
 /* Stem conv: 3x3 stride-2 pad-1 Conv(3->Cout)+bias+SiLU reading the predictor's input tensor.
  * Replaces: model.0 Conv of the YAMLs (cfg/models/v8/yolov8-p2-repvgg.yaml:17) together with the
  *           dtype cast of BasePredictor.preprocess (engine/predictor.py:132-135).
- * in      : NCHW [B,3,H,W] fp32 (values already /255, as LoadTensor supplies, data/loaders.py:516-584)
+ * in      : NCHW [B,3,H,W]; in_dtype DY_F32: values already in [0,1] (as LoadTensor supplies, data/loaders.py:516-584);
+ *           in_dtype DY_U8: raw 0..255 pixels as the predictor uploads them for image sources — the `/ 255` of
+ *           engine/predictor.py:134-135 is applied inside the kernel
  * weight  : fp32 [Cout][27] (cin-major: c*9 + ky*3 + kx), bias fp32 [Cout]; Cout % 8 == 0, <= 128
  * out     : bf16 NHWC [B,H/2,W/2,Cout] slice with pixel stride out_ld
  */
-int dy_stem_conv(const float* in, int B, int H, int W, const float* weight, const float* bias, int Cout,
+int dy_stem_conv(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout,
                  void* out, int out_ld, void* stream);
 
 /* SPPF pooling: y1=mp5(x), y2=mp5(y1), y3=mp5(y2) (5x5, stride 1, pad 2, -inf padding) in one pass.
@@ -152,7 +154,7 @@ typedef struct dy_program dy_program;
 int dy_program_create(dy_program** out);
 void dy_program_destroy(dy_program* p);
 int dy_program_add_conv(dy_program* p, const dy_conv_desc* d);
-int dy_program_add_stem(dy_program* p, const float* in, int B, int H, int W, const float* weight,
+int dy_program_add_stem(dy_program* p, const void* in, int in_dtype, int B, int H, int W, const float* weight,
                         const float* bias, int Cout, void* out, int out_ld);
 int dy_program_add_sppf_pool(dy_program* p, void* buf, int B, int H, int W, int C, int ld);
 int dy_program_add_upsample2x(dy_program* p, const void* in, int in_ld, int B, int H, int W, int C,

@@ -112,6 +112,10 @@ def test_stem_pool_upsample_dwconv(K, dev):
     w = (torch.randn(32, 3, 3, 3, generator=g) * 0.3).to(dev)
     b = torch.randn(32, generator=g).to(dev)
     close(K.stem_conv(x, w.reshape(32, 27).contiguous(), b), F.silu(F.conv2d(x, w, b, stride=2, padding=1)), 2e-2, 2e-2)
+    x8 = (x * 255).round().to(torch.uint8)                       # uint8 upload path: /255 happens inside the kernel
+    close(K.stem_conv(x8, w.reshape(32, 27).contiguous(), b), F.silu(F.conv2d(x8.float() / 255, w, b, stride=2, padding=1)), 2e-2, 2e-2)
+    xo = torch.rand(1, 3, 37, 51, generator=g).to(dev)           # odd sizes: ragged pixel quads and borders
+    close(K.stem_conv(xo, w.reshape(32, 27).contiguous(), b), F.silu(F.conv2d(xo, w, b, stride=2, padding=1)), 2e-2, 2e-2)
 
     for hw, c in ((20, 64), (40, 8), (7, 16)):
         buf = torch.zeros(2, hw, hw, 4 * c, device=dev, dtype=torch.bfloat16)
