@@ -22,7 +22,7 @@ OBJ_DIR = PKG / "build"
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-]
+] + (["-DDY_CONV_DEBUG"] if os.environ.get("DY_CONV_DEBUG_BUILD") else [])   # enables the DY_CONV_DBG knock-outs (tools/bench_conv.py)
 
 
 def _nvcc() -> str:

@@ -57,6 +57,8 @@ def run(name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32, iters=10):
 
 if __name__ == "__main__":
     import os
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    LAYERS = [l for l in LAYERS if only in l[0]]
     print("DY_CONV_DBG =", os.environ.get("DY_CONV_DBG", "0"))
     for layer in LAYERS:
         run(*layer)
