@@ -5,12 +5,15 @@ There is no CPU fallback: every op raises if the library is missing or the tenso
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libdroneyolo.so"
+if os.environ.get("DY_LIB"):                      # developer switch: a debug build (tools/trace_conv.py)
+    LIB_PATH = Path(os.environ["DY_LIB"])
 
 DY_BF16, DY_F32, DY_U8 = 0, 1, 2
 DY_ACT_NONE, DY_ACT_SILU = 0, 1

@@ -16,13 +16,17 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT_DIR = PKG / "lib"
-LIB = OUT_DIR / "libdroneyolo.so"
-OBJ_DIR = PKG / "build"
+DEBUG = bool(os.environ.get("DY_CONV_DEBUG_BUILD"))           # knock-outs + in-kernel timeline (tools/bench_conv.py, trace_conv.py)
+KNOCK = os.environ.get("DY_CONV_KNOCKOUT_BUILD", "")          # compile-time knock-out mask: release-speed "what bounds it" builds
+_TAG = "_dbg" if DEBUG else (f"_k{KNOCK}" if KNOCK else "")
+LIB = OUT_DIR / f"libdroneyolo{_TAG}.so"
+OBJ_DIR = PKG / f"build{_TAG}"
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-] + (["-DDY_CONV_DEBUG"] if os.environ.get("DY_CONV_DEBUG_BUILD") else [])   # enables the DY_CONV_DBG knock-outs (tools/bench_conv.py)
+] + (["-DDY_CONV_DEBUG"] if os.environ.get("DY_CONV_DEBUG_BUILD") else []) + (
+    [f"-DDY_CONV_DBG_CONST={int(os.environ['DY_CONV_KNOCKOUT_BUILD'])}"] if os.environ.get("DY_CONV_KNOCKOUT_BUILD") else [])
 
 
 def _nvcc() -> str:
@@ -49,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ and link lib/libdroneyolo.so. Skips when sources are unchanged."""
     OUT_DIR.mkdir(exist_ok=True)
     OBJ_DIR.mkdir(exist_ok=True)
-    stamp = OUT_DIR / "libdroneyolo.sha256"
+    stamp = OUT_DIR / (LIB.stem + ".sha256")
     digest = _digest()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == digest:
         return LIB

@@ -4,17 +4,20 @@
 // block.py:337-350,1480-1490).
 //
 // GEMM view: M = output pixels (B*Ho*Wo), N = Cout, K = k*k*Cin.  D[M,N] = A[M,K] * W[N,K]^T.
-//   * A is never materialised: for every filter tap (r,s) and every 64-channel block the TMA engine loads a
-//     [pixel tile x 64 ch] box of the NHWC activation, shifted by the tap offset; out-of-image coordinates are
-//     zero-filled by TMA, which IS the conv padding.  Stride-2 convs read four "parity" views of the input
-//     (even/odd rows x even/odd columns), so that every tap is again a dense box.
-//   * W is packed [tap][Cout_pad][Cin_pad] (K contiguous) and loaded by a 3-D TMA box.
-//   * Both operands land in shared memory in the 128B-swizzled K-major layout tcgen05.mma expects; one elected
-//     thread issues M=128 x N=BN x K=16 MMAs accumulating fp32 in TMEM (double-buffered accumulator).
-//   * 4 epilogue warps read the accumulator with tcgen05.ld, add the folded-BN bias, apply SiLU, add the optional
-//     residual, and store bf16 (or fp32) straight into a channel slice of the destination buffer (concat-write).
-//   * Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//     warps 4..7 = epilogue.
+//   * A is never materialised.  Generic 3x3: for every filter tap (r,s) and 64-channel block the TMA engine loads a
+//     [pixel tile x 64 ch] box of the NHWC activation shifted by the tap offset; out-of-image coordinates are zero-filled
+//     by TMA, which IS the conv padding.  Stride 2 reads four "parity" views of the input so every tap is a dense box.
+//     "Halo" modes (Cin <= 64, stride 1): ONE TMA box per tile brings the 8x16-pixel tile plus its 1-pixel border
+//     (10 x 18 pixels) and the nine taps are nine shifted UMMA descriptors over that single shared-memory tile
+//     (tcgen05 and TMA both apply the swizzle XOR to absolute shared-memory address bits, so a shifted start is legal).
+//     Cin <= 32 uses 64-byte rows (64B swizzle): half the shared-memory traffic and half the MMAs of the 64-channel form.
+//   * W is packed [tap][Cout_pad][Cin_pad] (K contiguous), loaded by a 3-D TMA box; small layers keep all taps resident.
+//   * One elected thread issues M=128 x N=BN x K=16 tcgen05.mma accumulating fp32 in TMEM (up to 8 accumulator stages).
+//   * Two independent epilogue groups (4 warps each, alternate tiles): tcgen05.ld -> bias -> SiLU (1 MUFU) -> + residual
+//     (TMA-prefetched into the staging tile) -> bf16/fp32 -> swizzled staging tile -> TMA store into the concat slice.
+//   * Persistent: grid = min(#tiles, #SMs); warp 0 = A producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = B producer,
+//     4..7 / 8..11 = epilogue groups.  The single-thread loops test the NEXT barrier before issuing the current work
+//     ("wait-ahead"): an mbarrier try_wait costs ~200 cycles even when the phase is already complete.
 #include "dy_common.cuh"
 #include "dy_ptx.cuh"
 #include "conv_igemm.h"
@@ -27,52 +30,73 @@ using namespace ptx;
 
 static constexpr int kBlockM = 128;           // UMMA M
 static constexpr int kBlockK = 64;            // bf16 per 128B swizzle row
-static constexpr int kABytes = kBlockM * 128; // one A stage
+static constexpr int kABytes = kBlockM * 128; // one 64-channel A block
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps
+static constexpr int kThreads = 384;          // 4 control warps + 2 x 4 epilogue warps
 static constexpr int kTmemCols = 512;
-static constexpr int kMaxDynSmem = 227 * 1024 - 2048;
-static constexpr int kHaloW = 16, kHaloH = 18;   // MODE 3 halo tile: 8x16 output pixels + 1-pixel border, row pitch padded to 16 pixels
-static constexpr int kHaloBytes = kHaloW * kHaloH * 128;
-static constexpr int kMaxAcc = 8;              // accumulator stages in TMEM: min(8, 512 / BN), BN columns apart
+static constexpr int kMaxBias = 1024;
+static constexpr int kMaxDynSmem = 227 * 1024 - 6 * 1024;   // static part: barriers + 4 KB of bias
+static constexpr int kHaloTW = 8, kHaloTH = 16;             // halo modes: 8x16 output pixels per tile
+static constexpr int kHaloRows = kHaloTH + 2;
+static constexpr int kMaxAcc = 8;             // accumulator stages in TMEM: min(8, 512 / BN), BN columns apart
 
-// Contiguous tile range per CTA: coordinates advance by carry instead of by integer division (the single-thread
-// producer / MMA loops are latency-bound, a div/mod chain per tile was ~600 cycles of pure overhead).
+// Contiguous tile range per CTA: coordinates advance by carry instead of by integer division.
 struct TileIter {
   int n_tile, tw_i, th_i, tb_i, remaining;
   __device__ __forceinline__ TileIter(const ConvParams& p, int cta, int ncta) {
-    const int total = p.m_tiles * p.n_tiles;
-    const int base = total / ncta, rem = total % ncta;
-    const int begin = cta * base + min(cta, rem);
-    remaining = base + (cta < rem ? 1 : 0);
-    n_tile = begin % p.n_tiles;
-    int m = begin / p.n_tiles;
+    int m;
+    if (p.n_split > 1) {                       // this CTA's n tile is fixed; its group shares the m tiles
+      n_tile = cta % p.n_split;
+      const int g = cta / p.n_split, ng = ncta / p.n_split;
+      const int base = p.m_tiles / ng, rem = p.m_tiles % ng;
+      m = g * base + min(g, rem);
+      remaining = base + (g < rem ? 1 : 0);
+    } else {
+      const int total = p.m_tiles * p.n_tiles;
+      const int base = total / ncta, rem = total % ncta;
+      const int begin = cta * base + min(cta, rem);
+      remaining = base + (cta < rem ? 1 : 0);
+      n_tile = begin % p.n_tiles;
+      m = begin / p.n_tiles;
+    }
     tw_i = m % p.tiles_w; m /= p.tiles_w;
     th_i = m % p.tiles_h;
     tb_i = m / p.tiles_h;
   }
   __device__ __forceinline__ bool valid() const { return remaining > 0; }
-  __device__ __forceinline__ void next(int n_tiles, int tiles_w, int tiles_h) {
+  // n_iter = number of n tiles iterated inside a CTA (1 when the n tile is fixed)
+  __device__ __forceinline__ void next(int n_iter, int tiles_w, int tiles_h) {
     --remaining;
-    if (++n_tile == n_tiles) {
+    if (n_iter > 1) {
+      if (++n_tile < n_iter) return;
       n_tile = 0;
-      if (++tw_i == tiles_w) {
-        tw_i = 0;
-        if (++th_i == tiles_h) { th_i = 0; ++tb_i; }
-      }
+    }
+    if (++tw_i == tiles_w) {
+      tw_i = 0;
+      if (++th_i == tiles_h) { th_i = 0; ++tb_i; }
     }
   }
 };
 
-// MODE = tap geometry, known at compile time so the single-thread loops carry no table look-ups:
-//   0: 1x1 (one tap), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (four parity views),
-//   3: 3x3 stride 1 "halo": Cin <= 64, weights resident; ONE TMA box per tile brings the 8x16-pixel tile plus its border
-//      (16 x 18 pixels x 64 ch) and the nine taps are nine shifted UMMA descriptors over that single smem tile.
-// CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true): 128-byte or
-// 64-byte staging rows.  CW = 0 selects the generic register->global epilogue (odd widths).
-//
-// Warp roles: 0 = A producer (TMA), 1 = MMA issuer, 2 = TMEM allocator, 3 = B producer (TMA), 4..11 = epilogue.
-// Shared memory: [resident weights (b_resident)] [stages x (A 16 KB [+ B BN*128])] [2 x 16 KB output staging].
+__device__ __forceinline__ void mbar_wait_unless(uint32_t bar, uint32_t parity, bool already) {
+  if (!already) mbar_wait_a(bar, parity);
+}
+
+// act(0.5*acc + hb) with hb = 0.5*bias for SiLU (h + h*tanh(h), one MUFU), acc + bias otherwise
+__device__ __forceinline__ float act1(uint32_t acc, float hb, bool silu) {
+  if (silu) {
+    const float h = fmaf(__uint_as_float(acc), 0.5f, hb);
+    return fmaf(h, tanh_fast(h), h);
+  }
+  return __uint_as_float(acc) + hb;
+}
+
+// MODE = tap geometry / A staging, known at compile time:
+//   0: 1x1 (one tap, flat pixel index), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (parity views),
+//   3: 3x3 stride 1 halo, one 64-channel block, 128-byte rows;  4: 3x3 stride 1 halo, Cin <= 32, 64-byte rows.
+// CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true).
+// CW = 0 selects the generic register->global epilogue (odd widths).
+// Shared memory: [resident weights][stages x (A blocks [+ B blocks])][2 groups x 2 staging tiles].
 template <int MODE, int CW, bool F32>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -81,42 +105,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
+  __shared__ __align__(8) uint64_t res_bar[4];          // [group][staging buffer]: residual tile landed
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_bias[kMaxBias];
 
   constexpr int NTAPS = MODE == 0 ? 1 : 9;
-  constexpr int LOADS = MODE == 3 ? 1 : NTAPS;    // TMA boxes per (tile, 64-channel block)
+  constexpr bool HALO = (MODE == 3 || MODE == 4);
+  constexpr int ROWB = MODE == 4 ? 64 : 128;            // bytes per pixel / per weight row in the A / B shared-memory tiles
+  constexpr int KSTEPS = ROWB / 32;                     // K = 16 MMAs per k-block
+  constexpr uint32_t LAYOUT = MODE == 4 ? 4u : 2u;      // UMMA layout type: 64B / 128B swizzle
+  constexpr int STG_BYTES = CW == 0 ? 0 : 128 * CW * (F32 ? 4 : 2);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * ROWB;
   const bool bres = p.b_resident != 0;
   const uint32_t bres_bytes = bres ? static_cast<uint32_t>(NTAPS * p.kblocks) * b_bytes : 0u;
-  const uint32_t stage_bytes = MODE == 3 ? static_cast<uint32_t>(kHaloBytes) : kABytes + (bres ? 0u : b_bytes);
-  const int total_tiles = p.m_tiles * p.n_tiles;
 #ifdef DY_CONV_DEBUG
   const int dbg = p.dbg;   // DY_CONV_DBG knock-outs for bottleneck hunting: 1 = no epilogue work, 2 = no MMA, 4 = no A loads, 8 = no B loads
+#define DY_TR(role, it, ev) do { if (p.trace && blockIdx.x == 0 && (it) < 96) p.trace[((role) * 96 + (it)) * 8 + (ev)] = clock64(); } while (0)
 #else
-  constexpr int dbg = 0;   // knock-outs compile away unless built with -DDY_CONV_DEBUG
+#ifdef DY_CONV_DBG_CONST
+  constexpr int dbg = DY_CONV_DBG_CONST;   // compile-time knock-out build (tools/build_knockouts.sh): release-speed loops
+#else
+  constexpr int dbg = 0;   // knock-outs and the timeline (DY_CONV_TRACE) compile away unless built with -DDY_CONV_DEBUG
+#endif
+#define DY_TR(role, it, ev) do { } while (0)
 #endif
   // `opaque` pins loop invariants in registers: without it the compiler re-derives the shared-window addresses
-  // (S2UR SR_CgaCtaId + ULEA) and re-reads kernel parameters inside the single-thread loops, whose cost is pure latency.
+  // and re-reads kernel parameters inside the single-thread loops, whose cost is pure latency.
   const uint32_t smem_base = opaque(smem_u32(smem));
-  const uint32_t stage0 = opaque(smem_base + bres_bytes);  // first pipeline stage (1024-aligned: bres_bytes is a multiple of 2048)
+  const uint32_t stage0 = opaque(smem_base + bres_bytes);  // first pipeline stage (1024-aligned: bres_bytes is a multiple of 1024)
   const uint32_t full0 = opaque(smem_u32(&full_bar[0])), empty0 = opaque(smem_u32(&empty_bar[0]));
   const uint32_t tfull0 = opaque(smem_u32(&tfull_bar[0])), tempty0 = opaque(smem_u32(&tempty_bar[0]));
   const uint32_t bres_b = opaque(smem_u32(&bres_bar));
   const int nstages = opaque(p.stages), nacc = opaque(p.nacc);
+  const uint32_t sbytes = opaque(static_cast<uint32_t>(p.stage_bytes));
+  const int kiters = NTAPS * p.kblocks, kps = HALO ? 1 : p.kps;
+  const int n_iter = p.n_split > 1 ? 1 : p.n_tiles;
 
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < p.nmaps; ++i) prefetch_tmap(&p.tmA[i]);
     prefetch_tmap(&p.tmB);
     if (CW > 0) prefetch_tmap(&p.tmO);
+    if (CW > 0 && p.has_res_tma) prefetch_tmap(&p.tmR);
   }
   if (warp == 1 && elect_one()) {
     const uint32_t producers = bres ? 1u : 2u;             // A thread (+ B thread) arrive on every full barrier
     for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(&bres_bar, 1);
     fence_mbar_init();
   }
@@ -131,36 +169,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   grid_dep_launch();
 
   if (warp == 0) {
-    // ===================== A producer: one TMA box per (tap, 64-channel block) =====================
+    // ===================== A producer =====================
     if (elect_one()) {
+      constexpr uint32_t lead = 1u;
       int stage = 0; uint32_t phase = 0;
+      [[maybe_unused]] int trk = 0;
       const uint32_t a_tx = (dbg & 4) ? 0u : static_cast<uint32_t>(p.TW * p.TH * p.TB) * 128u;
+      const uint32_t halo_tx = (dbg & 4) ? 0u : static_cast<uint32_t>(p.halo_pitch * kHaloRows * ROWB);
       const int kblocks = opaque(p.kblocks);
-      const int n_tiles = opaque(p.n_tiles), tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h);
+      const int tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h);
       const int TW = opaque(p.TW), TH = opaque(p.TH), TB = opaque(p.TB);
-      for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(n_tiles, tiles_w, tiles_h)) {
+      TileIter it(p, blockIdx.x, gridDim.x);
+      bool ok = mbar_try_wait_a(empty0, 1u);
+      [[maybe_unused]] const int kit = opaque(kiters), kps_r = opaque(kps), kcmax = opaque(kblocks * kBlockK);
+      [[maybe_unused]] const uint32_t e_minus_f = empty0 - full0;
+      [[maybe_unused]] uint32_t fullb = full0, dst = stage0;
+      for (; it.valid(); it.next(n_iter, tiles_w, tiles_h)) {
         const int w0 = it.tw_i * TW, h0 = it.th_i * TH, b0 = it.tb_i * TB;
-        if constexpr (MODE == 3) {
+        if constexpr (HALO) {
           const uint32_t fb = full0 + stage * 8;
-          mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
-          mbar_arrive_expect_tx_a(fb, (dbg & 4) ? 0u : static_cast<uint32_t>(kHaloBytes));
-          if (!(dbg & 4)) tma_load_4d_a(stage0 + stage * stage_bytes, &p.tmA[0], fb, 0, w0 - 1, h0 - 1, b0);
-          if (++stage == nstages) { stage = 0; phase ^= 1u; }
-          continue;
-        }
+          DY_TR(0, trk, 0);
+          mbar_wait_unless(empty0 + stage * 8, phase ^ 1u, ok);
+          DY_TR(0, trk, 1);
+          mbar_arrive_expect_tx_p(lead, fb, halo_tx);
+          const int ns = stage + 1 == nstages ? 0 : stage + 1;
+          const uint32_t nph = stage + 1 == nstages ? phase ^ 1u : phase;
+          ok = mbar_try_wait_a(empty0 + ns * 8, nph ^ 1u);                 // wait-ahead: resolved while the TMA issues
+          if (!(dbg & 4)) tma_load_4d_p(lead, stage0 + stage * sbytes, &p.tmA[0], fb, 0, w0 - 1, h0 - 1, b0);
+          DY_TR(0, trk, 2); ++trk;
+          stage = ns; phase = nph;
+        } else {
+          // lean loop: barrier / destination addresses are carried incrementally, coordinates advance by carry
+          int kc = 0, ox = MODE == 0 ? 0 : -1, oy = MODE == 0 ? 0 : -1;
+          for (int left = kit; left > 0; left -= kps_r) {
+            DY_TR(0, trk, 0);
+            mbar_wait_unless(fullb + e_minus_f, phase ^ 1u, ok);
+            DY_TR(0, trk, 1);
+            mbar_arrive_expect_tx_a(fullb, (left >= kps_r ? static_cast<uint32_t>(kps_r) : static_cast<uint32_t>(left)) * a_tx);
+            uint32_t nfullb = fullb + 8, ndst = dst + sbytes, nph = phase;
+            if (++stage == nstages) { stage = 0; nfullb = full0; ndst = stage0; nph ^= 1u; }
+            ok = mbar_try_wait_a(nfullb + e_minus_f, nph ^ 1u);
 #pragma unroll
-        for (int t = 0; t < LOADS; ++t) {
-          // compile-time tap geometry
-          const int oy = MODE == 0 ? 0 : t / 3 - 1, ox = MODE == 0 ? 0 : t % 3 - 1;
-          const int map = MODE == 2 ? ((oy & 1) * 2 + (ox & 1)) : 0;
-          const int dx = MODE == 2 ? (ox < 0 ? -1 : 0) : ox, dy = MODE == 2 ? (oy < 0 ? -1 : 0) : oy;
-          const CUtensorMap* tm = &p.tmA[map];
-          for (int kc = 0; kc < kblocks; ++kc) {
-            const uint32_t fb = full0 + stage * 8;
-            mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
-            mbar_arrive_expect_tx_a(fb, a_tx);
-            if (!(dbg & 4)) tma_load_4d_a(stage0 + stage * stage_bytes, tm, fb, kc * kBlockK, w0 + dx, h0 + dy, b0);
-            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            for (int j = 0; j < 2; ++j) {
+              if (j < kps_r && j < left) {
+                // stride 2: input coord 2*x+o -> parity view (o&1), coarse coord x + (o<0 ? -1 : 0)
+                const int map = MODE == 2 ? ((oy & 1) * 2 + (ox & 1)) : 0;
+                const int dx = MODE == 2 ? (ox < 0 ? -1 : 0) : ox, dy = MODE == 2 ? (oy < 0 ? -1 : 0) : oy;
+                if (!(dbg & 4)) tma_load_4d_a(dst + j * kABytes, &p.tmA[map], fullb, kc, w0 + dx, h0 + dy, b0);
+                kc += kBlockK;
+                if (kc == kcmax) { kc = 0; if (++ox == 2) { ox = -1; ++oy; } }
+              }
+            }
+            DY_TR(0, trk, 2); ++trk;
+            fullb = nfullb; dst = ndst; phase = nph;
           }
         }
       }
@@ -168,228 +229,323 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   } else if (warp == 3) {
     // ===================== B producer: weights, either once (resident) or per stage =====================
     if (elect_one()) {
+      constexpr uint32_t lead = 1u;
       const int kblocks = opaque(p.kblocks);
       if (bres) {
-        mbar_arrive_expect_tx_a(bres_b, (dbg & 8) ? 0u : bres_bytes);
+        const int n0 = (p.n_split > 1 ? static_cast<int>(blockIdx.x) % p.n_split : 0) * p.BN;
+        mbar_arrive_expect_tx_p(lead, bres_b, (dbg & 8) ? 0u : bres_bytes);
         if (!(dbg & 8)) {
           for (int t = 0; t < NTAPS; ++t)
             for (int kc = 0; kc < kblocks; ++kc)
-              tma_load_3d_a(smem_base + static_cast<uint32_t>(t * kblocks + kc) * b_bytes, &p.tmB, bres_b, kc * kBlockK, 0, t);
+              tma_load_3d_p(lead, smem_base + static_cast<uint32_t>(t * kblocks + kc) * b_bytes, &p.tmB, bres_b, kc * kBlockK, n0, t);
         }
       } else {
         int stage = 0; uint32_t phase = 0;
         const uint32_t b_tx = (dbg & 8) ? 0u : b_bytes;
-        const int n_tiles = opaque(p.n_tiles), tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h), BN = opaque(p.BN);
-        for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(n_tiles, tiles_w, tiles_h)) {
+        const int tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h), BN = opaque(p.BN);
+        const uint32_t b_off = static_cast<uint32_t>(kps) * kABytes;
+        const int kit = opaque(kiters), kps_r = opaque(kps), kcmax = opaque(kblocks * kBlockK);
+        const uint32_t e_minus_f = empty0 - full0;
+        const uint32_t bb = opaque(b_bytes);
+        uint32_t fullb = full0, dst = stage0 + b_off;
+        bool ok = mbar_try_wait_a(empty0, 1u);
+        for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(n_iter, tiles_w, tiles_h)) {
           const int n0 = it.n_tile * BN;
+          int kc = 0, t = 0;
+          for (int left = kit; left > 0; left -= kps_r) {
+            mbar_wait_unless(fullb + e_minus_f, phase ^ 1u, ok);
+            mbar_arrive_expect_tx_a(fullb, (left >= kps_r ? static_cast<uint32_t>(kps_r) : static_cast<uint32_t>(left)) * b_tx);
+            uint32_t nfullb = fullb + 8, ndst = dst + sbytes, nph = phase;
+            if (++stage == nstages) { stage = 0; nfullb = full0; ndst = stage0 + b_off; nph ^= 1u; }
+            ok = mbar_try_wait_a(nfullb + e_minus_f, nph ^ 1u);
 #pragma unroll
-          for (int t = 0; t < NTAPS; ++t) {
-            for (int kc = 0; kc < kblocks; ++kc) {
-              const uint32_t fb = full0 + stage * 8;
-              mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
-              mbar_arrive_expect_tx_a(fb, b_tx);
-              if (!(dbg & 8)) tma_load_3d_a(stage0 + stage * stage_bytes + kABytes, &p.tmB, fb, kc * kBlockK, n0, t);
-              if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            for (int j = 0; j < 2; ++j) {
+              if (j < kps_r && j < left) {
+                if (!(dbg & 8)) tma_load_3d_a(dst + j * bb, &p.tmB, fullb, kc, n0, t);
+                kc += kBlockK;
+                if (kc == kcmax) { kc = 0; ++t; }
+              }
             }
+            fullb = nfullb; dst = ndst; phase = nph;
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
+  } else if (warp == 1 || (HALO && warp == 2)) {
+    // ===================== MMA issuers =====================
+    // Halo modes: TWO issuing threads (warps 1 and 2) take alternate tiles, so one thread's barrier waits / commits overlap
+    // the other's MMA issue (the tensor pipe executes both streams; the accumulators and smem stages are disjoint).
+    // Other modes: one thread; every stage's first k-block carries the try_wait of the next stage (wait-ahead).
     if (elect_one()) {
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
+      constexpr uint32_t lead = 1u;
       const uint32_t idesc = umma_idesc_bf16(kBlockM, p.BN);
-      const int kiters = opaque(NTAPS * p.kblocks);
-      const uint32_t sbytes = opaque(stage_bytes), bbytes = opaque(b_bytes);
+      const uint32_t bbytes = opaque(b_bytes);
       // descriptor = constant high word | (address >> 4): only the low word changes
-      const uint64_t desc_hi = umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
-      const uint32_t desc_lo_const = static_cast<uint32_t>(umma_desc_sw128(0, 1024) & 0xffffffffull);   // LBO field
-      const uint64_t halo_hi = umma_desc_sw128(0, kHaloW * 128) & 0xffffffff00000000ull;               // SBO = one halo row of 16 pixels
-      if (bres) mbar_wait_a(bres_b, 0);
+      const uint64_t b_hi = umma_desc_kmajor(0, 8 * ROWB, LAYOUT) & 0xffffffff00000000ull;
+      const uint64_t a_hi = HALO ? (umma_desc_kmajor(0, static_cast<uint32_t>(p.halo_pitch) * ROWB, LAYOUT) & 0xffffffff00000000ull) : b_hi;
+      const uint32_t lo_const = static_cast<uint32_t>(umma_desc_kmajor(0, 1024, LAYOUT) & 0xffffffffull);   // LBO field
       const uint32_t BNu = opaque(static_cast<uint32_t>(p.BN));
-      int my_tiles = total_tiles / static_cast<int>(gridDim.x) + (static_cast<int>(blockIdx.x) < total_tiles % static_cast<int>(gridDim.x) ? 1 : 0);
-      for (; my_tiles > 0; --my_tiles) {
-        mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * BNu;
-        if constexpr (MODE == 3) {
-          mbar_wait_a(full0 + stage * 8, phase);
+      [[maybe_unused]] int trk = 0, trt = 0;
+      TileIter count_it(p, blockIdx.x, gridDim.x);
+      const int my_total = count_it.remaining;
+      if (bres) mbar_wait_a(bres_b, 0);
+      if constexpr (HALO) {
+        const int m = warp - 1;                                            // this issuer's tile parity
+        [[maybe_unused]] const int trole = m == 0 ? 1 : 2;
+        int stage = m % nstages; uint32_t phase = static_cast<uint32_t>(m / nstages) & 1u;
+        int acc = m % nacc; uint32_t acc_phase = static_cast<uint32_t>(m / nacc) & 1u;
+        bool okf = mbar_try_wait_a(full0 + stage * 8, phase);
+        bool oke = mbar_try_wait_a(tempty0 + acc * 8, acc_phase ^ 1u);
+        const uint32_t halo_rowstep = static_cast<uint32_t>(p.halo_pitch * ROWB) >> 4;   // descriptor units per halo row
+        const uint32_t b_lo = lo_const | ((smem_base & 0x3ffffu) >> 4);
+        const uint32_t bstep = bbytes >> 4;
+        for (int i = m; i < my_total; i += 2) {
+          DY_TR(trole, trk, 0);
+          mbar_wait_unless(tempty0 + acc * 8, acc_phase ^ 1u, oke);
+          mbar_wait_unless(full0 + stage * 8, phase, okf);
+          DY_TR(trole, trk, 1);
           tc_fence_after();
-          const uint32_t a_lo = desc_lo_const | (((stage0 + stage * sbytes) & 0x3ffffu) >> 4);
-          const uint32_t b_lo = desc_lo_const | ((smem_base & 0x3ffffu) >> 4);
-          const uint32_t bstep = bbytes >> 4;
+          int ns = stage + 2; uint32_t nph = phase;
+          if (ns >= nstages) { ns -= nstages; nph ^= 1u; }
+          int na = acc + 2; uint32_t nap = acc_phase;
+          if (na >= nacc) { na -= nacc; nap ^= 1u; }
+          okf = mbar_try_wait_a(full0 + ns * 8, nph);                      // wait-ahead for this issuer's next tile
+          oke = mbar_try_wait_a(tempty0 + na * 8, nap ^ 1u);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * BNu;
+          const uint32_t a_lo = lo_const | (((stage0 + stage * sbytes) & 0x3ffffu) >> 4);
           if (!(dbg & 2)) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              // tap (r, c): rows of the halo tile start (r*16 + c) pixels in; 8-pixel row groups are 16 pixels (2048 B) apart.
-              // The start is c rows into a 1024-byte swizzle atom.  Measured on B200: tcgen05 applies the 128B-swizzle XOR to
-              // ABSOLUTE shared-memory address bits (like TMA), so a row-shifted start needs no base-offset (setting the
-              // descriptor's base-offset field to c gives wrong results; DY_HALO_BASEOFF=1 reproduces that).
+              // tap (r, c): the 8-pixel row groups of the tile start (r*pitch + c) pixels into the halo tile and are one
+              // halo row (SBO) apart.  The swizzle XOR is applied to absolute address bits by TMA and tcgen05 alike, so
+              // neither the shifted start nor the SBO has to be a multiple of the 8-row swizzle atom.
               const uint32_t r = t / 3, c = t % 3;
-              const uint64_t hi = halo_hi | (p.halo_base_offset ? (static_cast<uint64_t>(c) << 49) : 0ull);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16_ss(d_tmem, hi | (a_lo + r * 128 + c * 8 + 2 * k), desc_hi | (b_lo + t * bstep + 2 * k), idesc, (t | k) ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16_ss_p(lead, d_tmem, a_hi | (a_lo + r * halo_rowstep + c * (ROWB >> 4) + 2 * k), b_hi | (b_lo + t * bstep + 2 * k), idesc,
+                               (t | k) ? 1u : 0u);
             }
           }
-          umma_commit_a(empty0 + stage * 8);
-          if (++stage == nstages) { stage = 0; phase ^= 1u; }
-          umma_commit_a(tfull0 + acc * 8);
-          if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
-          continue;
+          DY_TR(trole, trk, 2);
+          umma_commit_p(lead, empty0 + stage * 8);
+          umma_commit_p(lead, tfull0 + acc * 8);
+          DY_TR(trole, trk, 3); ++trk;
+          stage = ns; phase = nph; acc = na; acc_phase = nap;
         }
-        for (int kb = 0; kb < kiters; ++kb) {
-          mbar_wait_a(full0 + stage * 8, phase);
+      } else {
+        // Lean single-issuer loop: every address is carried incrementally (no multiplies, no parameter reloads); one asm block
+        // per stage issues the next stage's try_wait and all of the stage's MMAs.
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        bool okf = mbar_try_wait_a(full0, 0u);
+        bool oke = mbar_try_wait_a(tempty0, 1u);
+        const int bres_i = opaque(p.b_resident);
+        const int kit = opaque(kiters), kps_r = opaque(kps);
+        const uint32_t sstep = opaque(sbytes >> 4), bstep = opaque(bbytes >> 4);
+        const uint32_t a_lo0 = opaque(lo_const | ((stage0 & 0x3ffffu) >> 4));
+        const uint32_t bres_lo0 = opaque(lo_const | ((smem_base & 0x3ffffu) >> 4));
+        const uint32_t b_in_stage = opaque(static_cast<uint32_t>(kps) * (kABytes >> 4));
+        const uint32_t e_minus_f = empty0 - full0;
+        uint32_t a_lo = a_lo0, fullb = full0;
+        uint32_t tfb = tfull0, teb = tempty0, d_tmem = tmem_base;
+        for (int my_tiles = my_total; my_tiles > 0; --my_tiles) {
+          DY_TR(2, trt, 0);
+          mbar_wait_unless(teb, acc_phase ^ 1u, oke);
+          DY_TR(2, trt, 1);
           tc_fence_after();
-          const uint32_t a_addr = stage0 + stage * sbytes;
-          const uint32_t b_addr = bres ? smem_base + static_cast<uint32_t>(kb) * bbytes : a_addr + kABytes;
-          const uint32_t a_lo = desc_lo_const | ((a_addr & 0x3ffffu) >> 4), b_lo = desc_lo_const | ((b_addr & 0x3ffffu) >> 4);
-          if (!(dbg & 2)) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_ss(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kb | k) ? 1u : 0u);
+          uint32_t bres_lo = bres_lo0;
+          uint32_t accum = 0;
+          for (int left = kit; left > 0; left -= kps_r) {
+            DY_TR(1, trk, 0);
+            mbar_wait_unless(fullb, phase, okf);
+            DY_TR(1, trk, 1);
+            tc_fence_after();
+            uint32_t nfullb = fullb + 8, na_lo = a_lo + sstep, nph = phase;
+            if (++stage == nstages) { stage = 0; nfullb = full0; na_lo = a_lo0; nph ^= 1u; }
+            const uint32_t b_lo = bres_i ? bres_lo : a_lo + b_in_stage;
+            if (!(dbg & 2)) {
+              if (kps_r == 2 && left >= 2) okf = umma_bf16_ss_x8_waitahead(d_tmem, a_hi | a_lo, b_hi | b_lo, bstep, idesc, accum, nfullb, nph);
+              else okf = umma_bf16_ss_x4_waitahead(d_tmem, a_hi | a_lo, b_hi | b_lo, idesc, accum, nfullb, nph);
+            } else {
+              okf = mbar_try_wait_a(nfullb, nph);
+            }
+            accum = 1u;
+            bres_lo += bstep * static_cast<uint32_t>(kps_r);
+            DY_TR(1, trk, 2);
+            umma_commit_a(fullb + e_minus_f);           // frees the smem slot when these MMAs retire
+            DY_TR(1, trk, 3); ++trk;
+            fullb = nfullb; a_lo = na_lo; phase = nph;
           }
-          umma_commit_a(empty0 + stage * 8);          // frees the smem slot when these MMAs retire
-          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          uint32_t nteb = teb + 8, ntfb = tfb + 8, nd = d_tmem + BNu, nap = acc_phase;
+          if (++acc == nacc) { acc = 0; nteb = tempty0; ntfb = tfull0; nd = tmem_base; nap ^= 1u; }
+          oke = mbar_try_wait_a(nteb, nap ^ 1u);         // next accumulator stage: resolved behind the queued MMAs
+          umma_commit_a(tfb);                            // accumulator complete -> epilogue
+          DY_TR(2, trt, 2); ++trt;
+          teb = nteb; tfb = ntfb; d_tmem = nd; acc_phase = nap;
         }
-        umma_commit_a(tfull0 + acc * 8);              // accumulator complete -> epilogue
-        if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> bias/SiLU/residual -> (smem -> TMA store | global) ==========
-    // 8 warps: warp pair (q, half) owns TMEM lanes [32q, 32q+32) and one half of every CW-column chunk.
+    // Two groups of 4 warps take alternate tiles; inside a group warp q owns TMEM lanes [32q, 32q+32) == 32 pixels.
     const int ew = warp - 4;
+    const int g = ew >> 2;
     const int q = ew & 3;                           // TMEM lane quarter this warp may access (== warp % 4)
-    const int half = ew >> 2;
     const int row = q * 32 + lane;                  // accumulator row == pixel of the tile
-    const int etid = threadIdx.x - 4 * 32;          // 0..255
-    const int rows_valid = p.TW * p.TH * p.TB;
-    const bool issuer = (etid == 0);                // issues the TMA stores and owns their bulk groups
-    uint8_t* stage_base = smem + bres_bytes + static_cast<size_t>(p.stages) * stage_bytes;   // 2 x 16 KB output staging tiles
+    const bool leader = (threadIdx.x == 128 + g * 128);   // issues this group's TMA stores / residual loads
+    const int barid = 1 + g;
     const bool silu = (p.act == DY_ACT_SILU);
     const float bscale = silu ? 0.5f : 1.0f;        // SiLU path keeps 0.5*bias: h = 0.5*acc + 0.5*b in one FFMA
-    int acc = 0; uint32_t acc_phase = 0;
-    int store_ctr = 0;
-    const int wl = row % p.TW;                      // this thread's pixel inside the tile never changes
-    const int hl = (row / p.TW) % p.TH;
-    const int bl = row / (p.TW * p.TH);
-    for (TileIter it(p, blockIdx.x, gridDim.x); it.valid(); it.next(p.n_tiles, p.tiles_w, p.tiles_h)) {
+    {
+      const int nb = p.n_tiles * p.BN;              // == Cout padded to 16: the packed bias has that many entries
+      for (int i = threadIdx.x - 128; i < nb; i += 256) s_bias[i] = bscale * __ldg(p.bias + i);
+      named_bar_sync(3, 256);
+    }
+    [[maybe_unused]] int trt = 0;
+    [[maybe_unused]] const int trole = (lane == 0 && q == 0) ? 3 + g : 99;
+#ifdef DY_CONV_DEBUG
+#define DY_TRE(ev) do { if (trole < 99) DY_TR(trole, trt, ev); } while (0)
+#else
+#define DY_TRE(ev) do { } while (0)
+#endif
+    const int rows_valid = p.TW * p.TH * p.TB;
+    const uint32_t stg = smem_base + bres_bytes + static_cast<uint32_t>(p.stages) * sbytes + static_cast<uint32_t>(g * p.nbuf) * STG_BYTES;
+    const uint32_t resb0 = smem_u32(&res_bar[g * 2]);
+    const bool has_res = CW > 0 && !F32 && p.has_res_tma != 0;
+    const uint32_t res_tx = static_cast<uint32_t>(rows_valid) * CW * 2u;
+    TileIter it(p, blockIdx.x, gridDim.x);
+    if (g) it.next(n_iter, p.tiles_w, p.tiles_h);
+    int acc = g % nacc; uint32_t acc_phase = static_cast<uint32_t>(g / nacc) & 1u;
+    uint32_t sctr = 0;
+    const int nbuf = p.nbuf;
+    if (nbuf == 2 && has_res && leader && it.valid()) {          // residual of this group's first chunk
+      mbar_arrive_expect_tx_a(resb0, res_tx);
+      tma_load_4d_a(stg, &p.tmR, resb0, it.n_tile * p.BN, it.tw_i * p.TW, it.th_i * p.TH, it.tb_i * p.TB);
+    }
+    while (it.valid()) {
       const int w0 = it.tw_i * p.TW, h0 = it.th_i * p.TH, b0 = it.tb_i * p.TB;
-      const int w = w0 + wl, h = h0 + hl, b = b0 + bl;
-      const bool valid = (row < rows_valid) && (w < p.Wo) && (h < p.Ho) && (b < p.B);
-      const size_t pix = (static_cast<size_t>(b) * p.Ho + h) * p.Wo + w;
       const int n0 = it.n_tile * p.BN;
+      TileIter nx = it;                              // this group's next tile (two ahead)
+      nx.next(n_iter, p.tiles_w, p.tiles_h);
+      nx.next(n_iter, p.tiles_w, p.tiles_h);
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      DY_TRE(0);
+      mbar_wait_a(tfull0 + acc * 8, acc_phase);
+      DY_TRE(1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
 
       if constexpr (CW > 0) {
         // ---------------- fast path: every chunk is CW columns wide and leaves through a TMA store ----------------
-        constexpr int WC = CW / 2;                  // columns per warp
-        s_bias[etid] = (etid < p.BN) ? bscale * __ldg(p.bias + n0 + etid) : 0.f;   // visible after the chunk's first barrier
+        constexpr int ROWO = CW * (F32 ? 4 : 2);    // staging row bytes: 128 (128B swizzle) or 64 (64B swizzle)
         const int nchunks = (p.BN + CW - 1) / CW;   // a ragged last chunk only exists when n_tiles == 1: TMA clips columns >= Cout
         for (int c = 0; c < nchunks; ++c) {
-          const int col0 = c * CW + half * WC;
-          uint32_t r[WC];
-          if constexpr (WC == 32) tmem_ld_32x32b_x32(taddr + col0, r);
-          else tmem_ld_32x32b_x16(taddr + col0, r);
-          uint8_t* st = stage_base + (store_ctr & 1) * kABytes;
-          if (dbg & 1) {                             // knock-out: read the accumulator, release it, do nothing else
-            tmem_ld_wait();
-            if (c == nchunks - 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty_bar[acc]); }
-            continue;
+          const int buf = nbuf == 2 ? (sctr & 1) : 0;
+          const uint32_t st = stg + buf * STG_BYTES;
+          uint32_t r[CW];
+          tmem_ld_32x32b_x32(taddr + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          if constexpr (CW == 64) tmem_ld_32x32b_x32(taddr + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+          if (nbuf == 2) {
+            if (has_res) mbar_wait_a(resb0 + buf * 8, (sctr >> 1) & 1u);   // the residual tile has landed in `st`
+          } else {
+            // single staging tile: wait until the previous store has read it, then (residual) fetch this chunk's tile into it
+            if (leader) bulk_wait_group_read<0>();
+            named_bar_sync(barid, 128);
+            if (has_res) {
+              if (leader) {
+                mbar_arrive_expect_tx_a(resb0, res_tx);
+                tma_load_4d_a(st, &p.tmR, resb0, n0 + c * CW, w0, h0, b0);
+              }
+              mbar_wait_a(resb0, sctr & 1u);
+            }
           }
-          if (issuer) bulk_wait_group_read<1>();     // the store that last used this staging buffer has read it
-          named_bar_sync(1, 256);                    // ... and s_bias of this tile is complete
           tmem_ld_wait();
+          if (c == 0) DY_TRE(2);
           if (c == nchunks - 1) {                    // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
           }
-          float v[WC];
-          const float4* bs = reinterpret_cast<const float4*>(s_bias + col0);
-          if (silu) {
+          if (!(dbg & 1)) {
+            const uint32_t rowp = st + row * ROWO;
+            const float* bs = s_bias + n0 + c * CW;
+            if constexpr (F32) {
 #pragma unroll
-            for (int j = 0; j < WC / 4; ++j) {
-              const float4 hb = bs[j];
-              const float h0_ = fmaf(__uint_as_float(r[4 * j + 0]), 0.5f, hb.x), h1_ = fmaf(__uint_as_float(r[4 * j + 1]), 0.5f, hb.y);
-              const float h2_ = fmaf(__uint_as_float(r[4 * j + 2]), 0.5f, hb.z), h3_ = fmaf(__uint_as_float(r[4 * j + 3]), 0.5f, hb.w);
-              v[4 * j + 0] = fmaf(h0_, tanh_fast(h0_), h0_); v[4 * j + 1] = fmaf(h1_, tanh_fast(h1_), h1_);
-              v[4 * j + 2] = fmaf(h2_, tanh_fast(h2_), h2_); v[4 * j + 3] = fmaf(h3_, tanh_fast(h3_), h3_);
-            }
-          } else {
+              for (int gi = 0; gi < CW / 4; ++gi) {
+                const float4 hb = *reinterpret_cast<const float4*>(bs + 4 * gi);
+                float4 o;
+                o.x = act1(r[4 * gi + 0], hb.x, silu); o.y = act1(r[4 * gi + 1], hb.y, silu);
+                o.z = act1(r[4 * gi + 2], hb.z, silu); o.w = act1(r[4 * gi + 3], hb.w, silu);
+                sts128(rowp + ((gi ^ (row & 7)) << 4), make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < WC / 4; ++j) {
-              const float4 bb = bs[j];
-              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-            }
-          }
-          if (p.res != nullptr && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_ld + n0 + col0);
-#pragma unroll
-            for (int g = 0; g < WC / 8; ++g) {
-              if (n0 + col0 + 8 * g + 8 > p.Cout) break;     // ragged last chunk: stay inside the residual slice
-              const uint4 rr = __ldg(rp + g);
-              v[8 * g + 0] += bf16_lo(rr.x); v[8 * g + 1] += bf16_hi(rr.x); v[8 * g + 2] += bf16_lo(rr.y); v[8 * g + 3] += bf16_hi(rr.y);
-              v[8 * g + 4] += bf16_lo(rr.z); v[8 * g + 5] += bf16_hi(rr.z); v[8 * g + 6] += bf16_lo(rr.w); v[8 * g + 7] += bf16_hi(rr.w);
-            }
-          }
-          // stage the [128 px x CW ch] chunk: 128-byte rows are 128B-swizzled (CW == 64 bf16, CW == 32 fp32),
-          // 64-byte rows (CW == 32 bf16) are linear
-          if constexpr (F32) {
-            uint8_t* rowp = st + row * 128;
-#pragma unroll
-            for (int g = 0; g < WC / 4; ++g) {
-              const int chunk16 = half * (WC / 4) + g;
-              *reinterpret_cast<float4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            }
-          } else {
-            uint8_t* rowp = st + row * (CW * 2);
-#pragma unroll
-            for (int g = 0; g < WC / 8; ++g) {
-              uint4 o;
-              o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-              o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-              const int chunk16 = half * (WC / 8) + g;
-              if constexpr (CW == 64) *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = o;
-              else *reinterpret_cast<uint4*>(rowp + (chunk16 << 4)) = o;
+              for (int gi = 0; gi < CW / 8; ++gi) {
+                const int pos = (ROWO == 128) ? (gi ^ (row & 7)) : (gi ^ ((row >> 1) & 3));
+                const float4 hb0 = *reinterpret_cast<const float4*>(bs + 8 * gi), hb1 = *reinterpret_cast<const float4*>(bs + 8 * gi + 4);
+                float v0 = act1(r[8 * gi + 0], hb0.x, silu), v1 = act1(r[8 * gi + 1], hb0.y, silu);
+                float v2 = act1(r[8 * gi + 2], hb0.z, silu), v3 = act1(r[8 * gi + 3], hb0.w, silu);
+                float v4 = act1(r[8 * gi + 4], hb1.x, silu), v5 = act1(r[8 * gi + 5], hb1.y, silu);
+                float v6 = act1(r[8 * gi + 6], hb1.z, silu), v7 = act1(r[8 * gi + 7], hb1.w, silu);
+                const uint32_t sp = rowp + (pos << 4);
+                if (has_res) {
+                  const uint4 rr = lds128(sp);
+                  v0 += bf16_lo(rr.x); v1 += bf16_hi(rr.x); v2 += bf16_lo(rr.y); v3 += bf16_hi(rr.y);
+                  v4 += bf16_lo(rr.z); v5 += bf16_hi(rr.z); v6 += bf16_lo(rr.w); v7 += bf16_hi(rr.w);
+                }
+                uint4 o;
+                o.x = pack_bf16(v0, v1); o.y = pack_bf16(v2, v3); o.z = pack_bf16(v4, v5); o.w = pack_bf16(v6, v7);
+                sts128(sp, o);
+              }
             }
           }
+          if (c == 0) DY_TRE(3);
           fence_proxy_async_smem();
-          named_bar_sync(1, 256);
-          if (issuer) {
-            tma_store_4d(&p.tmO, st, n0 + c * CW, w0, h0, b0);
-            bulk_commit_group();
+          if (nbuf == 2 && leader) bulk_wait_group_read<0>();   // the previous store (other buffer) has read its tile: free after the barrier
+          named_bar_sync(barid, 128);
+          if (c == 0) DY_TRE(4);
+          if (leader) {
+            if (!(dbg & 1)) {
+              tma_store_4d_a(&p.tmO, st, n0 + c * CW, w0, h0, b0);
+              bulk_commit_group();
+            }
+            if (has_res && nbuf == 2) {              // prefetch the next chunk's residual into the buffer that just became free
+              const bool same_tile = c + 1 < nchunks;
+              if (same_tile || nx.valid()) {
+                const uint32_t rb = resb0 + (buf ^ 1) * 8;
+                mbar_arrive_expect_tx_a(rb, res_tx);
+                if (same_tile) tma_load_4d_a(stg + (buf ^ 1) * STG_BYTES, &p.tmR, rb, n0 + (c + 1) * CW, w0, h0, b0);
+                else tma_load_4d_a(stg + (buf ^ 1) * STG_BYTES, &p.tmR, rb, nx.n_tile * p.BN, nx.tw_i * p.TW, nx.th_i * p.TH, nx.tb_i * p.TB);
+              }
+            }
           }
-          ++store_ctr;
+          if (c == 0) DY_TRE(5);
+          ++sctr;
         }
       } else {
-        // ---------------- generic path: fp32 outputs and odd widths, registers -> global ----------------
-        const int nchunks = (p.BN + 63) >> 6;
+        // ---------------- generic path: odd widths, registers -> global ----------------
+        const int wl = row % p.TW, hl = (row / p.TW) % p.TH, bl = row / (p.TW * p.TH);
+        const int w = w0 + wl, h = h0 + hl, b = b0 + bl;
+        const bool valid = (row < rows_valid) && (w < p.Wo) && (h < p.Ho) && (b < p.B);
+        const size_t pix = (static_cast<size_t>(b) * p.Ho + h) * p.Wo + w;
+        const int nchunks = (p.BN + 31) >> 5;
         for (int c = 0; c < nchunks; ++c) {
-          const int col0 = c * 64 + half * 32;
-          const int ncols = min(32, p.BN - col0);    // 32, 16 or <= 0 (BN is a multiple of 16)
+          const int col0 = c * 32;
+          const int ncols = min(32, p.BN - col0);    // 32 or 16 (BN is a multiple of 16)
           uint32_t r[32];
           if (ncols >= 32) tmem_ld_32x32b_x32(taddr + col0, r);
-          else if (ncols > 0) tmem_ld_32x32b_x16(taddr + col0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          else tmem_ld_32x32b_x16(taddr + col0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld_wait();
           if (c == nchunks - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
           }
           const int n = n0 + col0;
-          if (ncols > 0 && valid && n < p.Cout) {
+          if (valid && n < p.Cout && !(dbg & 1)) {
             for (int j = 0; j < ncols; ++j) {
               if (n + j >= p.Cout) break;
-              float x = __uint_as_float(r[j]) + __ldg(p.bias + n + j);
-              if (silu) x = silu_fast(x);
+              float x = act1(r[j], s_bias[n + j], silu);
               if (p.res != nullptr) x += __bfloat162float(p.res[pix * p.res_ld + n + j]);
               r[j] = __float_as_uint(x);
             }
@@ -408,17 +564,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             } else {
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (g * 8 < ncols) {
-                  if (n + g * 8 + 8 <= p.Cout) {
+              for (int gi = 0; gi < 4; ++gi) {
+                if (gi * 8 < ncols) {
+                  if (n + gi * 8 + 8 <= p.Cout) {
                     uint4 o;
-                    o.x = pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
-                    o.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-                    o.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-                    o.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-                    reinterpret_cast<uint4*>(op)[g] = o;
+                    o.x = pack_bf16(__uint_as_float(r[8 * gi + 0]), __uint_as_float(r[8 * gi + 1]));
+                    o.y = pack_bf16(__uint_as_float(r[8 * gi + 2]), __uint_as_float(r[8 * gi + 3]));
+                    o.z = pack_bf16(__uint_as_float(r[8 * gi + 4]), __uint_as_float(r[8 * gi + 5]));
+                    o.w = pack_bf16(__uint_as_float(r[8 * gi + 6]), __uint_as_float(r[8 * gi + 7]));
+                    reinterpret_cast<uint4*>(op)[gi] = o;
                   } else {
-                    for (int e = 0; e < 8; ++e) if (n + g * 8 + e < p.Cout) op[g * 8 + e] = __float2bfloat16(__uint_as_float(r[g * 8 + e]));
+                    for (int e = 0; e < 8; ++e) if (n + gi * 8 + e < p.Cout) op[gi * 8 + e] = __float2bfloat16(__uint_as_float(r[gi * 8 + e]));
                   }
                 }
               }
@@ -426,9 +582,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
         }
       }
-      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
+      DY_TRE(7); ++trt;
+      acc += 2;
+      if (acc >= nacc) { acc -= nacc; acc_phase ^= 1u; }
+      it = nx;
     }
-    if (CW > 0 && issuer) bulk_wait_group<0>();     // all bulk stores complete before the CTA retires its smem
+    if (CW > 0 && leader) bulk_wait_group<0>();     // all bulk stores complete before the CTA retires its smem
   }
 
   tc_fence_before();
@@ -478,10 +637,25 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
   return DY_OK;
 }
 
-int conv_pick_bn(int cout_pad) {
-  int best = 16;
-  for (int bn = 16; bn <= 256; bn += 16)
-    if (cout_pad % bn == 0) best = bn;
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// N tile: a multiple of 16 dividing Cout_pad, <= max_bn.  Cost model per CTA (cycles): waves x (k-iterations x per-k-block
+// MMA time + per-tile overhead), where an M128 x N x K64 block costs 4 x max(N/2 [tensor pipe], 32 + N/4 [shared-memory
+// operand reads: tcgen05 reads 4 KB of A and N*32 B of B per K=16 step at 128 B/cycle]).
+static int pick_bn(int cout_pad, int m_tiles, int kiters, int max_bn) {
+  const int sms = num_sms();
+  int best = 16; double best_cost = 1e30;
+  for (int bn = 16; bn <= max_bn && bn <= 256; bn += 16) {
+    if (cout_pad % bn) continue;
+    const int n_tiles = cout_pad / bn;
+    const long long waves = ((long long)m_tiles * n_tiles + sms - 1) / sms;
+    const double per_k = 4.0 * (bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0);
+    const double cost = double(waves) * (kiters * per_k + 600.0) * (1.0 + 0.02 * (n_tiles - 1));   // + A re-reads per extra n tile
+    if (cost <= best_cost * 1.001) { if (cost < best_cost) best_cost = cost; best = bn; }          // ties -> wider tile
+  }
   return best;
 }
 
@@ -520,92 +694,104 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     DY_CHECK_ARG(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "conv: residual slice must be 16B aligned");
 
   memset(p, 0, sizeof(*p));
-  bool halo = false;
   const int k = d->ksize, s = d->stride;
   const int Ho = (d->H + 2 * (k / 2) - k) / s + 1, Wo = (d->W + 2 * (k / 2) - k) / s + 1;
   const int cin_pad = round_up(d->Cin, kBlockK), cout_pad = round_up(d->Cout, 16);
-  p->BN = conv_pick_bn(cout_pad);
-  p->n_tiles = cout_pad / p->BN;
-  p->kblocks = cin_pad / kBlockK;
+  DY_CHECK_ARG(cout_pad + 64 <= kMaxBias, "conv: Cout %d too large (max %d)", d->Cout, kMaxBias - 64);
+  const bool f32 = d->out_dtype == DY_F32;
   p->ntaps = k * k;
   p->Cout = d->Cout;
-  p->out = d->out; p->out_ld = d->out_ld; p->out_f32 = d->out_dtype == DY_F32;
+  p->out = d->out; p->out_ld = d->out_ld; p->out_f32 = f32;
   p->res = reinterpret_cast<const __nv_bfloat16*>(d->residual); p->res_ld = d->res_ld;
   p->bias = d->bias; p->act = d->act;
+  p->n_split = 1; p->kps = 1;
+  const int sms = num_sms();
 
+  // ---- mode, pixel tile, N tile ----
+  int mode = (k == 1) ? 0 : (s == 1 ? 1 : 2);
+  if (k == 3 && s == 1 && !env_int("DY_NO_HALO", 0)) {
+    const double eff = double(Wo) * Ho / (double(ceil_div(Wo, kHaloTW)) * kHaloTW * ceil_div(Ho, kHaloTH) * kHaloTH);
+    if (eff >= 0.8) {
+      if (d->Cin <= 32 && !env_int("DY_NO_K32", 0)) mode = 4;
+      else if (cin_pad == kBlockK) mode = 3;
+    }
+  }
+  if (mode >= 3) {
+    // halo: resident weights of ONE n tile per CTA (9 x BN rows); several n tiles -> static split of the grid
+    const int m_tiles = ceil_div(Wo, kHaloTW) * ceil_div(Ho, kHaloTH) * d->B;
+    const int bn = pick_bn(cout_pad, m_tiles, 9, mode == 4 ? 128 : 64);
+    if (cout_pad / bn > 4 || cout_pad / bn > sms) mode = 1;
+    else { p->BN = bn; p->n_tiles = cout_pad / bn; p->n_split = p->n_tiles; }
+  }
+  const bool halo = mode >= 3;
+  const int rowb = mode == 4 ? 64 : 128;
+  p->mode = mode;
+  p->kblocks = halo ? 1 : cin_pad / kBlockK;
+  const int kiters = p->ntaps * p->kblocks;
+  if (k == 1) {
+    const uint64_t M = uint64_t(d->B) * d->H * d->W;          // flat GEMM over all pixels: "image" of width M, height 1
+    DY_CHECK_ARG(M < (1ull << 31), "conv: too many pixels");
+    p->Ho = 1; p->Wo = int(M); p->B = 1;
+    p->TW = int(M < 128 ? M : 128); p->TH = 1; p->TB = 1;
+  } else {
+    p->Ho = Ho; p->Wo = Wo; p->B = d->B;
+    if (halo) { p->TW = kHaloTW; p->TH = kHaloTH; p->TB = 1; }
+    else pick_tile(Wo, Ho, d->B, &p->TW, &p->TH, &p->TB);
+  }
+  p->tiles_w = ceil_div(p->Wo, p->TW);
+  p->tiles_h = ceil_div(p->Ho, p->TH);
+  p->m_tiles = p->tiles_w * p->tiles_h * ceil_div(p->B, p->TB);
+  if (!halo) {
+    p->BN = pick_bn(cout_pad, p->m_tiles, kiters, env_int("DY_CONV_MAXBN", 256));
+    p->n_tiles = cout_pad / p->BN;
+  }
+  p->halo_pitch = halo ? (env_int("DY_HALO_PITCH16", 0) ? 16 : kHaloTW + 2) : 0;
+
+  // ---- activation tensor maps ----
   const uint64_t esz = 2;
   const uint64_t ld = d->in_ld;
   const char* base = reinterpret_cast<const char*>(d->in);
   if (k == 1) {
-    // flat GEMM over all pixels: "image" of width M, height 1
-    const uint64_t M = uint64_t(d->B) * d->H * d->W;
-    DY_CHECK_ARG(M < (1ull << 31), "conv: too many pixels");
-    p->Ho = 1; p->Wo = int(M); p->B = 1;
-    p->TW = int(M < 128 ? M : 128); p->TH = 1; p->TB = 1;
+    const uint64_t M = uint64_t(p->Wo);
     const uint64_t dims[4] = {uint64_t(d->Cin), M, 1, 1};
     const uint64_t strides[3] = {ld * esz, M * ld * esz, M * ld * esz};
     const uint32_t box[4] = {kBlockK, uint32_t(p->TW), 1, 1};
     int rc = encode_map(&p->tmA[0], base, 4, dims, strides, box);
     if (rc) return rc;
     p->nmaps = 1;
-    p->taps[0] = ConvTap{0, 0, 0, 0};
+  } else if (s == 1) {
+    const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(d->W), uint64_t(d->H), uint64_t(d->B)};
+    const uint64_t strides[3] = {ld * esz, uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
+    const uint32_t box[4] = {uint32_t(rowb / 2), uint32_t(halo ? p->halo_pitch : p->TW), uint32_t(halo ? kHaloRows : p->TH), uint32_t(p->TB)};
+    int rc = encode_map(&p->tmA[0], base, 4, dims, strides, box, mode == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    p->nmaps = 1;
   } else {
-    p->Ho = Ho; p->Wo = Wo; p->B = d->B;
-    pick_tile(Wo, Ho, d->B, &p->TW, &p->TH, &p->TB);
-    // Halo mode: one activation load per tile instead of nine.  Needs a single 64-channel block, all weights resident and
-    // 8x16-pixel tiles that fill the map well.
-    {
-      const double eff = double(Wo) * Ho / (double(ceil_div(Wo, 8)) * 8 * ceil_div(Ho, 16) * 16);
-      const int b_all9 = 9 * p->BN * 128;
-      halo = (s == 1 && cin_pad == kBlockK && p->n_tiles == 1 && eff >= 0.8 &&
-              b_all9 + 2 * kHaloBytes + 2 * kABytes + 1024 <= kMaxDynSmem && getenv("DY_NO_HALO") == nullptr);
-      if (halo) { p->TW = 8; p->TH = 16; p->TB = 1; }
-    }
-    const uint32_t box[4] = {kBlockK, uint32_t(halo ? kHaloW : p->TW), uint32_t(halo ? kHaloH : p->TH), uint32_t(p->TB)};
-    if (s == 1) {
-      const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t(d->W), uint64_t(d->H), uint64_t(d->B)};
-      const uint64_t strides[3] = {ld * esz, uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
-      int rc = encode_map(&p->tmA[0], base, 4, dims, strides, box);
-      if (rc) return rc;
-      p->nmaps = 1;
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) p->taps[r * 3 + c] = ConvTap{0, int16_t(c - 1), int16_t(r - 1), 0};
-    } else {
-      DY_CHECK_ARG(d->H >= 2 && d->W >= 2, "conv: stride-2 needs H,W >= 2");
-      for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-          const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((d->W - px + 1) / 2), uint64_t((d->H - py + 1) / 2), uint64_t(d->B)};
-          const uint64_t strides[3] = {2 * ld * esz, 2 * uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
-          int rc = encode_map(&p->tmA[py * 2 + px], base + (uint64_t(py) * d->W + px) * ld * esz, 4, dims, strides, box);
-          if (rc) return rc;
-        }
-      p->nmaps = 4;
-      // tap offset o in {-1,0,+1}: input coord 2*x+o  ->  parity (o&1), coarse coord x + (o<0 ? -1 : 0)
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-          const int oy = r - 1, ox = c - 1;
-          const int py = oy & 1, px = ox & 1;
-          p->taps[r * 3 + c] = ConvTap{int16_t(py * 2 + px), int16_t(ox < 0 ? -1 : 0), int16_t(oy < 0 ? -1 : 0), 0};
-        }
-    }
+    DY_CHECK_ARG(d->H >= 2 && d->W >= 2, "conv: stride-2 needs H,W >= 2");
+    const uint32_t box[4] = {kBlockK, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((d->W - px + 1) / 2), uint64_t((d->H - py + 1) / 2), uint64_t(d->B)};
+        const uint64_t strides[3] = {2 * ld * esz, 2 * uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
+        int rc = encode_map(&p->tmA[py * 2 + px], base + (uint64_t(py) * d->W + px) * ld * esz, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+    p->nmaps = 4;
   }
-  p->tiles_w = ceil_div(p->Wo, p->TW);
-  p->tiles_h = ceil_div(p->Ho, p->TH);
-  p->m_tiles = p->tiles_w * p->tiles_h * ceil_div(p->B, p->TB);
 
+  // ---- weight tensor map: [tap][Cout_pad][Cin_pad], box = one k-block of one n tile ----
   {
     const uint64_t dims[3] = {uint64_t(cin_pad), uint64_t(cout_pad), uint64_t(p->ntaps)};
     const uint64_t strides[2] = {uint64_t(cin_pad) * esz, uint64_t(cin_pad) * cout_pad * esz};
-    const uint32_t box[3] = {kBlockK, uint32_t(p->BN), 1};
-    int rc = encode_map(&p->tmB, d->weight, 3, dims, strides, box);
+    const uint32_t box[3] = {uint32_t(rowb / 2), uint32_t(p->BN), 1};
+    int rc = encode_map(&p->tmB, d->weight, 3, dims, strides, box, mode == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 
-  // output tensor map for the TMA-store epilogue (same pixel box as A, CW channels wide).  A ragged last chunk is only
-  // allowed with a single N tile, where every column >= BN is also >= Cout and is clipped by the tensor map.
+  // ---- output / residual tensor maps for the TMA-store epilogue (same pixel box as the tile, CW channels wide).  A ragged
+  // last chunk is only allowed with a single N tile, where every column >= BN is also >= Cout and is clipped by the map.
   p->use_tma_store = 0;
   {
-    const bool f32 = d->out_dtype == DY_F32;
     int cw = 0;
     // (TMA clips the innermost dimension at 16-byte granularity: the slice width must be a multiple of 16 bytes)
     if (f32) { if ((p->BN % 32 == 0 || p->n_tiles == 1) && d->Cout % 4 == 0) cw = 32; }
@@ -613,50 +799,101 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       if (p->BN % 64 == 0) cw = 64;
       else if (p->BN % 32 == 0) cw = 32;
       else if (p->n_tiles == 1) cw = p->BN > 32 ? 64 : 32;
+      // K-heavy tiles: the epilogue has time to spare, shared memory does not -> narrow staging tiles.  The 64-channel halo
+      // mode needs the room for a fourth activation stage (HBM latency x bandwidth ~ 64 KB in flight per SM).
+      if (cw == 64 && (mode == 3 || (!halo && kiters >= 8)) && p->BN % 32 == 0) cw = 32;
+      if (env_int("DY_CONV_CW", 0) == 32 && cw == 64 && p->BN % 32 == 0) cw = 32;
     }
+    if (d->residual && f32) cw = 0;                            // fp32 + residual: generic path (not used by the model)
     if (cw) {
       const uint64_t oes = out_esz;
-      const uint64_t old = d->out_ld;
       const uint32_t obox[4] = {uint32_t(cw), uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
-      const CUtensorMapSwizzle sw = (cw * out_esz == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+      const int rowo = cw * out_esz;
+      const CUtensorMapSwizzle sw = rowo == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-      int rc;
+      uint64_t dims[4], strides[3], rstrides[3];
       if (k == 1) {
-        const uint64_t M = uint64_t(d->B) * d->H * d->W;
-        const uint64_t dims[4] = {uint64_t(d->Cout), M, 1, 1};
-        const uint64_t strides[3] = {old * oes, M * old * oes, M * old * oes};
-        rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox, sw, dt);
+        const uint64_t M = uint64_t(p->Wo);
+        dims[0] = uint64_t(d->Cout); dims[1] = M; dims[2] = 1; dims[3] = 1;
+        strides[0] = uint64_t(d->out_ld) * oes; strides[1] = strides[2] = M * d->out_ld * oes;
+        rstrides[0] = uint64_t(d->res_ld) * 2; rstrides[1] = rstrides[2] = M * d->res_ld * 2;
       } else {
-        const uint64_t dims[4] = {uint64_t(d->Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
-        const uint64_t strides[3] = {old * oes, uint64_t(Wo) * old * oes, uint64_t(Ho) * Wo * old * oes};
-        rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox, sw, dt);
+        dims[0] = uint64_t(d->Cout); dims[1] = uint64_t(Wo); dims[2] = uint64_t(Ho); dims[3] = uint64_t(d->B);
+        strides[0] = uint64_t(d->out_ld) * oes; strides[1] = uint64_t(Wo) * d->out_ld * oes; strides[2] = uint64_t(Ho) * Wo * d->out_ld * oes;
+        rstrides[0] = uint64_t(d->res_ld) * 2; rstrides[1] = uint64_t(Wo) * d->res_ld * 2; rstrides[2] = uint64_t(Ho) * Wo * d->res_ld * 2;
       }
+      int rc = encode_map(&p->tmO, d->out, 4, dims, strides, obox, sw, dt);
       if (rc) return rc;
+      if (d->residual) {
+        rc = encode_map(&p->tmR, d->residual, 4, dims, rstrides, obox, sw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
+        p->has_res_tma = 1;
+      }
       p->use_tma_store = cw;
     }
   }
 
-  // Shared-memory plan.  Small layers keep ALL their weights resident (loaded once per CTA): the per-stage traffic and the
-  // per-stage TMA issue then only cover the activation tile.  Everything else streams B next to A.
-  const int b_tile = p->BN * 128;
+  // ---- shared-memory plan ----
+  // Small layers keep ALL their weights resident (loaded once per CTA): the per-stage traffic and TMA issue then only
+  // cover the activation tile.  Everything else streams B next to A.
+  const int cw = p->use_tma_store;
+  // K-heavy generic tiles: one staging tile per group (the epilogue has slack), the room goes to fatter pipeline stages
+  p->nbuf = (!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) ? 1 : 2;
+  const int staging = 2 * p->nbuf * 128 * cw * out_esz;                     // 2 groups x nbuf tiles
+  const int budget = kMaxDynSmem - 1024 - staging;
+  const int b_tile = p->BN * rowb;
   const int b_all = p->ntaps * p->kblocks * b_tile;
-  const int budget = kMaxDynSmem - 1024 - 2 * kABytes;                  // minus alignment slack and the output staging tiles
-  p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes) ? 1 : 0;   // leave room for >= 4 activation stages
-  if (getenv("DY_NO_BRES")) p->b_resident = 0;
-  if (halo) p->b_resident = 1;
-  const int stage_bytes = halo ? kHaloBytes : kABytes + (p->b_resident ? 0 : b_tile);
-  int stages = (budget - (p->b_resident ? b_all : 0)) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
-  p->stages = stages;
-  p->nacc = 512 / p->BN < kMaxAcc ? 512 / p->BN : kMaxAcc;
-  l->smem_bytes = (p->b_resident ? b_all : 0) + stages * stage_bytes + 2 * kABytes + 1024;
-  p->mode = (k == 1) ? 0 : (halo ? 3 : (s == 1 ? 1 : 2));
-  { const char* e = getenv("DY_HALO_BASEOFF"); p->halo_base_offset = e ? atoi(e) : 0; }   // measured on B200: the swizzle XOR uses absolute smem address bits, the field must stay 0
+  if (halo) {
+    p->b_resident = 1;
+    p->stage_bytes = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
+    int stages = (budget - b_all) / p->stage_bytes;
+    DY_CHECK_ARG(stages >= 2, "conv: halo mode does not fit shared memory (BN %d)", p->BN);
+    p->stages = stages > kMaxStages ? kMaxStages : stages;
+    const int cap = env_int("DY_HALO_STAGES", 0);
+    if (cap >= 2 && cap < p->stages) p->stages = cap;
+    // two MMA issuers take alternate tiles: with an EVEN ring every stage (and accumulator) always belongs to the same
+    // issuer, which the mbarrier parity test needs (a waiter may be at most one phase ahead of the barrier)
+    p->stages &= ~1;
+  } else {
+    p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes && !env_int("DY_NO_BRES", 0)) ? 1 : 0;   // leave room for >= 4 activation stages
+    const int per_k = kABytes + (p->b_resident ? 0 : b_tile);
+    const int avail = budget - (p->b_resident ? b_all : 0);
+    // k-blocks per stage: the issuing thread pays ~300 cycles per stage (barrier wait, commit), a k-block is 4 x max(BN/2,
+    // 32 + BN/4) cycles of MMA: fatten the stages of narrow tiles until a stage holds >= ~512 cycles, keeping >= 3 stages.
+    int kps = env_int("DY_CONV_KPS", 0);
+    if (kps < 1) kps = p->BN >= 256 ? 1 : 2;
+    if (kps > 2) kps = 2;
+    while (kps > 1 && (kps > kiters || avail / (kps * per_k) < 3)) --kps;
+    p->kps = kps;
+    p->stage_bytes = kps * per_k;
+    int stages = avail / p->stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    DY_CHECK_ARG(stages >= 2, "conv: pipeline does not fit shared memory (BN %d)", p->BN);
+    p->stages = stages;
+  }
+  // accumulator stages: BN columns apart; a ragged last chunk reads up to CW-1 columns past its stage
+  {
+    const int overrun = cw ? (ceil_div(p->BN, cw) * cw - p->BN) : (ceil_div(p->BN, 32) * 32 - p->BN);
+    int nacc = (kTmemCols - overrun) / p->BN;
+    if (nacc > kMaxAcc) nacc = kMaxAcc;
+    if (halo) nacc &= ~1;
+    DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
+    p->nacc = nacc;
+  }
+  l->smem_bytes = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + staging + 1024;
   const int total = p->m_tiles * p->n_tiles;
-  const int sms = num_sms();
-  l->grid = total < sms ? total : sms;
-  { const char* e = getenv("DY_CONV_DBG"); p->dbg = e ? atoi(e) : 0; }
+  if (p->n_split > 1) {
+    const int per = sms / p->n_split < p->m_tiles ? sms / p->n_split : p->m_tiles;
+    l->grid = per * p->n_split;
+  } else {
+    l->grid = total < sms ? total : sms;
+  }
+  p->dbg = env_int("DY_CONV_DBG", 0);
+  { const char* e = getenv("DY_CONV_TRACE"); p->trace = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+  if (env_int("DY_CONV_VERBOSE", 0))
+    fprintf(stderr, "conv k%d s%d %d->%d %dx%dx%d: mode %d BN %d n_tiles %d n_split %d tile %dx%dx%d m_tiles %d kps %d stages %d x %d B nacc %d bres %d cw %d res_tma %d smem %d grid %d\n",
+            k, s, d->Cin, d->Cout, d->B, d->H, d->W, p->mode, p->BN, p->n_tiles, p->n_split, p->TW, p->TH, p->TB, p->m_tiles, p->kps,
+            p->stages, p->stage_bytes, p->nacc, p->b_resident, cw * 10 + p->nbuf, p->has_res_tma, l->smem_bytes, l->grid);
   return DY_OK;
 }
 
@@ -664,7 +901,7 @@ template <int MODE, int CW, bool F32>
 static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   static int max_smem_set = 0;
   if (max_smem_set < l->smem_bytes) {
-    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 2 KB
+    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 6 KB
     DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     max_smem_set = kMaxDynSmem;
   }
@@ -692,10 +929,13 @@ static int conv_launch_m(const ConvParams* p, const ConvLaunch* l, cudaStream_t 
 }
 
 int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
-  if (p->mode == 0) return conv_launch_m<0>(p, l, stream);
-  if (p->mode == 1) return conv_launch_m<1>(p, l, stream);
-  if (p->mode == 3) return conv_launch_m<3>(p, l, stream);
-  return conv_launch_m<2>(p, l, stream);
+  switch (p->mode) {
+    case 0: return conv_launch_m<0>(p, l, stream);
+    case 1: return conv_launch_m<1>(p, l, stream);
+    case 2: return conv_launch_m<2>(p, l, stream);
+    case 3: return conv_launch_m<3>(p, l, stream);
+    default: return conv_launch_m<4>(p, l, stream);
+  }
 }
 
 }  // namespace dy

@@ -8,20 +8,23 @@
 
 namespace dy {
 
-struct ConvTap { int16_t map, dx, dy, pad; };   // which A tensor map, and the box shift in that map's pixels
-
 struct ConvParams {
   CUtensorMap tmA[4];      // activation views (1 for stride 1, 4 parity views for stride 2)
   CUtensorMap tmB;         // packed weights [tap][Cout_pad][Cin_pad]
-  CUtensorMap tmO;         // bf16 output slice (TMA-store epilogue)
-  ConvTap taps[9];
+  CUtensorMap tmO;         // output slice (TMA-store epilogue)
+  CUtensorMap tmR;         // residual slice, same box as tmO (TMA-prefetched into the staging tile)
   int nmaps, ntaps, kblocks;
-  int BN, n_tiles;
+  int BN, n_tiles, n_split;            // n_split > 1: every CTA owns ONE n tile for its whole life (weights resident per CTA)
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
   int B, Ho, Wo, Cout;
-  int stages, nacc, b_resident, mode, halo_base_offset;
-  int use_tma_store;
+  int stages, stage_bytes, kps;        // pipeline stages, bytes per stage, 64-channel k-blocks per stage
+  int nacc, b_resident, mode;
+  int halo_pitch;                      // pixels per halo-tile row in shared memory (TW + 2)
+  int use_tma_store;                   // chunk width CW of the TMA-store epilogue (0 = generic register->global path)
+  int has_res_tma;
+  int nbuf;                            // staging tiles per epilogue group (2, or 1 when shared memory is short)
   int dbg;
+  unsigned long long* trace;           // debug builds only (DY_CONV_TRACE)
   void* out; int out_ld; int out_f32;
   const __nv_bfloat16* res; int res_ld;
   const float* bias; int act;
@@ -29,7 +32,6 @@ struct ConvParams {
 
 struct ConvLaunch { int grid; int smem_bytes; };
 
-int conv_pick_bn(int cout_pad);
 int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l);
 int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream);
 

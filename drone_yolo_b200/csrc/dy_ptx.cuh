@@ -85,6 +85,59 @@ __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- lane-predicated forms ---------------------------------------------------------------------
+// The producer / MMA loops run WARP-UNIFORM (all 32 lanes execute the loop, so ptxas keeps stage counters, barrier
+// addresses and descriptors in uniform registers instead of converting per-thread values with R2UR on every use); only
+// the instructions with side effects are predicated on the elected lane.
+__device__ __forceinline__ void mbar_arrive_expect_tx_p(uint32_t lead, uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred L;\n\tsetp.ne.b32 L, %0, 0;\n\t@L mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %2;\n\t}"
+               ::"r"(lead), "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_p(uint32_t lead, uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred L;\n\tsetp.ne.b32 L, %0, 0;\n\t"
+      "@L cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%4, %5, %6, %7}], [%3];\n\t}"
+      ::"r"(lead), "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(uint32_t lead, uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred L;\n\tsetp.ne.b32 L, %0, 0;\n\t"
+      "@L cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%4, %5, %6}], [%3];\n\t}"
+      ::"r"(lead), "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t lead, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred L;\n\tsetp.ne.b32 L, %0, 0;\n\t"
+               "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(lead), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_p(uint32_t lead, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred L, p;\n\tsetp.ne.b32 L, %0, 0;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "@L tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t}"
+      ::"r"(lead), "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// One 64-channel k-block (4 x K16), elected lane only, with the NEXT barrier's try_wait (all lanes) issued first: its
+// ~200-cycle latency overlaps the MMA issue.  Returns whether that barrier phase had already completed.
+__device__ __forceinline__ bool umma_bf16_ss_x4_waitahead_p(uint32_t lead, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                            uint32_t accumulate_first, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred L, p, q, t;\n\t.reg .b64 a, b;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+      "setp.ne.b32 L, %8, 0;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 t, %4, 0;\n\t"                       // always true (the instruction descriptor is never 0)
+      "@L tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+      "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "@L tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+      "@L tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+      "@L tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(ok) : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_parity), "r"(lead) : "memory");
+  return ok != 0;
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -118,6 +171,19 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// 16-byte shared-memory accesses on 32-bit shared-window addresses (generic pointers make ptxas emit LD.E/ST.E)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_a(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // Programmatic dependent launch: wait for the upstream grid's memory / let the downstream grid start its prologue
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -140,6 +206,56 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// One 64-channel k-block (4 x K16) with the NEXT barrier's try_wait issued first: its ~200-cycle latency overlaps the MMA
+// issue instead of stalling the (in-order) issuing thread.  Returns whether that barrier phase had already completed.
+__device__ __forceinline__ bool umma_bf16_ss_x4_waitahead(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                          uint32_t accumulate_first, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 t, %4, 0;\n\t"                       // always true (the instruction descriptor is never 0)
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+      "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(ok) : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_parity) : "memory");
+  return ok != 0;
+}
+// Two k-blocks (8 x K16) of one pipeline stage: A blocks 16 KB apart, B blocks `bstep` (16-byte units) apart.
+__device__ __forceinline__ bool umma_bf16_ss_x8_waitahead(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t bstep, uint32_t idesc,
+                                                          uint32_t accumulate_first, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b, b1, st;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 t, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+      "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "cvt.u64.u32 st, %8;\n\tadd.u64 b1, %3, st;\n\t"
+      "add.u64 a, %2, 1024;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b1, %4, t;\n\t"
+      "add.u64 a, %2, 1026;\n\tadd.u64 b, b1, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 1028;\n\tadd.u64 b, b1, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 1030;\n\tadd.u64 b, b1, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(ok) : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_parity), "r"(bstep) : "memory");
+  return ok != 0;
 }
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -169,15 +285,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, K-major operand, 128B swizzle, rows of 128 bytes
 // (64 bf16), 8-row groups `sbo_bytes` apart.  Bit layout (cute/arch/mma_sm100_desc.hpp):
 // [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout (2 = SW128)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset = 0) {
+// layout: 2 = 128B swizzle (128-byte rows), 4 = 64B swizzle (64-byte rows)
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout & 7u) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return umma_desc_kmajor(smem_addr, sbo_bytes, 2u);
 }
 // Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32, M x N tile.
 // [4,6) c_format=1 (f32) | [7,10) a_format=1 (bf16) | [10,13) b_format=1 | [15] a_major=0 | [16] b_major=0

@@ -66,6 +66,21 @@ CONV_CASES = [
     (1, 48, 96, 15, 15, 3, 2, True, False, False, 0, 0, 0),         # odd map, stride 2
     (1, 64, 64, 1, 1, 3, 1, True, False, False, 0, 0, 0),           # single pixel
     (2, 1024, 512, 20, 20, 1, 1, True, False, False, 0, 0, 0),      # SPPF cv2 (K = 1024)
+    (2, 64, 64, 48, 48, 3, 1, True, True, False, 0, 0, 0),          # halo mode (one TMA box per tile) + TMA-prefetched residual
+    (2, 64, 128, 32, 40, 3, 1, True, False, False, 0, 0, 0),        # halo mode, two n tiles split statically over the grid
+    (2, 32, 32, 48, 40, 3, 1, True, True, False, 32, 64, 0),        # 32-channel halo mode (64B swizzle) inside concat slices
+    (1, 16, 48, 32, 32, 3, 1, True, False, False, 16, 16, 0),       # 32-channel halo mode, N = 48 (ragged 64-wide chunk)
+    (2, 128, 128, 24, 24, 3, 1, True, True, False, 0, 0, 0),        # generic 3x3 + residual, 32-wide chunks
+    (1, 256, 256, 20, 20, 3, 1, True, True, False, 0, 0, 0),        # several n tiles + residual
+    (2, 64, 64, 16, 16, 1, 1, True, True, False, 0, 0, 0),          # 1x1 + residual
+    (4, 64, 64, 160, 160, 3, 1, True, True, False, 0, 0, 0),        # > 2 tiles per CTA: both epilogue groups, all pipeline phases
+    (4, 32, 32, 160, 160, 3, 1, True, True, False, 0, 64, 0),
+    (4, 64, 64, 160, 160, 1, 1, True, False, False, 0, 0, 0),
+    (4, 192, 64, 160, 160, 1, 1, True, False, False, 0, 32, 0),
+    (8, 128, 128, 80, 80, 3, 1, True, True, False, 0, 0, 0),
+    (8, 64, 128, 160, 160, 3, 2, True, False, False, 0, 0, 0),
+    (16, 512, 512, 20, 20, 1, 1, True, False, False, 0, 0, 0),
+    (4, 64, 64, 160, 160, 1, 1, False, False, True, 0, 0, 16),      # Detect box logits at P2: fp32, no activation
 ]
 
 

@@ -27,6 +27,12 @@ LAYERS = [  # name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32
     ("P4 3x3 128->128", 64, 128, 128, 40, 40, 3, 1, False, 128, 128, False),
     ("P5 3x3 256->256", 64, 256, 256, 20, 20, 3, 1, False, 256, 256, False),
     ("P5 1x1 1024->512", 64, 1024, 512, 20, 20, 1, 1, False, 1024, 512, False),
+    ("P3 3x3 64->64 +res", 64, 64, 64, 80, 80, 3, 1, True, 192, 192, False),
+    ("P4 3x3 128->128 +res", 64, 128, 128, 40, 40, 3, 1, True, 384, 384, False),
+    ("P3 1x1 256->128", 64, 256, 128, 80, 80, 1, 1, False, 256, 128, False),
+    ("P4 1x1 512->256", 64, 512, 256, 40, 40, 1, 1, False, 512, 256, False),
+    ("P3 3x3 s2 128->256", 64, 128, 256, 80, 80, 3, 2, False, 128, 256, False),
+    ("P4 3x3 256->128", 64, 256, 128, 40, 40, 3, 1, False, 256, 128, False),
 ]
 
 
@@ -39,6 +45,8 @@ def run(name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32, iters=10):
     ob = torch.empty(B, Ho, Wo, out_ld, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
     out = ob.permute(0, 3, 1, 2)[:, :cout]
     r = ob.permute(0, 3, 1, 2)[:, out_ld - cout:] if res else None      # another slice of the same buffer, like C2f
+    if res and out_ld - cout < cout:
+        r = torch.randn(B, Ho, Wo, cout, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)
     for _ in range(2):
         K.conv2d(x, wp, bp, cout, k, s, True, residual=r, out=out)
     torch.cuda.synchronize()
