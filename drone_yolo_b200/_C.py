@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_dtype", C.c_int32),
         ("residual", C.c_void_p), ("res_ld", C.c_int32),
         ("act", C.c_int32),
+        ("up_out", C.c_void_p), ("up_ld", C.c_int32),
     ]
 
 

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     prefetch_tmap(&p.tmB);
     if (CW > 0) prefetch_tmap(&p.tmO);
     if (CW > 0 && p.has_res_tma) prefetch_tmap(&p.tmR);
+    if (CW > 0 && p.has_up) for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmU[i]);
   }
   if (warp == 1 && elect_one()) {
     const uint32_t producers = bres ? 1u : 2u;             // A thread (+ B thread) arrive on every full barrier
@@ -443,6 +444,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const int buf = nbuf == 2 ? (sctr & 1) : 0;
           const uint32_t st = stg + buf * STG_BYTES;
           uint32_t r[CW];
+          [[maybe_unused]] float4 hbv[CW == 32 ? 8 : 1];
+          if constexpr (CW == 32) {                  // bias of this chunk -> registers while the TMEM load is in flight (the
+            const float* bs = s_bias + n0 + c * CW;  // shared-memory port is saturated by the tensor core: LDS latency is long)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hbv[i] = *reinterpret_cast<const float4*>(bs + 4 * i);
+          }
           tmem_ld_32x32b_x32(taddr + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
           if constexpr (CW == 64) tmem_ld_32x32b_x32(taddr + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
           if (nbuf == 2) {
@@ -468,11 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
           if (!(dbg & 1)) {
             const uint32_t rowp = st + row * ROWO;
-            const float* bs = s_bias + n0 + c * CW;
+            [[maybe_unused]] const float* bs = s_bias + n0 + c * CW;
             if constexpr (F32) {
 #pragma unroll
               for (int gi = 0; gi < CW / 4; ++gi) {
-                const float4 hb = *reinterpret_cast<const float4*>(bs + 4 * gi);
+                const float4 hb = hbv[gi];
                 float4 o;
                 o.x = act1(r[4 * gi + 0], hb.x, silu); o.y = act1(r[4 * gi + 1], hb.y, silu);
                 o.z = act1(r[4 * gi + 2], hb.z, silu); o.w = act1(r[4 * gi + 3], hb.w, silu);
@@ -482,7 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 #pragma unroll
               for (int gi = 0; gi < CW / 8; ++gi) {
                 const int pos = (ROWO == 128) ? (gi ^ (row & 7)) : (gi ^ ((row >> 1) & 3));
-                const float4 hb0 = *reinterpret_cast<const float4*>(bs + 8 * gi), hb1 = *reinterpret_cast<const float4*>(bs + 8 * gi + 4);
+                const float4 hb0 = CW == 32 ? hbv[(2 * gi) % (CW == 32 ? 8 : 1)] : *reinterpret_cast<const float4*>(bs + 8 * gi);
+                const float4 hb1 = CW == 32 ? hbv[(2 * gi + 1) % (CW == 32 ? 8 : 1)] : *reinterpret_cast<const float4*>(bs + 8 * gi + 4);
                 float v0 = act1(r[8 * gi + 0], hb0.x, silu), v1 = act1(r[8 * gi + 1], hb0.y, silu);
                 float v2 = act1(r[8 * gi + 2], hb0.z, silu), v3 = act1(r[8 * gi + 3], hb0.w, silu);
                 float v4 = act1(r[8 * gi + 4], hb1.x, silu), v5 = act1(r[8 * gi + 5], hb1.y, silu);
@@ -507,6 +515,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           if (leader) {
             if (!(dbg & 1)) {
               tma_store_4d_a(&p.tmO, st, n0 + c * CW, w0, h0, b0);
+              if (p.has_up) {                        // fused nn.Upsample(2x nearest): the same tile into the four parity views
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tma_store_4d_a(&p.tmU[u], st, n0 + c * CW, w0, h0, b0);
+              }
               bulk_commit_group();
             }
             if (has_res && nbuf == 2) {              // prefetch the next chunk's residual into the buffer that just became free
@@ -648,8 +660,12 @@ static int env_int(const char* name, int dflt) {
 static int pick_bn(int cout_pad, int m_tiles, int kiters, int max_bn) {
   const int sms = num_sms();
   int best = 16; double best_cost = 1e30;
+  bool any_tma = false;                                   // widths the TMA-store epilogue can tile: 32-column chunks, or one ragged N tile
+  for (int bn = 16; bn <= max_bn && bn <= 256; bn += 16)
+    if (cout_pad % bn == 0 && (bn % 32 == 0 || cout_pad == bn)) any_tma = true;
   for (int bn = 16; bn <= max_bn && bn <= 256; bn += 16) {
     if (cout_pad % bn) continue;
+    if (any_tma && !(bn % 32 == 0 || cout_pad == bn)) continue;
     const int n_tiles = cout_pad / bn;
     const long long waves = ((long long)m_tiles * n_tiles + sms - 1) / sms;
     const double per_k = 4.0 * (bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0);
@@ -728,8 +744,13 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   p->mode = mode;
   p->kblocks = halo ? 1 : cin_pad / kBlockK;
   const int kiters = p->ntaps * p->kblocks;
-  if (k == 1) {
-    const uint64_t M = uint64_t(d->B) * d->H * d->W;          // flat GEMM over all pixels: "image" of width M, height 1
+  const bool flat = (k == 1 && d->up_out == nullptr);         // 1x1: flat GEMM over all pixels unless a spatial tile is needed
+  if (d->up_out) {
+    DY_CHECK_ARG(!f32 && d->up_ld % 8 == 0 && d->up_ld >= d->Cout && (reinterpret_cast<uintptr_t>(d->up_out) & 15) == 0,
+                 "conv: up_out needs a bf16 primary output and a 16B-aligned slice");
+  }
+  if (flat) {
+    const uint64_t M = uint64_t(d->B) * d->H * d->W;          // "image" of width M, height 1
     DY_CHECK_ARG(M < (1ull << 31), "conv: too many pixels");
     p->Ho = 1; p->Wo = int(M); p->B = 1;
     p->TW = int(M < 128 ? M : 128); p->TH = 1; p->TB = 1;
@@ -751,7 +772,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const uint64_t esz = 2;
   const uint64_t ld = d->in_ld;
   const char* base = reinterpret_cast<const char*>(d->in);
-  if (k == 1) {
+  if (flat) {
     const uint64_t M = uint64_t(p->Wo);
     const uint64_t dims[4] = {uint64_t(d->Cin), M, 1, 1};
     const uint64_t strides[3] = {ld * esz, M * ld * esz, M * ld * esz};
@@ -812,7 +833,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       const CUtensorMapSwizzle sw = rowo == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
       uint64_t dims[4], strides[3], rstrides[3];
-      if (k == 1) {
+      if (flat) {
         const uint64_t M = uint64_t(p->Wo);
         dims[0] = uint64_t(d->Cout); dims[1] = M; dims[2] = 1; dims[3] = 1;
         strides[0] = uint64_t(d->out_ld) * oes; strides[1] = strides[2] = M * d->out_ld * oes;
@@ -829,9 +850,21 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
         if (rc) return rc;
         p->has_res_tma = 1;
       }
+      if (d->up_out) {
+        // destination pixel (2y+dy, 2x+dx) <- source pixel (y, x): one strided view per (dy, dx)
+        const uint64_t ues = 2, W2 = 2 * uint64_t(Wo), H2 = 2 * uint64_t(Ho);
+        const uint64_t ustr[3] = {2 * uint64_t(d->up_ld) * ues, 2 * W2 * d->up_ld * ues, H2 * W2 * d->up_ld * ues};
+        for (int u = 0; u < 4; ++u) {
+          const char* ub = reinterpret_cast<const char*>(d->up_out) + (uint64_t(u >> 1) * W2 + (u & 1)) * d->up_ld * ues;
+          rc = encode_map(&p->tmU[u], ub, 4, dims, ustr, obox, sw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+          if (rc) return rc;
+        }
+        p->has_up = 1;
+      }
       p->use_tma_store = cw;
     }
   }
+  if (d->up_out && !p->has_up) return fail(DY_ERR_UNSUPPORTED, "conv: up_out needs the TMA-store epilogue (Cout %% 8 == 0)");
 
   // ---- shared-memory plan ----
   // Small layers keep ALL their weights resident (loaded once per CTA): the per-stage traffic and TMA issue then only

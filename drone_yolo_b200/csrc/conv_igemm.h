@@ -13,6 +13,7 @@ struct ConvParams {
   CUtensorMap tmB;         // packed weights [tap][Cout_pad][Cin_pad]
   CUtensorMap tmO;         // output slice (TMA-store epilogue)
   CUtensorMap tmR;         // residual slice, same box as tmO (TMA-prefetched into the staging tile)
+  CUtensorMap tmU[4];      // fused 2x nearest upsample: the four (dy,dx) parity views of the upsampled destination
   int nmaps, ntaps, kblocks;
   int BN, n_tiles, n_split;            // n_split > 1: every CTA owns ONE n tile for its whole life (weights resident per CTA)
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
@@ -22,6 +23,7 @@ struct ConvParams {
   int halo_pitch;                      // pixels per halo-tile row in shared memory (TW + 2)
   int use_tma_store;                   // chunk width CW of the TMA-store epilogue (0 = generic register->global path)
   int has_res_tma;
+  int has_up;
   int nbuf;                            // staging tiles per epilogue group (2, or 1 when shared memory is short)
   int dbg;
   unsigned long long* trace;           // debug builds only (DY_CONV_TRACE)

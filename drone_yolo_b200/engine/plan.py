@@ -13,6 +13,7 @@ chunk/cat/upsample copies around it:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import namedtuple
 from typing import Optional
 
@@ -45,11 +46,21 @@ class LayerPlan:
         self.bufs: list[_Buf] = []
         self.ops: list[dict] = []
         self.keep = []                      # packed weights etc. that must outlive the program
+        self.fuse_upsample = not os.environ.get("DY_NO_FUSE_UPSAMPLE")
         self._build_symbolic()
         self._assign_arena()
         self._emit(images, y)
 
     # ---------------------------------------------------------------------------------------------
+    def _producer_of(self, ref):
+        """Index of the conv op that writes exactly `ref` (and can take a fused upsample store), else None."""
+        for idx in range(len(self.ops) - 1, -1, -1):
+            op = self.ops[idx]
+            if op.get("out") == ref:
+                ok = op["kind"] == "conv" and "up" not in op and ref.c % 8 == 0
+                return idx if ok else None
+        return None
+
     def _new_buf(self, Cc, H, W, esz=2):
         self.bufs.append(_Buf(Cc, H, W, esz, len(self.ops)))
         return len(self.bufs) - 1
@@ -134,7 +145,16 @@ class LayerPlan:
                 self._op(kind="conv", mod=m.cv2, inp=Ref(cat, 0, 4 * c_, src.H, src.W), out=out)
             elif isinstance(m, Upsample):
                 out = dest(i, src.c, src.H * 2, src.W * 2)
-                self._op(kind="upsample", inp=src, out=out)
+                prod = self._producer_of(src)
+                if prod is not None and self.fuse_upsample:
+                    # nn.Upsample(2x nearest) folded into its producer: the conv's epilogue also stores every output tile
+                    # into the four (dy, dx) parity views of this destination (dy_conv_desc.up_out)
+                    self.ops[prod]["up"] = out
+                    b = self.bufs[out.buf]
+                    b.first = min(b.first, prod)
+                    b.last = max(b.last, prod)
+                else:
+                    self._op(kind="upsample", inp=src, out=out)
             elif isinstance(m, Concat):
                 b = self.bufs[cat_buf[i]]
                 out = Ref(cat_buf[i], 0, b.C, b.H, b.W)
@@ -253,7 +273,8 @@ class LayerPlan:
                     (w, b), cout, k, s, act = op["w"], op["cout"], op["k"], op["s"], op["act"]
                 self.keep.append((w, b))
                 res = self.tensor(op["res"]) if op.get("res") is not None else None
-                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, self.tensor(op["out"]), res)
+                up = self.tensor(op["up"]) if op.get("up") is not None else None
+                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, self.tensor(op["out"]), res, up)
                 _C.check(lib.dy_program_add_conv(h, C.byref(d)), "add_conv")
             elif kind == "pool":
                 t = self.tensor(op["inp"])

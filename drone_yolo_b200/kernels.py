@@ -64,7 +64,7 @@ def pack_conv_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
 
 
 def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, k: int, s: int, act: bool,
-              out: torch.Tensor, residual: Optional[torch.Tensor] = None) -> _C.ConvDesc:
+              out: torch.Tensor, residual: Optional[torch.Tensor] = None, up_out: Optional[torch.Tensor] = None) -> _C.ConvDesc:
     xp, xld, B, H, W, Cin = nhwc_view(x, "conv input")
     op, old, Bo, Ho, Wo, Co = nhwc_view(out, "conv output")
     if x.dtype != torch.bfloat16:
@@ -91,17 +91,24 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
     else:
         d.residual, d.res_ld = None, 0
     d.act = _C.DY_ACT_SILU if act else _C.DY_ACT_NONE
+    if up_out is not None:
+        up, uld, Bu, Hu, Wu, Cu = nhwc_view(up_out, "conv upsampled output")
+        if (Bu, Hu, Wu, Cu) != (B, 2 * eh, 2 * ew, cout) or up_out.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+            raise _C.DroneYoloError("conv up_out must be bf16 (B, Cout, 2*Ho, 2*Wo), with a bf16 primary output")
+        d.up_out, d.up_ld = up, uld
+    else:
+        d.up_out, d.up_ld = None, 0
     return d
 
 
 def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, residual=None, out=None,
-           out_dtype=torch.bfloat16) -> torch.Tensor:
+           out_dtype=torch.bfloat16, up_out=None) -> torch.Tensor:
     """act(conv(x) + bias) [+ residual] on tcgen05 tensor cores (dy_conv2d)."""
     B, _, H, W = x.shape
     p = k // 2
     if out is None:
         out = empty_nhwc(B, cout, (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1, x.device, out_dtype)
-    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual)
+    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual, up_out)
     _C.check(_C.lib().dy_conv2d(C.byref(d), _C.stream_ptr(x.device)), "dy_conv2d")
     return out
 

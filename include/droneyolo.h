@@ -55,6 +55,9 @@ int dy_device_check(int device);            /* DY_OK iff `device` is compute cap
  * bias    : fp32 [Cout_pad]
  * out     : bf16 or fp32 NHWC [B,Ho,Wo,Cout] slice, pixel stride out_ld; Ho=(H+2p-k)/s+1, p=k/2
  * residual: optional bf16 NHWC [B,Ho,Wo,Cout] slice added AFTER the activation, or NULL
+ * up_out  : optional second destination, bf16 NHWC [B,2*Ho,2*Wo,Cout] slice with pixel stride up_ld: the
+ *           output is ALSO written 2x nearest-upsampled (nn.Upsample(None, 2, 'nearest') of the model YAMLs,
+ *           cfg/models/v8/yolov8-p2-repvgg.yaml:30,34,38, fused into its producer), or NULL
  * ksize in {1,3}; stride in {1,2} (stride 2 needs even H and W); no dilation, no groups.
  */
 typedef struct dy_conv_desc {
@@ -65,6 +68,7 @@ typedef struct dy_conv_desc {
   void* out;           int32_t out_ld;  int32_t out_dtype;   /* dy_dtype */
   const void* residual; int32_t res_ld;
   int32_t act;                                               /* dy_act   */
+  void* up_out;        int32_t up_ld;
 } dy_conv_desc;
 
 int dy_conv2d(const dy_conv_desc* d, void* stream);

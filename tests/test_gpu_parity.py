@@ -109,6 +109,26 @@ def test_conv_vs_fp32_reference(K, dev, case):
     assert bool((ob[..., :out_pad] == 7.0).all()) and bool((ob[..., out_pad + cout:] == 7.0).all()), "wrote outside its slice"
 
 
+@pytest.mark.parametrize("shape", [(2, 192, 128, 16, 16), (3, 1024, 512, 20, 20), (2, 384, 256, 40, 40)])
+def test_conv_fused_upsample(K, dev, shape):
+    """1x1 conv that also writes its output 2x nearest-upsampled into a slice of the next Concat buffer
+    (the nn.Upsample + Concat pair of the neck, cfg/models/v8/yolov8-p2-repvgg.yaml:30-31)."""
+    B, cin, cout, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    wp, bp = K.pack_conv_weight(w, b)
+    skip = 64
+    cat = torch.full((B, 2 * H, 2 * W, cout + skip), 3.0, device=dev, dtype=torch.bfloat16)
+    up = cat.permute(0, 3, 1, 2)[:, :cout]
+    out = K.conv2d(x, wp, bp, cout, 1, 1, True, up_out=up)
+    ref = F.silu(F.conv2d(x.float(), w.to(torch.bfloat16).float(), b))
+    close(out, ref, 2e-2, 2e-2)
+    assert torch.equal(up, F.interpolate(out.float(), scale_factor=2, mode="nearest").to(torch.bfloat16)), "upsampled copy differs from the primary output"
+    assert bool((cat[..., cout:] == 3.0).all()), "wrote outside its slice"
+
+
 def test_conv_rejects_bad_arguments(K, dev):
     from drone_yolo_b200._C import DroneYoloError
 

@@ -25,6 +25,7 @@ def plan_ops(scale, imgsz, batch):
     lp = LayerPlan.__new__(LayerPlan)
     lp.model, lp.mb, lp.H, lp.W, lp.device = model, batch, imgsz, imgsz, None
     lp.bufs, lp.ops, lp.keep = [], [], []
+    lp.fuse_upsample = True
     lp._build_symbolic()
     rows = []
     for op in lp.ops:
@@ -42,7 +43,9 @@ def plan_ops(scale, imgsz, batch):
             byts = batch * inp.H * inp.W * cin * 2 + M * cout * oes + k * k * cin * cout * 2
             if op.get("res") is not None:
                 byts += M * cout * 2
-            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" f32" if oes == 4 else ""),
+            if op.get("up") is not None:
+                byts += 4 * M * cout * 2
+            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (" f32" if oes == 4 else ""),
                              flops=flops, bytes=byts))
         elif kind == "stem":
             out = op["out"]
