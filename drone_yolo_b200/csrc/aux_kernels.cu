@@ -6,6 +6,7 @@
 //   upsample2x_kernel  nn.Upsample(None,2,'nearest') written straight into a Concat slice (conv.py:331-333)
 //   dwconv3x3s2_kernel DWConv(c1,c2,3,2), groups=c2, c1=2*c2, of the "-sf" graph (conv.py:102-107)
 #include "dy_common.cuh"
+#include <cstdlib>
 
 namespace dy {
 
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const TIn* __re
   }
 }
 
+int stem_tc_launch(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
+                   int out_ld, cudaStream_t stream);   // stem_igemm.cu
+
 int stem_launch(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout, void* out,
                 int out_ld, cudaStream_t stream) {
   DY_CHECK_ARG(in_dtype == DY_F32 || in_dtype == DY_U8, "stem: input must be fp32 or uint8");
@@ -99,6 +103,11 @@ int stem_launch(const void* in, int in_dtype, int B, int H, int W, const float* 
   DY_CHECK_ARG(B > 0 && H > 0 && W > 0, "stem: bad shape");
   DY_CHECK_ARG(Cout % 8 == 0 && Cout > 0 && Cout <= kStemMaxC, "stem: Cout must be a multiple of 8, <= %d", kStemMaxC);
   DY_CHECK_ARG(out_ld % 8 == 0 && out_ld >= Cout && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem: out slice must be 16B aligned");
+  if (getenv("DY_STEM_CUDA_CORES") == nullptr) {
+    // tensor-core stem (stem_igemm.cu); shapes it does not cover (odd widths, Cout > 112) run on the CUDA-core kernel below
+    const int rc = stem_tc_launch(in, in_dtype, B, H, W, weight, bias, Cout, out, out_ld, stream);
+    if (rc != DY_ERR_UNSUPPORTED) return rc;
+  }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = static_cast<long long>(B) * Ho * ((Wo + kStemPix - 1) / kStemPix);
   const long long blocks = (total + kStemThreads - 1) / kStemThreads;

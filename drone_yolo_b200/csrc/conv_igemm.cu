@@ -626,9 +626,8 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
-                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, CUtensorMapSwizzle swizzle, CUtensorMapDataType dtype) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return fail(DY_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];

@@ -34,6 +34,10 @@ struct ConvParams {
 
 struct ConvLaunch { int grid; int smem_bytes; };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda); strides_bytes has rank-1 entries
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+               CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l);
 int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream);
 

@@ -141,6 +141,26 @@ def test_conv_rejects_bad_arguments(K, dev):
 
 
 # ---------------------------------------------------------------------------------------------- aux kernels
+@pytest.mark.parametrize("cout,B,H,W", [(32, 4, 640, 640), (16, 2, 320, 256), (48, 1, 256, 320), (80, 2, 128, 128), (64, 3, 96, 160)])
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_stem_tensor_core(K, dev, cout, B, H, W, dtype):
+    """model.0 on tcgen05 (stem_igemm.cu): every scale's width, many tiles per CTA, both input types, vs conv2d fp32."""
+    g = torch.Generator().manual_seed(cout)
+    x = torch.rand(B, 3, H, W, generator=g).to(dev)
+    w = (torch.randn(cout, 3, 3, 3, generator=g) * 0.3).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    if dtype == torch.uint8:
+        x = (x * 255).round().to(torch.uint8)
+        ref_in = x.float() / 255
+    else:
+        ref_in = x
+    ob = torch.full((B, H // 2, W // 2, cout + 8), 5.0, device=dev, dtype=torch.bfloat16)
+    out = ob.permute(0, 3, 1, 2)[:, :cout]
+    K.stem_conv(x, w.reshape(cout, 27).contiguous(), b, out=out)
+    close(out, F.silu(F.conv2d(ref_in, w, b, stride=2, padding=1)), 2e-2, 2e-2)
+    assert bool((ob[..., cout:] == 5.0).all()), "wrote outside its slice"
+
+
 def test_stem_pool_upsample_dwconv(K, dev):
     g = torch.Generator().manual_seed(0)
     x = torch.rand(2, 3, 64, 96, generator=g).to(dev)
