@@ -34,6 +34,8 @@ class ConvDesc(C.Structure):
         ("residual", C.c_void_p), ("res_ld", C.c_int32),
         ("act", C.c_int32),
         ("up_out", C.c_void_p), ("up_ld", C.c_int32),
+        ("weight2", C.c_void_p), ("bias2", C.c_void_p),
+        ("Cout2", C.c_int32), ("out2", C.c_void_p), ("out2_ld", C.c_int32),
     ]
 
 

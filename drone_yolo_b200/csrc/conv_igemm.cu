@@ -97,7 +97,10 @@ __device__ __forceinline__ float act1(uint32_t acc, float hb, bool silu) {
 // CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true).
 // CW = 0 selects the generic register->global epilogue (odd widths).
 // Shared memory: [resident weights][stages x (A blocks [+ B blocks])][2 groups x 2 staging tiles].
-template <int MODE, int CW, bool F32>
+// FUSE2 (MODE 3, CW 32 only): the Detect branch tail.  The SiLU output tile never leaves the SM: its two 32-channel bf16
+// staging chunks ARE the K-major A operand of a second GEMM (x W2[N2,64]^T, issued by the epilogue group's leader into a
+// private TMEM region); the fp32 result + bias2 goes out through the same staging memory and a TMA store.
+template <int MODE, int CW, bool F32, bool FUSE2 = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t res_bar[4];          // [group][staging buffer]: residual tile landed
+  __shared__ __align__(8) uint64_t d2_bar[2];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[kMaxBias];
@@ -120,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * ROWB;
   const bool bres = p.b_resident != 0;
-  const uint32_t bres_bytes = bres ? static_cast<uint32_t>(NTAPS * p.kblocks) * b_bytes : 0u;
+  const uint32_t w2_bytes = FUSE2 ? static_cast<uint32_t>(p.N2) * 128u : 0u;      // two 32-channel k-blocks of N2 x 64 B
+  const uint32_t bres_bytes = (bres ? static_cast<uint32_t>(NTAPS * p.kblocks) * b_bytes : 0u) + w2_bytes;
 #ifdef DY_CONV_DEBUG
   const int dbg = p.dbg;   // DY_CONV_DBG knock-outs for bottleneck hunting: 1 = no epilogue work, 2 = no MMA, 4 = no A loads, 8 = no B loads
 #define DY_TR(role, it, ev) do { if (p.trace && blockIdx.x == 0 && (it) < 96) p.trace[((role) * 96 + (it)) * 8 + (ev)] = clock64(); } while (0)
@@ -147,15 +152,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < p.nmaps; ++i) prefetch_tmap(&p.tmA[i]);
     prefetch_tmap(&p.tmB);
-    if (CW > 0) prefetch_tmap(&p.tmO);
+    if (CW > 0 && !FUSE2) prefetch_tmap(&p.tmO);
     if (CW > 0 && p.has_res_tma) prefetch_tmap(&p.tmR);
     if (CW > 0 && p.has_up) for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmU[i]);
+    if (FUSE2) { prefetch_tmap(&p.tmW2); prefetch_tmap(&p.tmO2); }
   }
   if (warp == 1 && elect_one()) {
     const uint32_t producers = bres ? 1u : 2u;             // A thread (+ B thread) arrive on every full barrier
     for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1);
     mbar_init(&bres_bar, 1);
     fence_mbar_init();
   }
@@ -239,6 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           for (int t = 0; t < NTAPS; ++t)
             for (int kc = 0; kc < kblocks; ++kc)
               tma_load_3d_p(lead, smem_base + static_cast<uint32_t>(t * kblocks + kc) * b_bytes, &p.tmB, bres_b, kc * kBlockK, n0, t);
+          if constexpr (FUSE2) {                      // tail weights behind the nine tap tiles: k-block 0, k-block 1
+            const uint32_t w2 = smem_base + static_cast<uint32_t>(NTAPS * kblocks) * b_bytes;
+            tma_load_3d_p(lead, w2, &p.tmW2, bres_b, 0, 0, 0);
+            tma_load_3d_p(lead, w2 + (w2_bytes >> 1), &p.tmW2, bres_b, 32, 0, 0);
+          }
         }
       } else {
         int stage = 0; uint32_t phase = 0;
@@ -400,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     {
       const int nb = p.n_tiles * p.BN;              // == Cout padded to 16: the packed bias has that many entries
       for (int i = threadIdx.x - 128; i < nb; i += 256) s_bias[i] = bscale * __ldg(p.bias + i);
+      if constexpr (FUSE2) { for (int i = threadIdx.x - 128; i < 64; i += 256) s_bias[512 + i] = i < p.N2 ? __ldg(p.bias2 + i) : 0.f; }
       named_bar_sync(3, 256);
     }
     [[maybe_unused]] int trt = 0;
@@ -436,7 +449,89 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.BN);
 
-      if constexpr (CW > 0) {
+      if constexpr (FUSE2) {
+        // ---------------- fused Detect tail: SiLU tile (2 x 32 channels, bf16, 64B swizzle) -> second GEMM -> fp32 out ----------------
+        static_assert(!FUSE2 || (MODE == 3 && CW == 32 && !F32), "fused tail: 64-channel halo mode with 32-wide chunks");
+        const uint32_t d2b = smem_u32(&d2_bar[g]);
+        const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(kTmemCols - 128 + 64 * g);       // this group's private columns
+        if (leader) bulk_wait_group_read<0>();       // the previous tile's output stores have read the staging memory
+        named_bar_sync(barid, 128);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float4 hbv[8];
+          const float* bs = s_bias + c * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hbv[i] = *reinterpret_cast<const float4*>(bs + 4 * i);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == 1) {                              // accumulator fully read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
+          }
+          const uint32_t rowp = stg + c * STG_BYTES + row * 64;
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            const float4 hb0 = hbv[2 * gi], hb1 = hbv[2 * gi + 1];
+            uint4 o;
+            o.x = pack_bf16(act1(r[8 * gi + 0], hb0.x, silu), act1(r[8 * gi + 1], hb0.y, silu));
+            o.y = pack_bf16(act1(r[8 * gi + 2], hb0.z, silu), act1(r[8 * gi + 3], hb0.w, silu));
+            o.z = pack_bf16(act1(r[8 * gi + 4], hb1.x, silu), act1(r[8 * gi + 5], hb1.y, silu));
+            o.w = pack_bf16(act1(r[8 * gi + 6], hb1.z, silu), act1(r[8 * gi + 7], hb1.w, silu));
+            sts128(rowp + ((gi ^ ((row >> 1) & 3)) << 4), o);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        named_bar_sync(barid, 128);
+        if (leader) {
+          // D2[128, N2] = tile[128, 64] x W2[N2, 64]^T: two 32-channel k-blocks, two K16 steps each (64-byte rows, 64B swizzle)
+          tc_fence_after();
+          const uint64_t hi2 = umma_desc_kmajor(0, 512, 4u) & 0xffffffff00000000ull;
+          const uint32_t lo2 = static_cast<uint32_t>(umma_desc_kmajor(0, 512, 4u) & 0xffffffffull);
+          const uint32_t w2 = smem_base + bres_bytes - w2_bytes;
+          const uint32_t idesc2 = umma_idesc_bf16(kBlockM, p.N2);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t a_lo = lo2 | (((stg + c * STG_BYTES) & 0x3ffffu) >> 4), b_lo = lo2 | (((w2 + c * (w2_bytes >> 1)) & 0x3ffffu) >> 4);
+
+            umma_bf16_ss(d2_tmem, hi2 | a_lo, hi2 | b_lo, idesc2, c ? 1u : 0u);
+            umma_bf16_ss(d2_tmem, hi2 | (a_lo + 2), hi2 | (b_lo + 2), idesc2, 1u);
+          }
+          umma_commit_a(d2b);
+        }
+        mbar_wait_a(d2b, sctr & 1u);                 // one tail GEMM per tile of this group
+        tc_fence_after();
+        const uint32_t t2addr = d2_tmem + (static_cast<uint32_t>(q * 32) << 16);
+        const int nout = (p.N2 + 31) >> 5;           // 32-column fp32 output chunks (the last one may be ragged: TMA clips)
+        for (int oc = 0; oc < nout; ++oc) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t2addr + oc * 32, r);
+          tmem_ld_wait();
+          if (oc > 0) {                              // the staging memory is being read by the previous chunk's store
+            if (leader) bulk_wait_group_read<0>();
+            named_bar_sync(barid, 128);
+          }
+          const uint32_t rowp = stg + row * 128;     // 128 rows x 32 fp32 = both 8 KB staging tiles, 128B swizzle
+          const float* b2 = s_bias + 512 + oc * 32;
+#pragma unroll
+          for (int gi = 0; gi < 8; ++gi) {
+            const float4 bb = *reinterpret_cast<const float4*>(b2 + 4 * gi);
+            sts128(rowp + ((gi ^ (row & 7)) << 4),
+                   make_uint4(__float_as_uint(__uint_as_float(r[4 * gi + 0]) + bb.x), __float_as_uint(__uint_as_float(r[4 * gi + 1]) + bb.y),
+                              __float_as_uint(__uint_as_float(r[4 * gi + 2]) + bb.z), __float_as_uint(__uint_as_float(r[4 * gi + 3]) + bb.w)));
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          named_bar_sync(barid, 128);
+          if (leader) {
+            tma_store_4d_a(&p.tmO2, stg, oc * 32, w0, h0, b0);
+            bulk_commit_group();
+          }
+        }
+        ++sctr;
+      } else if constexpr (CW > 0) {
         // ---------------- fast path: every chunk is CW columns wide and leaves through a TMA store ----------------
         constexpr int ROWO = CW * (F32 ? 4 : 2);    // staging row bytes: 128 (128B swizzle) or 64 (64B swizzle)
         const int nchunks = (p.BN + CW - 1) / CW;   // a ragged last chunk only exists when n_tiles == 1: TMA clips columns >= Cout
@@ -694,7 +789,7 @@ static void pick_tile(int Wo, int Ho, int B, int* TW, int* TH, int* TB) {
 
 int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   DY_CHECK_ARG(d && p && l, "null conv descriptor");
-  DY_CHECK_ARG(d->in && d->weight && d->bias && d->out, "conv: null tensor pointer");
+  DY_CHECK_ARG(d->in && d->weight && d->bias && (d->out || d->weight2), "conv: null tensor pointer");
   DY_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported (1 or 3)", d->ksize);
   DY_CHECK_ARG(d->stride == 1 || (d->stride == 2 && d->ksize == 3), "conv: stride %d with k=%d unsupported", d->stride, d->ksize);
   DY_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: bad shape");
@@ -703,10 +798,19 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
                "conv: in/weight must be 16B aligned");
   const int out_esz = d->out_dtype == DY_F32 ? 4 : 2;
   DY_CHECK_ARG(d->out_dtype == DY_BF16 || d->out_dtype == DY_F32, "conv: bad out dtype");
-  DY_CHECK_ARG((d->out_ld * out_esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "conv: out slice must be 16B aligned");
+  DY_CHECK_ARG(d->weight2 || ((d->out_ld * out_esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0), "conv: out slice must be 16B aligned");
   DY_CHECK_ARG((reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "conv: bias must be 16B aligned");
   if (d->residual)
     DY_CHECK_ARG(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "conv: residual slice must be 16B aligned");
+  const bool fuse2 = d->weight2 != nullptr;
+  if (fuse2) {
+    DY_CHECK_ARG(d->bias2 && d->out2 && d->Cout2 > 0, "conv: fused tail needs weight2, bias2, out2 and Cout2");
+    DY_CHECK_ARG((d->out2_ld * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight2) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->bias2) & 15) == 0, "conv: fused tail tensors must be 16B aligned");
+    if (!(d->ksize == 3 && d->stride == 1 && d->Cin > 32 && d->Cin <= 64 && d->Cout == 64 && d->Cout2 <= 64 && d->Cout2 % 4 == 0 &&
+          d->residual == nullptr && d->up_out == nullptr && d->act == DY_ACT_SILU))
+      return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs k3 s1, 32 < Cin <= 64, Cout 64, Cout2 <= 64, SiLU, no residual / upsample");
+  }
 
   memset(p, 0, sizeof(*p));
   const int k = d->ksize, s = d->stride;
@@ -734,10 +838,11 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   if (mode >= 3) {
     // halo: resident weights of ONE n tile per CTA (9 x BN rows); several n tiles -> static split of the grid
     const int m_tiles = ceil_div(Wo, kHaloTW) * ceil_div(Ho, kHaloTH) * d->B;
-    const int bn = pick_bn(cout_pad, m_tiles, 9, mode == 4 ? 128 : 64);
+    const int bn = fuse2 ? 64 : pick_bn(cout_pad, m_tiles, 9, mode == 4 ? 128 : 64);   // the fused tail contracts over all 64 channels of one tile
     if (cout_pad / bn > 4 || cout_pad / bn > sms) mode = 1;
     else { p->BN = bn; p->n_tiles = cout_pad / bn; p->n_split = p->n_tiles; }
   }
+  if (fuse2 && mode != 3) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs a map the 8x16 halo tiles cover (>= 80 %%)");
   const bool halo = mode >= 3;
   const int rowb = mode == 4 ? 64 : 128;
   p->mode = mode;
@@ -825,7 +930,24 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       if (env_int("DY_CONV_CW", 0) == 32 && cw == 64 && p->BN % 32 == 0) cw = 32;
     }
     if (d->residual && f32) cw = 0;                            // fp32 + residual: generic path (not used by the model)
-    if (cw) {
+    if (fuse2) {
+      p->fuse2 = 1; p->N2 = round_up(d->Cout2, 16); p->bias2 = d->bias2;
+      {
+        const uint64_t dims[3] = {uint64_t(kBlockK), uint64_t(p->N2), 1};
+        const uint64_t strides[2] = {uint64_t(kBlockK) * 2, uint64_t(kBlockK) * p->N2 * 2};
+        const uint32_t box[3] = {32, uint32_t(p->N2), 1};
+        int rc = encode_map(&p->tmW2, d->weight2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+      {
+        const uint64_t dims[4] = {uint64_t(d->Cout2), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
+        const uint64_t strides[3] = {uint64_t(d->out2_ld) * 4, uint64_t(Wo) * d->out2_ld * 4, uint64_t(Ho) * Wo * d->out2_ld * 4};
+        const uint32_t box[4] = {32, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+        int rc = encode_map(&p->tmO2, d->out2, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (rc) return rc;
+      }
+      p->use_tma_store = 32;                                   // staging: two 8 KB tiles per group (the tail's A operand, then its fp32 output)
+    } else if (cw) {
       const uint64_t oes = out_esz;
       const uint32_t obox[4] = {uint32_t(cw), uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
       const int rowo = cw * out_esz;
@@ -874,7 +996,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int staging = 2 * p->nbuf * 128 * cw * out_esz;                     // 2 groups x nbuf tiles
   const int budget = kMaxDynSmem - 1024 - staging;
   const int b_tile = p->BN * rowb;
-  const int b_all = p->ntaps * p->kblocks * b_tile;
+  const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
   if (halo) {
     p->b_resident = 1;
     p->stage_bytes = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
@@ -908,6 +1030,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     const int overrun = cw ? (ceil_div(p->BN, cw) * cw - p->BN) : (ceil_div(p->BN, 32) * 32 - p->BN);
     int nacc = (kTmemCols - overrun) / p->BN;
     if (nacc > kMaxAcc) nacc = kMaxAcc;
+    if (fuse2 && nacc > (kTmemCols - 128) / p->BN) nacc = (kTmemCols - 128) / p->BN;   // the last 128 columns hold the two tail accumulators
     if (halo) nacc &= ~1;
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;
@@ -929,12 +1052,12 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   return DY_OK;
 }
 
-template <int MODE, int CW, bool F32>
+template <int MODE, int CW, bool F32, bool FUSE2 = false>
 static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   static int max_smem_set = 0;
   if (max_smem_set < l->smem_bytes) {
     // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 6 KB
-    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32, FUSE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     max_smem_set = kMaxDynSmem;
   }
   static const bool use_pdl = (getenv("DY_NO_PDL") == nullptr);
@@ -948,7 +1071,7 @@ static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<MODE, CW, F32>, *p));
+  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<MODE, CW, F32, FUSE2>, *p));
   return launch_status("conv_igemm_kernel");
 }
 
@@ -965,7 +1088,7 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 0: return conv_launch_m<0>(p, l, stream);
     case 1: return conv_launch_m<1>(p, l, stream);
     case 2: return conv_launch_m<2>(p, l, stream);
-    case 3: return conv_launch_m<3>(p, l, stream);
+    case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream) : conv_launch_m<3>(p, l, stream);
     default: return conv_launch_m<4>(p, l, stream);
   }
 }

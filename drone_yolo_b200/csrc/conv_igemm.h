@@ -14,6 +14,8 @@ struct ConvParams {
   CUtensorMap tmO;         // output slice (TMA-store epilogue)
   CUtensorMap tmR;         // residual slice, same box as tmO (TMA-prefetched into the staging tile)
   CUtensorMap tmU[4];      // fused 2x nearest upsample: the four (dy,dx) parity views of the upsampled destination
+  CUtensorMap tmW2;        // fused 1x1 tail: packed weights [1][N2][64], box = one 32-channel k-block (64B swizzle)
+  CUtensorMap tmO2;        // fused 1x1 tail: fp32 output slice, box {32, TW, TH, TB}
   int nmaps, ntaps, kblocks;
   int BN, n_tiles, n_split;            // n_split > 1: every CTA owns ONE n tile for its whole life (weights resident per CTA)
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
@@ -24,6 +26,8 @@ struct ConvParams {
   int use_tma_store;                   // chunk width CW of the TMA-store epilogue (0 = generic register->global path)
   int has_res_tma;
   int has_up;
+  int fuse2, N2;                       // fused 1x1 tail (Detect output conv): N2 = Cout2 padded to 16
+  const float* bias2;
   int nbuf;                            // staging tiles per epilogue group (2, or 1 when shared memory is short)
   int dbg;
   unsigned long long* trace;           // debug builds only (DY_CONV_TRACE)

@@ -47,6 +47,7 @@ class LayerPlan:
         self.ops: list[dict] = []
         self.keep = []                      # packed weights etc. that must outlive the program
         self.fuse_upsample = not os.environ.get("DY_NO_FUSE_UPSAMPLE")
+        self.fuse_tail = not os.environ.get("DY_NO_FUSE_TAIL")
         self._build_symbolic()
         self._assign_arena()
         self._emit(images, y)
@@ -72,7 +73,7 @@ class LayerPlan:
                 self.bufs[r.buf].last = max(self.bufs[r.buf].last, t)
 
     def _op(self, **kw):
-        self._touch(kw.get("inp"), kw.get("out"), kw.get("res"))
+        self._touch(kw.get("inp"), kw.get("out"), kw.get("res"), kw["tail"][3] if kw.get("tail") else None)
         for r in kw.get("levels", ()):
             self._touch(r)
         self.ops.append(kw)
@@ -204,16 +205,24 @@ class LayerPlan:
             c2, c3 = m.cv2[i][0].conv.out_channels, m.cv3[i][0].conv.out_channels
             (wf, bf), (wbx, bbx), (wcl, bcl) = packed[i]
             t1 = self._new_buf(c2 + c3, H, W)
-            t2 = self._new_buf(c2 + c3, H, W)
             raw = self._new_buf(m.raw_ld, H, W, esz=4)
-            self._op(kind="conv", w=(wf, bf), cout=c2 + c3, k=3, s=1, act=True, inp=src, out=Ref(t1, 0, c2 + c3, H, W))
-            self._op(kind="conv", mod=m.cv2[i][1], inp=Ref(t1, 0, c2, H, W), out=Ref(t2, 0, c2, H, W))
-            self._op(kind="conv", mod=m.cv3[i][1], inp=Ref(t1, c2, c3, H, W), out=Ref(t2, c2, c3, H, W))
-            self._op(kind="conv", w=(wbx, bbx), cout=4 * m.reg_max, k=1, s=1, act=False, inp=Ref(t2, 0, c2, H, W),
-                     out=Ref(raw, 0, 4 * m.reg_max, H, W))
             ncp = m.raw_ld - 4 * m.reg_max          # class logits padded to 16 channels (zero weights) -> TMA-store path
-            self._op(kind="conv", w=(wcl, bcl), cout=ncp, k=1, s=1, act=False, inp=Ref(t2, c2, c3, H, W),
-                     out=Ref(raw, 4 * m.reg_max, ncp, H, W))
+            self._op(kind="conv", w=(wf, bf), cout=c2 + c3, k=3, s=1, act=True, inp=src, out=Ref(t1, 0, c2 + c3, H, W))
+            # Each branch ends Conv(c,c,3) -> nn.Conv2d(c,n,1) (head.py:41-47).  Where the 64-channel halo kernel applies, the
+            # 1x1 runs inside the 3x3's epilogue (dy_conv_desc.weight2) and the intermediate tensor is never written.
+            halo_ok = self.fuse_tail and H * W / (-(-W // 8) * 8 * -(-H // 16) * 16) >= 0.8
+            t2 = None
+            for (mod3, cin0, cw, (w1, b1), cout1, c0out) in ((m.cv2[i][1], 0, c2, (wbx, bbx), 4 * m.reg_max, 0),
+                                                            (m.cv3[i][1], c2, c3, (wcl, bcl), ncp, 4 * m.reg_max)):
+                if halo_ok and cw == 64 and cout1 <= 64:
+                    self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=None,
+                             tail=(w1, b1, cout1, Ref(raw, c0out, cout1, H, W)))
+                else:
+                    if t2 is None:
+                        t2 = self._new_buf(c2 + c3, H, W)
+                    self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=Ref(t2, cin0, cw, H, W))
+                    self._op(kind="conv", w=(w1, b1), cout=cout1, k=1, s=1, act=False, inp=Ref(t2, cin0, cw, H, W),
+                             out=Ref(raw, c0out, cout1, H, W))
             levels.append(Ref(raw, 0, m.no, H, W))
         self._op(kind="decode", levels=levels, det=m)
         self.raw_refs = levels
@@ -274,7 +283,13 @@ class LayerPlan:
                 self.keep.append((w, b))
                 res = self.tensor(op["res"]) if op.get("res") is not None else None
                 up = self.tensor(op["up"]) if op.get("up") is not None else None
-                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, self.tensor(op["out"]), res, up)
+                tail = None
+                if op.get("tail") is not None:
+                    w2, b2, cout2, r2 = op["tail"]
+                    self.keep.append((w2, b2))
+                    tail = (w2, b2, cout2, self.tensor(r2))
+                out_t = self.tensor(op["out"]) if op.get("out") is not None else None
+                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, out_t, res, up, tail)
                 _C.check(lib.dy_program_add_conv(h, C.byref(d)), "add_conv")
             elif kind == "pool":
                 t = self.tensor(op["inp"])

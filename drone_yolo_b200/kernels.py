@@ -64,9 +64,20 @@ def pack_conv_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
 
 
 def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, k: int, s: int, act: bool,
-              out: torch.Tensor, residual: Optional[torch.Tensor] = None, up_out: Optional[torch.Tensor] = None) -> _C.ConvDesc:
+              out: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None, up_out: Optional[torch.Tensor] = None,
+              tail=None) -> _C.ConvDesc:
+    """`tail` = (w2_packed, bias2, cout2, out2): fused 1x1 output conv (fp32, no activation); `out` may then be None."""
     xp, xld, B, H, W, Cin = nhwc_view(x, "conv input")
-    op, old, Bo, Ho, Wo, Co = nhwc_view(out, "conv output")
+    if out is None:
+        if tail is None:
+            raise _C.DroneYoloError("conv needs an output tensor")
+    if out is None:
+        p_ = k // 2
+        op, old, Bo, Ho, Wo, Co = 0, cout, B, (H + 2 * p_ - k) // s + 1, (W + 2 * p_ - k) // s + 1, cout
+        out_dtype_is_f32 = False
+    else:
+        op, old, Bo, Ho, Wo, Co = nhwc_view(out, "conv output")
+        out_dtype_is_f32 = out.dtype == torch.float32
     if x.dtype != torch.bfloat16:
         raise _C.DroneYoloError(f"conv input must be bf16, got {x.dtype}")
     p = k // 2
@@ -75,14 +86,14 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
         raise _C.DroneYoloError(f"conv output shape {(Bo, Co, Ho, Wo)} != expected {(B, cout, eh, ew)}")
     if w_packed.shape != (k * k, _ceil(cout, 16), _ceil(Cin, BLOCK_K)) or w_packed.dtype != torch.bfloat16:
         raise _C.DroneYoloError(f"packed weight shape {tuple(w_packed.shape)} does not match Cin={Cin} Cout={cout} k={k}")
-    if out.dtype not in (torch.bfloat16, torch.float32):
+    if out is not None and out.dtype not in (torch.bfloat16, torch.float32):
         raise _C.DroneYoloError(f"conv output dtype {out.dtype} unsupported")
     d = _C.ConvDesc()
     d.in_, d.in_ld, d.B, d.H, d.W, d.Cin = xp, xld, B, H, W, Cin
     d.weight, d.bias = w_packed.data_ptr(), bias.data_ptr()
     d.Cout, d.ksize, d.stride = cout, k, s
     d.out, d.out_ld = op, old
-    d.out_dtype = _C.DY_F32 if out.dtype == torch.float32 else _C.DY_BF16
+    d.out_dtype = _C.DY_F32 if out_dtype_is_f32 else _C.DY_BF16
     if residual is not None:
         rp, rld, Br, Hr, Wr, Cr = nhwc_view(residual, "conv residual")
         if (Br, Hr, Wr, Cr) != (B, eh, ew, cout) or residual.dtype != torch.bfloat16:
@@ -93,24 +104,35 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
     d.act = _C.DY_ACT_SILU if act else _C.DY_ACT_NONE
     if up_out is not None:
         up, uld, Bu, Hu, Wu, Cu = nhwc_view(up_out, "conv upsampled output")
-        if (Bu, Hu, Wu, Cu) != (B, 2 * eh, 2 * ew, cout) or up_out.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        if (Bu, Hu, Wu, Cu) != (B, 2 * eh, 2 * ew, cout) or up_out.dtype != torch.bfloat16 or out is None or out.dtype != torch.bfloat16:
             raise _C.DroneYoloError("conv up_out must be bf16 (B, Cout, 2*Ho, 2*Wo), with a bf16 primary output")
         d.up_out, d.up_ld = up, uld
     else:
         d.up_out, d.up_ld = None, 0
+    if tail is not None:
+        w2, b2, cout2, out2 = tail
+        o2, o2ld, B2, H2, W2, C2 = nhwc_view(out2, "conv tail output")
+        if (B2, H2, W2, C2) != (B, eh, ew, cout2) or out2.dtype != torch.float32:
+            raise _C.DroneYoloError("conv tail output must be fp32 (B, Cout2, Ho, Wo)")
+        if w2.shape != (1, _ceil(cout2, 16), _ceil(cout, BLOCK_K)) or w2.dtype != torch.bfloat16:
+            raise _C.DroneYoloError(f"packed tail weight shape {tuple(w2.shape)} does not match {cout}->{cout2}")
+        d.weight2, d.bias2, d.Cout2, d.out2, d.out2_ld = w2.data_ptr(), b2.data_ptr(), cout2, o2, o2ld
+    else:
+        d.weight2, d.bias2, d.Cout2, d.out2, d.out2_ld = None, None, 0, None, 0
     return d
 
 
 def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, residual=None, out=None,
-           out_dtype=torch.bfloat16, up_out=None) -> torch.Tensor:
-    """act(conv(x) + bias) [+ residual] on tcgen05 tensor cores (dy_conv2d)."""
+           out_dtype=torch.bfloat16, up_out=None, tail=None) -> torch.Tensor:
+    """act(conv(x) + bias) [+ residual] on tcgen05 tensor cores (dy_conv2d).  With `tail` (see conv_desc) the fused
+    1x1 output conv's fp32 tensor is returned instead and the intermediate is never written."""
     B, _, H, W = x.shape
     p = k // 2
-    if out is None:
+    if out is None and tail is None:
         out = empty_nhwc(B, cout, (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1, x.device, out_dtype)
-    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual, up_out)
+    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual, up_out, tail)
     _C.check(_C.lib().dy_conv2d(C.byref(d), _C.stream_ptr(x.device)), "dy_conv2d")
-    return out
+    return tail[3] if tail is not None else out
 
 
 def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -58,6 +58,12 @@ int dy_device_check(int device);            /* DY_OK iff `device` is compute cap
  * up_out  : optional second destination, bf16 NHWC [B,2*Ho,2*Wo,Cout] slice with pixel stride up_ld: the
  *           output is ALSO written 2x nearest-upsampled (nn.Upsample(None, 2, 'nearest') of the model YAMLs,
  *           cfg/models/v8/yolov8-p2-repvgg.yaml:30,34,38, fused into its producer), or NULL
+ * weight2 : optional fused 1x1 tail (the Detect branch ends `Conv(c,c,3) -> nn.Conv2d(c, n, 1)`, nn/modules/head.py:41-47):
+ *           out2 = conv1x1(act(conv(in)+bias), weight2) + bias2, fp32, no activation; the intermediate never leaves the
+ *           SM and `out` is not written (may be NULL).  weight2 is bf16 packed [1][ceil16(Cout2)][64], bias2 fp32
+ *           [ceil16(Cout2)], out2 an fp32 NHWC [B,Ho,Wo,Cout2] slice with pixel stride out2_ld.  Requires ksize 3,
+ *           stride 1, 32 < Cin <= 64, Cout == 64, Cout2 <= 64 and a map the 8x16 halo tiles cover well; anything else
+ *           returns DY_ERR_UNSUPPORTED (run the two convs separately).
  * ksize in {1,3}; stride in {1,2} (stride 2 needs even H and W); no dilation, no groups.
  */
 typedef struct dy_conv_desc {
@@ -69,6 +75,8 @@ typedef struct dy_conv_desc {
   const void* residual; int32_t res_ld;
   int32_t act;                                               /* dy_act   */
   void* up_out;        int32_t up_ld;
+  const void* weight2; const float* bias2;
+  int32_t Cout2;       void* out2;      int32_t out2_ld;
 } dy_conv_desc;
 
 int dy_conv2d(const dy_conv_desc* d, void* stream);

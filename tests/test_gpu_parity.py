@@ -129,6 +129,30 @@ def test_conv_fused_upsample(K, dev, shape):
     assert bool((cat[..., cout:] == 3.0).all()), "wrote outside its slice"
 
 
+@pytest.mark.parametrize("B,H,W,cout2", [(2, 48, 40, 64), (4, 160, 160, 64), (4, 160, 160, 10), (3, 80, 80, 16), (2, 40, 40, 10)])
+def test_conv_fused_detect_tail(K, dev, B, H, W, cout2):
+    """Detect branch tail `Conv(64,64,3) -> nn.Conv2d(64,n,1)` (nn/modules/head.py:41-47) in ONE kernel: the SiLU tile is the
+    second GEMM's A operand in shared memory; compared with the two-kernel path and with fp32 PyTorch."""
+    g = torch.Generator().manual_seed(B * 1000 + cout2)
+    x = torch.randn(B, 64, H, W, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w1 = (torch.randn(64, 64, 3, 3, generator=g) / 24.0).to(dev); b1 = torch.randn(64, generator=g).to(dev)
+    w2 = (torch.randn(cout2, 64, 1, 1, generator=g) / 8.0).to(dev); b2 = torch.randn(cout2, generator=g).to(dev)
+    w1p, b1p = K.pack_conv_weight(w1, b1)
+    w2p, b2p = K.pack_conv_weight(w2, b2)
+    c2p = (cout2 + 3) // 4 * 4                                       # Detect pads the 10 class logits' slice to 16 channels
+    raw = torch.full((B, H, W, 16 + c2p + 8), -3.0, device=dev, dtype=torch.float32)
+    out2 = raw.permute(0, 3, 1, 2)[:, 16:16 + c2p]
+    if c2p != cout2:                                                  # padded rows of the packed weight are zero
+        w2p, b2p = K.pack_conv_weight(torch.cat((w2, torch.zeros(c2p - cout2, 64, 1, 1, device=dev))), torch.cat((b2, torch.zeros(c2p - cout2, device=dev))))
+    K.conv2d(x, w1p, b1p, 64, 3, 1, True, tail=(w2p, b2p, c2p, out2))
+    mid = K.conv2d(x, w1p, b1p, 64, 3, 1, True)                       # two-kernel path
+    two = K.conv2d(mid, w2p, b2p, c2p, 1, 1, False, out_dtype=torch.float32)
+    close(out2, two, 1e-3, 1e-3)                                      # same bf16 intermediate, same bf16 weights, fp32 accumulation
+    ref = F.conv2d(F.silu(F.conv2d(x.float(), w1.to(torch.bfloat16).float(), b1, padding=1)), w2.to(torch.bfloat16).float(), b2)
+    close(out2[:, :cout2], ref, 2e-2, 3e-2)
+    assert bool((raw[..., :16] == -3.0).all()) and bool((raw[..., 16 + c2p:] == -3.0).all()), "wrote outside its slice"
+
+
 def test_conv_rejects_bad_arguments(K, dev):
     from drone_yolo_b200._C import DroneYoloError
 

@@ -26,6 +26,7 @@ def plan_ops(scale, imgsz, batch):
     lp.model, lp.mb, lp.H, lp.W, lp.device = model, batch, imgsz, imgsz, None
     lp.bufs, lp.ops, lp.keep = [], [], []
     lp.fuse_upsample = True
+    lp.fuse_tail = True
     lp._build_symbolic()
     rows = []
     for op in lp.ops:
@@ -37,15 +38,20 @@ def plan_ops(scale, imgsz, batch):
                 cout, k, s = op["cout"], op["k"], op["s"]
             inp, out = op["inp"], op["out"]
             cin = inp.c
+            tail = op.get("tail")
+            if out is None:
+                out = tail[3]
             M = batch * out.H * out.W
             flops = 2.0 * M * cout * k * k * cin
             oes = lp.bufs[out.buf].esz
-            byts = batch * inp.H * inp.W * cin * 2 + M * cout * oes + k * k * cin * cout * 2
+            byts = batch * inp.H * inp.W * cin * 2 + M * (tail[2] if tail else cout) * oes + k * k * cin * cout * 2
+            if tail:
+                flops += 2.0 * M * cout * tail[2]
             if op.get("res") is not None:
                 byts += M * cout * 2
             if op.get("up") is not None:
                 byts += 4 * M * cout * 2
-            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (" f32" if oes == 4 else ""),
+            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (f" +1x1->{op['tail'][2]}" if op.get("tail") else "") + (" f32" if oes == 4 else ""),
                              flops=flops, bytes=byts))
         elif kind == "stem":
             out = op["out"]
