@@ -351,24 +351,35 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
       if (lane == 0) s.remv[warp] = dead_bits;
       __syncthreads();
-      // ---- (e) upper-triangular suppression bitmask: thread i owns row i; mask[w][i] covers j in [32w, 32w+32).
-      //      Only candidates that survived (d) matter, as rows and as columns.
-      if (have) {
-        for (int w = 0; w < kWords; ++w) {
-          unsigned int bits = 0u;
+      // ---- (e) upper-triangular suppression bitmask, mask[w][i] covers columns j in [32w, 32w+32) of row i (j > i only).
+      //      Only candidates that survived (d) matter, as rows and as columns.  The triangle is cut into (row, 32-column word)
+      //      units, word-major: word w has rows 0 .. 32w+31, i.e. 16w(w+1) units precede it.  Units are dealt round-robin, so
+      //      every thread gets the same amount of IoU work (one row per thread left thread 0 with 511 tests and thread 511
+      //      with none: half of the block idled at the barrier).
+      {
+        const int nwords = (K + 31) / 32;
+        const int units = 16 * nwords * (nwords + 1);
+        int w = 0;
+        for (int u = tid; u < units; u += kSelThreads) {
+          while (16 * (w + 1) * (w + 2) <= u) ++w;                      // u only grows: w is carried
+          const int i = u - 16 * w * (w + 1);
           const int j0 = w * 32;
-          if (j0 + 31 > tid && j0 < K && !dead) {
-            unsigned int todo = ~s.remv[w];                          // columns still alive after (d)
+          unsigned int bits = 0u;
+          if (i < K && !((s.remv[i >> 5] >> (i & 31)) & 1u)) {
+            unsigned int todo = ~s.remv[w];                              // columns still alive after (d)
             if (K - j0 < 32) todo &= (1u << (K - j0)) - 1u;
-            if (tid >= j0) todo &= ~((2u << (tid - j0)) - 1u);       // only j > i
-            while (todo) {
-              const int jj = __ffs(todo) - 1;
-              todo &= todo - 1u;
-              const int j = j0 + jj;
-              if (iou_suppresses(mybox, myarea, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+            if (i >= j0) todo &= ~((2u << (i - j0)) - 1u);               // only j > i
+            if (todo) {
+              const float4 bi = s.box[i]; const float ai = s.area[i];
+              while (todo) {
+                const int jj = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const int j = j0 + jj;
+                if (iou_suppresses(bi, ai, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+              }
             }
           }
-          s.mask[w * (kK + 1) + tid] = bits;
+          if (i < kK) s.mask[w * (kK + 1) + i] = bits;
         }
       }
       __syncthreads();
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
             const int i = wi * 32 + bit;
             if (lane == 0) s.kidx[kept - kept0] = static_cast<unsigned short>(i);
             kept++;
-            if (lane < kWords) remv |= s.mask[lane * (kK + 1) + i];
+            if (lane < kWords && lane >= wi) remv |= s.mask[lane * (kK + 1) + i];   // words below the diagonal are never written
             cur = __shfl_sync(0xffffffffu, remv, wi);
             avail = ~cur & range & ~((2u << bit) - 1u);    // only bits above the one just taken
           }
