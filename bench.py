@@ -260,11 +260,15 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local)           # nvidia-smi answers every ~100 ms: sample from the warm-up on (same load) to the end
+    if rank == 0:                           # of the timed region so that a 20-step run still yields several readings
+        sampler.start()
     for _ in range(max(a.warmup, 3)):
         step_resident()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    torch.cuda.synchronize(dev)
+    t_fill = time.perf_counter()
+    while time.perf_counter() - t_fill < 0.4:   # keep the same load up for a few sampler periods
+        step_resident()
     ms_total = timed(step_resident, a.steps)
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
@@ -301,6 +305,13 @@ def run_ours(a):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback (B200_PROFILING.md)"
 
+    # DRAM traffic of the launch group: measured separately under ncu (a number taken under a profiler is never a bench
+    # value, but the byte counters are exact) and committed under profiles/; only valid for the default workload
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "r01_dram_traffic_s640_b64.json"
+    if tf.exists() and (a.scale, a.imgsz, a.batch) == ("s", 640, 64):
+        t = json.loads(tf.read_text())
+        traffic, traffic_src = t["plan_dram_bytes"], t["source"]
     imgs = a.batch * world
     ms_step = ms_total / a.steps
     value = imgs / (ms_step / 1e3)
@@ -324,7 +335,7 @@ def run_ours(a):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv stack plan: stem + 78 tcgen05 convs + pool/upsample + decode)",
                      "achieved": conv_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": conv_tflops / tf_peak,
-                     "traffic": None, "peak_source": peak_src, "ms_per_launch_group": ms_plan,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch_group": ms_plan,
                      "algorithmic_gflop_per_image": gf},
         "stages": {"conv_stack_decode_ms": ms_plan, "nms_ms": ms_nms,
                    "nms_hbm_gbs": nms_bytes / ms_nms / 1e6, "nms_frac_of_hbm": nms_bytes / ms_nms / 1e6 / hbm_peak,
