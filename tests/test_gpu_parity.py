@@ -394,7 +394,9 @@ def test_model_vs_reference_golden(dev, golden_dir, tag, path):
     close(y[:, 4:], torch.from_numpy(g["y"][:, 4:]), 2e-2, 1e-4)
 
 
-@pytest.mark.parametrize("scale,imgsz,B,mb", [("s", 640, 4, 2), ("n", 320, 3, 1), ("x", 320, 2, 2), ("m", 256, 2, 1)])
+@pytest.mark.parametrize("scale,imgsz,B,mb", [("s", 640, 4, 2), ("n", 320, 3, 1), ("x", 320, 2, 2), ("m", 256, 2, 1),
+                                              ("l", 1280, 1, 1),      # BASELINE config 3: P2 at 320x320, 136 000 anchors
+                                              ("x", 640, 2, 2)])      # BASELINE config 5
 def test_engine_vs_cpu_oracle(dev, scale, imgsz, B, mb):
     """Full path at real resolutions vs the CPU oracle (fp32): raw maps, boxes, and NMS bit-exact on the engine's own
     pre-NMS tensor.  Micro-batched replays must not leak state between micro-batches."""
