@@ -86,14 +86,19 @@ __device__ __forceinline__ void mbar_wait_unless(uint32_t bar, uint32_t parity, 
 __device__ __forceinline__ float act1(uint32_t acc, float hb, bool silu) {
   if (silu) {
     const float h = fmaf(__uint_as_float(acc), 0.5f, hb);
+#if defined(DY_CONV_DBG_CONST) && (DY_CONV_DBG_CONST & 16)
+    return fmaf(h, 0.75f, h);        // knock-out build: SiLU without its MUFU
+#else
     return fmaf(h, tanh_fast(h), h);
+#endif
   }
   return __uint_as_float(acc) + hb;
 }
 
 // MODE = tap geometry / A staging, known at compile time:
 //   0: 1x1 (one tap, flat pixel index), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (parity views),
-//   3: 3x3 stride 1 halo, one 64-channel block, 128-byte rows;  4: 3x3 stride 1 halo, Cin <= 32, 64-byte rows.
+//   3: 3x3 stride 1 halo, one 64-channel block, 128-byte rows;  4: 3x3 stride 1 halo, Cin <= 32, 64-byte rows;
+//   5: 3x3 stride 2, Cin <= 32, 64-byte rows (a filter row of three taps per pipeline stage).
 // CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true).
 // CW = 0 selects the generic register->global epilogue (odd widths).
 // Shared memory: [resident weights][stages x (A blocks [+ B blocks])][2 groups x 2 staging tiles].
@@ -116,9 +121,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
   constexpr int NTAPS = MODE == 0 ? 1 : 9;
   constexpr bool HALO = (MODE == 3 || MODE == 4);
-  constexpr int ROWB = MODE == 4 ? 64 : 128;            // bytes per pixel / per weight row in the A / B shared-memory tiles
+  constexpr bool S2 = (MODE == 2 || MODE == 5);         // stride 2: four parity views
+  constexpr int ROWB = (MODE == 4 || MODE == 5) ? 64 : 128;   // bytes per pixel / per weight row in the A / B shared-memory tiles
+  constexpr int A_BLK = kBlockM * ROWB;                 // one A k-block: 64 channels (16 KB) or 32 channels (8 KB)
   constexpr int KSTEPS = ROWB / 32;                     // K = 16 MMAs per k-block
-  constexpr uint32_t LAYOUT = MODE == 4 ? 4u : 2u;      // UMMA layout type: 64B / 128B swizzle
+  constexpr uint32_t LAYOUT = ROWB == 64 ? 4u : 2u;     // UMMA layout type: 64B / 128B swizzle
   constexpr int STG_BYTES = CW == 0 ? 0 : 128 * CW * (F32 ? 4 : 2);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       constexpr uint32_t lead = 1u;
       int stage = 0; uint32_t phase = 0;
       [[maybe_unused]] int trk = 0;
-      const uint32_t a_tx = (dbg & 4) ? 0u : static_cast<uint32_t>(p.TW * p.TH * p.TB) * 128u;
+      const uint32_t a_tx = (dbg & 4) ? 0u : static_cast<uint32_t>(p.TW * p.TH * p.TB * ROWB);
       const uint32_t halo_tx = (dbg & 4) ? 0u : static_cast<uint32_t>(p.halo_pitch * kHaloRows * ROWB);
       const int kblocks = opaque(p.kblocks);
       const int tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h);
@@ -218,12 +225,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (++stage == nstages) { stage = 0; nfullb = full0; ndst = stage0; nph ^= 1u; }
             ok = mbar_try_wait_a(nfullb + e_minus_f, nph ^ 1u);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 3; ++j) {
               if (j < kps_r && j < left) {
                 // stride 2: input coord 2*x+o -> parity view (o&1), coarse coord x + (o<0 ? -1 : 0)
-                const int map = MODE == 2 ? ((oy & 1) * 2 + (ox & 1)) : 0;
-                const int dx = MODE == 2 ? (ox < 0 ? -1 : 0) : ox, dy = MODE == 2 ? (oy < 0 ? -1 : 0) : oy;
-                if (!(dbg & 4)) tma_load_4d_a(dst + j * kABytes, &p.tmA[map], fullb, kc, w0 + dx, h0 + dy, b0);
+                const int map = S2 ? ((oy & 1) * 2 + (ox & 1)) : 0;
+                const int dx = S2 ? (ox < 0 ? -1 : 0) : ox, dy = S2 ? (oy < 0 ? -1 : 0) : oy;
+                if (!(dbg & 4)) tma_load_4d_a(dst + j * A_BLK, &p.tmA[map], fullb, kc, w0 + dx, h0 + dy, b0);
                 kc += kBlockK;
                 if (kc == kcmax) { kc = 0; if (++ox == 2) { ox = -1; ++oy; } }
               }
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         int stage = 0; uint32_t phase = 0;
         const uint32_t b_tx = (dbg & 8) ? 0u : b_bytes;
         const int tiles_w = opaque(p.tiles_w), tiles_h = opaque(p.tiles_h), BN = opaque(p.BN);
-        const uint32_t b_off = static_cast<uint32_t>(kps) * kABytes;
+        const uint32_t b_off = static_cast<uint32_t>(kps) * A_BLK;
         const int kit = opaque(kiters), kps_r = opaque(kps), kcmax = opaque(kblocks * kBlockK);
         const uint32_t e_minus_f = empty0 - full0;
         const uint32_t bb = opaque(b_bytes);
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (++stage == nstages) { stage = 0; nfullb = full0; ndst = stage0 + b_off; nph ^= 1u; }
             ok = mbar_try_wait_a(nfullb + e_minus_f, nph ^ 1u);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 3; ++j) {
               if (j < kps_r && j < left) {
                 if (!(dbg & 8)) tma_load_3d_a(dst + j * bb, &p.tmB, fullb, kc, n0, t);
                 kc += kBlockK;
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const uint32_t sstep = opaque(sbytes >> 4), bstep = opaque(bbytes >> 4);
         const uint32_t a_lo0 = opaque(lo_const | ((stage0 & 0x3ffffu) >> 4));
         const uint32_t bres_lo0 = opaque(lo_const | ((smem_base & 0x3ffffu) >> 4));
-        const uint32_t b_in_stage = opaque(static_cast<uint32_t>(kps) * (kABytes >> 4));
+        const uint32_t b_in_stage = opaque(static_cast<uint32_t>(kps) * (A_BLK >> 4));
         const uint32_t e_minus_f = empty0 - full0;
         uint32_t a_lo = a_lo0, fullb = full0;
         uint32_t tfb = tfull0, teb = tempty0, d_tmem = tmem_base;
@@ -376,7 +383,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             uint32_t nfullb = fullb + 8, na_lo = a_lo + sstep, nph = phase;
             if (++stage == nstages) { stage = 0; nfullb = full0; na_lo = a_lo0; nph ^= 1u; }
             const uint32_t b_lo = bres_i ? bres_lo : a_lo + b_in_stage;
-            if (!(dbg & 2)) {
+            if constexpr (KSTEPS == 2) {
+              // 32-channel k-blocks (64-byte rows): a whole filter row (3 taps, 6 MMAs) per stage when it fits
+              if (!(dbg & 2)) {
+                if (kps_r == 3 && left >= 3) okf = umma_bf16_ss_k32x3_waitahead(d_tmem, a_hi | a_lo, b_hi | b_lo, bstep, idesc, accum, nfullb, nph);
+                else {
+                  okf = mbar_try_wait_a(nfullb, nph);
+                  for (int j = 0; j < kps_r && j < left; ++j)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                      umma_bf16_ss(d_tmem, a_hi | (a_lo + j * (A_BLK >> 4) + 2 * k), b_hi | (b_lo + j * bstep + 2 * k), idesc, (accum | j | k) ? 1u : 0u);
+                }
+              } else okf = mbar_try_wait_a(nfullb, nph);
+            } else if (!(dbg & 2)) {
               if (kps_r == 2 && left >= 2) okf = umma_bf16_ss_x8_waitahead(d_tmem, a_hi | a_lo, b_hi | b_lo, bstep, idesc, accum, nfullb, nph);
               else okf = umma_bf16_ss_x4_waitahead(d_tmem, a_hi | a_lo, b_hi | b_lo, idesc, accum, nfullb, nph);
             } else {
@@ -608,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           named_bar_sync(barid, 128);
           if (c == 0) DY_TRE(4);
           if (leader) {
-            if (!(dbg & 1)) {
+            if (!(dbg & 1) && !(dbg & 32)) {
               tma_store_4d_a(&p.tmO, st, n0 + c * CW, w0, h0, b0);
               if (p.has_up) {                        // fused nn.Upsample(2x nearest): the same tile into the four parity views
 #pragma unroll
@@ -828,6 +847,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
 
   // ---- mode, pixel tile, N tile ----
   int mode = (k == 1) ? 0 : (s == 1 ? 1 : 2);
+  if (mode == 2 && d->Cin <= 32 && !env_int("DY_NO_K32", 0)) mode = 5;          // stride 2 with 64-byte rows: half the MMA / smem / L2 work
   if (k == 3 && s == 1 && !env_int("DY_NO_HALO", 0)) {
     const double eff = double(Wo) * Ho / (double(ceil_div(Wo, kHaloTW)) * kHaloTW * ceil_div(Ho, kHaloTH) * kHaloTH);
     if (eff >= 0.8) {
@@ -835,7 +855,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       else if (cin_pad == kBlockK) mode = 3;
     }
   }
-  if (mode >= 3) {
+  if (mode == 3 || mode == 4) {
     // halo: resident weights of ONE n tile per CTA (9 x BN rows); several n tiles -> static split of the grid
     const int m_tiles = ceil_div(Wo, kHaloTW) * ceil_div(Ho, kHaloTH) * d->B;
     const int bn = fuse2 ? 64 : pick_bn(cout_pad, m_tiles, 9, mode == 4 ? 128 : 64);   // the fused tail contracts over all 64 channels of one tile
@@ -843,10 +863,11 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     else { p->BN = bn; p->n_tiles = cout_pad / bn; p->n_split = p->n_tiles; }
   }
   if (fuse2 && mode != 3) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs a map the 8x16 halo tiles cover (>= 80 %%)");
-  const bool halo = mode >= 3;
-  const int rowb = mode == 4 ? 64 : 128;
+  const bool halo = (mode == 3 || mode == 4);
+  const int rowb = (mode == 4 || mode == 5) ? 64 : 128;
+  const int a_blk = kBlockM * rowb;
   p->mode = mode;
-  p->kblocks = halo ? 1 : cin_pad / kBlockK;
+  p->kblocks = (halo || mode == 5) ? 1 : cin_pad / kBlockK;
   const int kiters = p->ntaps * p->kblocks;
   const bool flat = (k == 1 && d->up_out == nullptr);         // 1x1: flat GEMM over all pixels unless a spatial tile is needed
   if (d->up_out) {
@@ -893,12 +914,13 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     p->nmaps = 1;
   } else {
     DY_CHECK_ARG(d->H >= 2 && d->W >= 2, "conv: stride-2 needs H,W >= 2");
-    const uint32_t box[4] = {kBlockK, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+    const uint32_t box[4] = {uint32_t(rowb / 2), uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         const uint64_t dims[4] = {uint64_t(d->Cin), uint64_t((d->W - px + 1) / 2), uint64_t((d->H - py + 1) / 2), uint64_t(d->B)};
         const uint64_t strides[3] = {2 * ld * esz, 2 * uint64_t(d->W) * ld * esz, uint64_t(d->H) * d->W * ld * esz};
-        int rc = encode_map(&p->tmA[py * 2 + px], base + (uint64_t(py) * d->W + px) * ld * esz, 4, dims, strides, box);
+        int rc = encode_map(&p->tmA[py * 2 + px], base + (uint64_t(py) * d->W + px) * ld * esz, 4, dims, strides, box,
+                            rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
       }
     p->nmaps = 4;
@@ -909,7 +931,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     const uint64_t dims[3] = {uint64_t(cin_pad), uint64_t(cout_pad), uint64_t(p->ntaps)};
     const uint64_t strides[2] = {uint64_t(cin_pad) * esz, uint64_t(cin_pad) * cout_pad * esz};
     const uint32_t box[3] = {uint32_t(rowb / 2), uint32_t(p->BN), 1};
-    int rc = encode_map(&p->tmB, d->weight, 3, dims, strides, box, mode == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_map(&p->tmB, d->weight, 3, dims, strides, box, rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 
@@ -1010,13 +1032,13 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     p->stages &= ~1;
   } else {
     p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes && !env_int("DY_NO_BRES", 0)) ? 1 : 0;   // leave room for >= 4 activation stages
-    const int per_k = kABytes + (p->b_resident ? 0 : b_tile);
+    const int per_k = a_blk + (p->b_resident ? 0 : b_tile);
     const int avail = budget - (p->b_resident ? b_all : 0);
     // k-blocks per stage: the issuing thread pays ~300 cycles per stage (barrier wait, commit), a k-block is 4 x max(BN/2,
     // 32 + BN/4) cycles of MMA: fatten the stages of narrow tiles until a stage holds >= ~512 cycles, keeping >= 3 stages.
     int kps = env_int("DY_CONV_KPS", 0);
-    if (kps < 1) kps = p->BN >= 256 ? 1 : 2;
-    if (kps > 2) kps = 2;
+    if (kps < 1) kps = mode == 5 ? 3 : (p->BN >= 256 ? 1 : 2);
+    if (kps > (mode == 5 ? 3 : 2)) kps = mode == 5 ? 3 : 2;
     while (kps > 1 && (kps > kiters || avail / (kps * per_k) < 3)) --kps;
     p->kps = kps;
     p->stage_bytes = kps * per_k;
@@ -1089,7 +1111,8 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 1: return conv_launch_m<1>(p, l, stream);
     case 2: return conv_launch_m<2>(p, l, stream);
     case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream) : conv_launch_m<3>(p, l, stream);
-    default: return conv_launch_m<4>(p, l, stream);
+    case 4: return conv_launch_m<4>(p, l, stream);
+    default: return conv_launch_m<5>(p, l, stream);
   }
 }
 

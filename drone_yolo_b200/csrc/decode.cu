@@ -68,18 +68,21 @@ __global__ void __launch_bounds__(kDecThreads) decode_nhwc_kernel(const __grid_c
   const int pitch = row_bytes + 16;
   const uint8_t* src = static_cast<const uint8_t*>(p.lvl[l]) + (static_cast<size_t>(b) * p.hw[l] + a0) * row_bytes;
 
-  // cooperative, fully coalesced slab copy
+  // cooperative, fully coalesced slab copy.  Ten independent 16-byte loads per thread are issued before the first is
+  // consumed: with ~5 CTAs per SM that keeps > 60 KB per SM in flight, what HBM latency x bandwidth needs (4 loads per
+  // thread left the kernel at 46 % of DRAM peak).
+  constexpr int kU = 10;
   const int vec_per_row = row_bytes >> 4;
   const int nvec = cnt * vec_per_row;
-  for (int i = threadIdx.x; i < nvec; i += kDecThreads * 4) {
-    uint4 v[4];
+  for (int i = threadIdx.x; i < nvec; i += kDecThreads * kU) {
+    uint4 v[kU];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kU; ++j) {
       const int idx = i + j * kDecThreads;
       if (idx < nvec) v[j] = ldg_nc_v4(src + static_cast<size_t>(idx) * 16);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kU; ++j) {
       const int idx = i + j * kDecThreads;
       if (idx < nvec) {
         const int r = idx / vec_per_row, c = idx - r * vec_per_row;

@@ -257,6 +257,31 @@ __device__ __forceinline__ bool umma_bf16_ss_x8_waitahead(uint32_t tmem_d, uint6
       : "=r"(ok) : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_parity), "r"(bstep) : "memory");
   return ok != 0;
 }
+// Three 32-channel k-blocks (64-byte rows: 2 x K16 each) of one pipeline stage: A blocks 8 KB apart, B blocks `bstep` apart.
+__device__ __forceinline__ bool umma_bf16_ss_k32x3_waitahead(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t bstep, uint32_t idesc,
+                                                             uint32_t accumulate_first, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b, b1, b2, st;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 t, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+      "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "cvt.u64.u32 st, %8;\n\tadd.u64 b1, %3, st;\n\tadd.u64 b2, b1, st;\n\t"
+      "add.u64 a, %2, 512;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b1, %4, t;\n\t"
+      "add.u64 a, %2, 514;\n\tadd.u64 b, b1, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "add.u64 a, %2, 1024;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b2, %4, t;\n\t"
+      "add.u64 a, %2, 1026;\n\tadd.u64 b, b2, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(ok) : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_parity), "r"(bstep) : "memory");
+  return ok != 0;
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -81,6 +81,9 @@ CONV_CASES = [
     (8, 64, 128, 160, 160, 3, 2, True, False, False, 0, 0, 0),
     (16, 512, 512, 20, 20, 1, 1, True, False, False, 0, 0, 0),
     (4, 64, 64, 160, 160, 1, 1, False, False, True, 0, 0, 16),      # Detect box logits at P2: fp32, no activation
+    (4, 32, 64, 320, 320, 3, 2, True, False, False, 0, 0, 0),       # stride 2 with 64-byte rows (model.1 of the s scale)
+    (2, 16, 32, 64, 96, 3, 2, True, False, False, 16, 32, 0),       # ... n scale, inside slices
+    (1, 24, 48, 31, 45, 3, 2, True, False, False, 0, 0, 0),         # ... odd map
 ]
 
 

@@ -18,6 +18,11 @@ LAYERS = [  # name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32
     ("P2 3x3 32->32 +res", 64, 32, 32, 160, 160, 3, 1, True, 96, 96, False),
     ("P2 3x3 32->32 nores", 64, 32, 32, 160, 160, 3, 1, False, 96, 96, False),
     ("P2 3x3 32->32 dense", 64, 32, 32, 160, 160, 3, 1, False, 32, 32, False),
+    ("P2 3x3 32->32 out_ld64", 64, 32, 32, 160, 160, 3, 1, False, 96, 64, False),
+    ("P2 3x3 32->32 out_ld128", 64, 32, 32, 160, 160, 3, 1, False, 96, 128, False),
+    ("P2 3x3 32->32 in32 out96", 64, 32, 32, 160, 160, 3, 1, False, 32, 96, False),
+    ("P2 1x1 64->64 out_ld64", 64, 64, 64, 160, 160, 1, 1, False, 64, 64, False),
+    ("P2 1x1 64->64 out_ld128", 64, 64, 64, 160, 160, 1, 1, False, 64, 128, False),
     ("P2 3x3 64->64", 64, 64, 64, 160, 160, 3, 1, False, 128, 128, False),
     ("P3 3x3 64->64", 64, 64, 64, 80, 80, 3, 1, False, 128, 128, False),
     ("P2 3x3 64->128", 64, 64, 128, 160, 160, 3, 1, False, 64, 128, False),

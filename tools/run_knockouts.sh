@@ -1,9 +1,9 @@
 #!/bin/bash
-# Release-speed knock-out matrix: time a few layers with every compile-time knock-out build
-# (DY_CONV_KNOCKOUT_BUILD=<mask> python -m drone_yolo_b200.build; mask bits: 1 epilogue, 2 MMA, 4 A loads, 8 B loads).
+# Release-speed knock-out matrix: time a few layers with every compile-time knock-out build present under lib/
+# (DY_CONV_KNOCKOUT_BUILD=<mask> python -m drone_yolo_b200.build; mask bits: 1 epilogue math+stores, 2 MMA, 4 A loads,
+#  8 B loads, 16 SiLU without MUFU, 32 no TMA store).
 mkdir -p gpurun_out
-for k in "" _k1 _k2 _k4 _k12 _k15; do
-  lib=drone_yolo_b200/lib/libdroneyolo$k.so
+for lib in drone_yolo_b200/lib/libdroneyolo.so drone_yolo_b200/lib/libdroneyolo_k*.so; do
   [ -f $lib ] || continue
   echo "##### $lib"
   for pat in "$@"; do
