@@ -325,7 +325,9 @@ def run_ours(a):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload_name(a, world), "global_batch": imgs, "micro_batch": eng.mb, "parallelism": f"dp{world}",
-                   "cuda_graph": not a.no_graph, "weights": f"random-init (seed 0) + seeded BN recipe, class-bias shift {a.cls_delta}",
+                   "cuda_graph": not a.no_graph,
+                   "decode": ("fused into the Detect conv tails for %d of %d levels (logits never reach HBM); standalone kernel for the rest"
+                              % (sum(r is None for r in eng.plan.raw_refs), len(eng.plan.raw_refs))), "weights": f"random-init (seed 0) + seeded BN recipe, class-bias shift {a.cls_delta}",
                    "l2": f"inputs larger than L2: {a.batch * 3 * a.imgsz * a.imgsz * 4 / 1e6:.0f} MB of images per step, "
                          f"arena {eng.plan.arena_bytes / 1e6:.0f} MB per micro-batch"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host8.numel() * world,

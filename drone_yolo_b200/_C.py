@@ -36,6 +36,8 @@ class ConvDesc(C.Structure):
         ("up_out", C.c_void_p), ("up_ld", C.c_int32),
         ("weight2", C.c_void_p), ("bias2", C.c_void_p),
         ("Cout2", C.c_int32), ("out2", C.c_void_p), ("out2_ld", C.c_int32),
+        ("tail_decode", C.c_int32), ("y", C.c_void_p), ("y_A", C.c_int32), ("y_nc", C.c_int32), ("y_anchor_off", C.c_int32),
+        ("y_stride", C.c_float),
     ]
 
 
@@ -45,6 +47,7 @@ class DecodeDesc(C.Structure):
         ("stride", C.c_float * 4),
         ("nl", C.c_int32), ("B", C.c_int32), ("nc", C.c_int32), ("dtype", C.c_int32), ("layout", C.c_int32),
         ("out", C.c_void_p),
+        ("A_total", C.c_int32), ("anchor_off", C.c_int32 * 4),
     ]
 
 

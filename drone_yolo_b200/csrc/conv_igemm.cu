@@ -523,6 +523,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         mbar_wait_a(d2b, sctr & 1u);                 // one tail GEMM per tile of this group
         tc_fence_after();
         const uint32_t t2addr = d2_tmem + (static_cast<uint32_t>(q * 32) << 16);
+        if (p.tail_decode) {
+          // ---- fused Detect decode (head.py:100-131): the logits never leave the SM.  Staging = [planes][16 rows][8 cols]
+          //      fp32 (512 B per plane), stored by TMA into the channel-planar prediction tensor (B, 4+nc, A) ----
+          const float* b2 = s_bias + 512;
+          const uint32_t cell = stg + static_cast<uint32_t>(row) * 4u;
+          int nplanes;
+          if (p.tail_decode == 1) {                  // box branch: 4 sides x 16 bins -> DFL expectation -> dist2bbox(xywh) * stride
+            float dist[4];
+#pragma unroll
+            for (int sd = 0; sd < 4; ++sd) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(t2addr + sd * 16, r);
+              tmem_ld_wait();
+              float x[kRegMax];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]) + b2[sd * 16 + i];
+              dist[sd] = dfl_expect(x);
+            }
+            float bx[4];
+            dist2bbox_xywh(static_cast<float>(w0 + (row & 7)) + 0.5f, static_cast<float>(h0 + (row >> 3)) + 0.5f, dist, p.y_stride, bx);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cell + c * 512), "f"(bx[c]) : "memory");
+            nplanes = 4;
+          } else {                                   // class branch: sigmoid
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t2addr, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < p.y_nc) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cell + c * 512), "f"(sigmoid_fast(__uint_as_float(r[c]) + b2[c])) : "memory");
+            nplanes = p.y_nc;
+          }
+          (void)nplanes;
+          fence_proxy_async_smem();
+          tc_fence_before();
+          named_bar_sync(barid, 128);
+          if (leader) {
+            tma_store_4d_a(&p.tmO2, stg, w0, h0, 0, b0);
+            bulk_commit_group();
+          }
+        } else {
         const int nout = (p.N2 + 31) >> 5;           // 32-column fp32 output chunks (the last one may be ragged: TMA clips)
         for (int oc = 0; oc < nout; ++oc) {
           uint32_t r[32];
@@ -548,6 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             tma_store_4d_a(&p.tmO2, stg, oc * 32, w0, h0, b0);
             bulk_commit_group();
           }
+        }
         }
         ++sctr;
       } else if constexpr (CW > 0) {
@@ -785,6 +827,10 @@ static int pick_bn(int cout_pad, int m_tiles, int kiters, int max_bn) {
     const double cost = double(waves) * (kiters * per_k + 600.0) * (1.0 + 0.02 * (n_tiles - 1));   // + A re-reads per extra n tile
     if (cost <= best_cost * 1.001) { if (cost < best_cost) best_cost = cost; best = bn; }          // ties -> wider tile
   }
+  if (env_int("DY_CONV_WIDE_BN", 0)) {                      // experiment: always the widest legal N tile
+    for (int bn = 16; bn <= max_bn && bn <= 256; bn += 16)
+      if (cout_pad % bn == 0 && (!any_tma || bn % 32 == 0 || cout_pad == bn)) best = bn;
+  }
   return best;
 }
 
@@ -823,9 +869,18 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     DY_CHECK_ARG(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "conv: residual slice must be 16B aligned");
   const bool fuse2 = d->weight2 != nullptr;
   if (fuse2) {
-    DY_CHECK_ARG(d->bias2 && d->out2 && d->Cout2 > 0, "conv: fused tail needs weight2, bias2, out2 and Cout2");
-    DY_CHECK_ARG((d->out2_ld * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight2) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(d->bias2) & 15) == 0, "conv: fused tail tensors must be 16B aligned");
+    DY_CHECK_ARG(d->bias2 && d->Cout2 > 0, "conv: fused tail needs weight2, bias2 and Cout2");
+    DY_CHECK_ARG((d->tail_decode || ((d->out2_ld * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0)) &&
+                 (reinterpret_cast<uintptr_t>(d->weight2) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->bias2) & 15) == 0,
+                 "conv: fused tail tensors must be 16B aligned");
+    DY_CHECK_ARG(d->out2 || d->tail_decode, "conv: fused tail needs out2 (or tail_decode)");
+    if (d->tail_decode) {
+      DY_CHECK_ARG(d->tail_decode == 1 || d->tail_decode == 2, "conv: tail_decode must be 1 (box) or 2 (class)");
+      DY_CHECK_ARG(d->y && d->y_A > 0 && d->y_nc > 0 && d->y_anchor_off >= 0, "conv: tail_decode needs y, y_A, y_nc, y_anchor_off");
+      if (!(d->y_nc <= 32 && (d->tail_decode == 1 ? d->Cout2 == 64 : d->Cout2 >= d->y_nc && d->Cout2 <= 32) && d->W % 4 == 0 && d->y_A % 4 == 0 &&
+            d->y_anchor_off % 4 == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0))
+        return fail(DY_ERR_UNSUPPORTED, "conv: tail_decode needs nc <= 32, W, A, anchor offset multiples of 4 and a 16B-aligned y");
+    }
     if (!(d->ksize == 3 && d->stride == 1 && d->Cin > 32 && d->Cin <= 64 && d->Cout == 64 && d->Cout2 <= 64 && d->Cout2 % 4 == 0 &&
           d->residual == nullptr && d->up_out == nullptr && d->act == DY_ACT_SILU))
       return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs k3 s1, 32 < Cin <= 64, Cout 64, Cout2 <= 64, SiLU, no residual / upsample");
@@ -961,7 +1016,17 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
         int rc = encode_map(&p->tmW2, d->weight2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
       }
-      {
+      if (d->tail_decode) {
+        // the level's window of the channel-planar prediction tensor (B, 4+nc, A): x fastest, then y, then channel plane
+        p->tail_decode = d->tail_decode; p->y_nc = d->y_nc; p->y_stride = d->y_stride;
+        const int planes = d->tail_decode == 1 ? 4 : d->y_nc;
+        const float* ybase = d->y + d->y_anchor_off + (d->tail_decode == 1 ? 0 : size_t(4) * d->y_A);
+        const uint64_t dims[4] = {uint64_t(Wo), uint64_t(Ho), uint64_t(planes), uint64_t(d->B)};
+        const uint64_t strides[3] = {uint64_t(Wo) * 4, uint64_t(d->y_A) * 4, uint64_t(4 + d->y_nc) * d->y_A * 4};
+        const uint32_t box[4] = {uint32_t(p->TW), uint32_t(p->TH), uint32_t(planes), 1};
+        int rc = encode_map(&p->tmO2, ybase, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (rc) return rc;
+      } else {
         const uint64_t dims[4] = {uint64_t(d->Cout2), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
         const uint64_t strides[3] = {uint64_t(d->out2_ld) * 4, uint64_t(Wo) * d->out2_ld * 4, uint64_t(Ho) * Wo * d->out2_ld * 4};
         const uint32_t box[4] = {32, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};

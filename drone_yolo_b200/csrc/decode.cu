@@ -16,7 +16,6 @@
 namespace dy {
 
 static constexpr int kDecThreads = 128;
-static constexpr int kRegMax = 16;
 
 struct DecodeParams {
   const void* lvl[4];
@@ -29,30 +28,11 @@ struct DecodeParams {
 __device__ __forceinline__ float load_as_float(const float* p) { return *p; }
 __device__ __forceinline__ float load_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
-// Expectation of a 16-bin distribution given its logits (softmax over the bins, weights 0..15).
-__device__ __forceinline__ float dfl_expect(const float (&x)[kRegMax]) {
-  float m = x[0];
-#pragma unroll
-  for (int i = 1; i < kRegMax; ++i) m = fmaxf(m, x[i]);
-  float s = 0.f, t = 0.f;
-#pragma unroll
-  for (int i = 0; i < kRegMax; ++i) {
-    const float e = __expf(x[i] - m);
-    s += e;
-    t = fmaf(static_cast<float>(i), e, t);
-  }
-  return __fdividef(t, s);
-}
-
 __device__ __forceinline__ void write_box(float* out, size_t plane, float ax, float ay, const float (&d)[4], float stride) {
-  // dist2bbox (utils/tal.py:348-357): lt, rb = chunk; x1y1 = a - lt; x2y2 = a + rb; c = (x1y1+x2y2)/2; wh = x2y2-x1y1
-  const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
-  out[0 * plane] = (x1 + x2) * 0.5f * stride;
-  out[1 * plane] = (y1 + y2) * 0.5f * stride;
-  out[2 * plane] = (x2 - x1) * stride;
-  out[3 * plane] = (y2 - y1) * stride;
+  float b[4];
+  dist2bbox_xywh(ax, ay, d, stride, b);
+  out[0 * plane] = b[0]; out[1 * plane] = b[1]; out[2 * plane] = b[2]; out[3 * plane] = b[3];
 }
-
 template <typename T>
 __global__ void __launch_bounds__(kDecThreads) decode_nhwc_kernel(const __grid_constant__ DecodeParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -121,7 +101,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_nhwc_kernel(const __grid_c
   write_box(o, plane, ax, ay, d, p.stride[l]);
   for (int c = 0; c < p.nc; ++c) {
     const float x = load_as_float(row + 4 * kRegMax + c);
-    o[(4 + c) * plane] = 1.f / (1.f + __expf(-x));
+    o[(4 + c) * plane] = sigmoid_fast(x);
   }
 }
 
@@ -152,7 +132,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_nchw_kernel(const __grid_c
   write_box(o, plane, ax, ay, d, p.stride[l]);
   for (int c = 0; c < p.nc; ++c) {
     const float x = load_as_float(base + static_cast<size_t>(4 * kRegMax + c) * hw);
-    o[(4 + c) * plane] = 1.f / (1.f + __expf(-x));
+    o[(4 + c) * plane] = sigmoid_fast(x);
   }
 }
 
@@ -169,7 +149,7 @@ int decode_launch(const dy_decode_desc* d, size_t out_offset_bytes, cudaStream_t
     DY_CHECK_ARG(d->lvl[l] && d->H[l] > 0 && d->W[l] > 0, "decode: level %d invalid", l);
     p.lvl[l] = d->lvl[l]; p.ld[l] = d->ld[l]; p.H[l] = d->H[l]; p.W[l] = d->W[l];
     p.hw[l] = d->H[l] * d->W[l]; p.stride[l] = d->stride[l];
-    p.tile0[l] = tiles; p.aoff[l] = A;
+    p.tile0[l] = tiles; p.aoff[l] = d->A_total ? d->anchor_off[l] : A;
     tiles += ceil_div(p.hw[l], kDecThreads); A += p.hw[l];
     if (d->layout == DY_NHWC) {
       DY_CHECK_ARG(d->ld[l] >= 4 * kRegMax + d->nc, "decode: ld[%d]=%d < no", l, d->ld[l]);
@@ -177,6 +157,11 @@ int decode_launch(const dy_decode_desc* d, size_t out_offset_bytes, cudaStream_t
                    "decode: NHWC rows must be 16B aligned");
       if (d->ld[l] > max_ld) max_ld = d->ld[l];
     }
+  }
+  if (d->A_total) {
+    for (int l = 0; l < d->nl; ++l)
+      DY_CHECK_ARG(d->anchor_off[l] >= 0 && d->anchor_off[l] + p.hw[l] <= d->A_total, "decode: level %d does not fit A_total", l);
+    A = d->A_total;
   }
   p.nl = d->nl; p.B = d->B; p.nc = d->nc; p.A = A; p.ntiles = tiles;
   p.out = reinterpret_cast<float*>(reinterpret_cast<char*>(d->out) + out_offset_bytes);

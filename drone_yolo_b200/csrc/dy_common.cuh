@@ -58,6 +58,34 @@ __device__ __forceinline__ float silu_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// ---- Detect decode math, shared by decode.cu and the fused Detect tail of conv_igemm.cu (same source -> same results) ----
+static constexpr int kRegMax = 16;
+// Expectation of a 16-bin distribution given its logits (DFL.forward, nn/modules/block.py:73-76: softmax over the bins,
+// weights 0..15).
+__device__ __forceinline__ float dfl_expect(const float (&x)[kRegMax]) {
+  float m = x[0];
+#pragma unroll
+  for (int i = 1; i < kRegMax; ++i) m = fmaxf(m, x[i]);
+  float s = 0.f, t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRegMax; ++i) {
+    const float e = __expf(__fsub_rn(x[i], m));
+    s = __fadd_rn(s, e);
+    t = fmaf(static_cast<float>(i), e, t);
+  }
+  return __fdividef(t, s);
+}
+// dist2bbox(xywh=True) * stride (utils/tal.py:348-357, head.py:129): lt, rb = chunk; x1y1 = a - lt; x2y2 = a + rb;
+// c = (x1y1 + x2y2) / 2; wh = x2y2 - x1y1.  Explicit roundings: no FMA contraction, identical in every caller.
+__device__ __forceinline__ void dist2bbox_xywh(float ax, float ay, const float (&d)[4], float stride, float (&b)[4]) {
+  const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]), x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
+  b[0] = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride);
+  b[1] = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride);
+  b[2] = __fmul_rn(__fsub_rn(x2, x1), stride);
+  b[3] = __fmul_rn(__fsub_rn(y2, y1), stride);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

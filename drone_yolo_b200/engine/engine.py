@@ -33,7 +33,7 @@ class Engine:
     def __init__(self, model, batch: int, imgsz, device, micro_batch: int = 0, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
                  max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True,
-                 input_dtype: torch.dtype = torch.float32):
+                 input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True):
         device = torch.device(device)
         if device.type != "cuda":
             raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
@@ -49,7 +49,7 @@ class Engine:
                 raise _C.DroneYoloError("engine input must be float32 in [0,1] or uint8 0..255")
             self.images = torch.zeros((batch, 3, H, W), device=device, dtype=input_dtype)
             self.y = torch.empty((batch, 4 + self.nc, self.A), device=device, dtype=torch.float32)
-            self.plan = LayerPlan(model, self.mb, H, W, device, self.images, self.y)
+            self.plan = LayerPlan(model, self.mb, H, W, device, self.images, self.y, fuse_decode=fuse_decode)
             ml = bool(multi_label) and self.nc > 1
             self.nms_bufs = K.NmsBuffers(batch, self.nc, self.A, max_det, ml, device)
             self.nms_cfg = dict(conf=conf, iou=iou, max_det=max_det, classes=classes, agnostic=agnostic, multi_label=ml,

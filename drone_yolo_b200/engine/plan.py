@@ -39,7 +39,7 @@ class _Buf:
 class LayerPlan:
     """Symbolic pass -> arena assignment -> dy_program."""
 
-    def __init__(self, model, mb: int, H: int, W: int, device, images: torch.Tensor, y: torch.Tensor):
+    def __init__(self, model, mb: int, H: int, W: int, device, images: torch.Tensor, y: torch.Tensor, fuse_decode: bool = False):
         if H % 32 or W % 32:
             raise _C.DroneYoloError(f"input {H}x{W} must be a multiple of the maximum stride 32")
         self.model, self.mb, self.H, self.W, self.device = model, mb, H, W, device
@@ -48,6 +48,10 @@ class LayerPlan:
         self.keep = []                      # packed weights etc. that must outlive the program
         self.fuse_upsample = not os.environ.get("DY_NO_FUSE_UPSAMPLE")
         self.fuse_tail = not os.environ.get("DY_NO_FUSE_TAIL")
+        # decode inside the Detect tails: the raw maps of those levels are never materialised (Engine.raw_maps() is then
+        # unavailable); needs the whole batch in one replay because the prediction tensor's address is baked into tensor maps
+        self.fuse_decode = (bool(fuse_decode) and self.fuse_tail and not os.environ.get("DY_NO_FUSE_DECODE")
+                            and y is not None and mb == y.shape[0])
         self._build_symbolic()
         self._assign_arena()
         self._emit(images, y)
@@ -199,33 +203,43 @@ class LayerPlan:
 
     def _emit_detect(self, m: Detect, srcs):
         packed = m.packed()
-        levels = []
+        levels, level_off, level_stride, all_levels = [], [], [], []
+        a_off = 0
         for i, src in enumerate(srcs):
             H, W = src.H, src.W
             c2, c3 = m.cv2[i][0].conv.out_channels, m.cv3[i][0].conv.out_channels
             (wf, bf), (wbx, bbx), (wcl, bcl) = packed[i]
             t1 = self._new_buf(c2 + c3, H, W)
-            raw = self._new_buf(m.raw_ld, H, W, esz=4)
             ncp = m.raw_ld - 4 * m.reg_max          # class logits padded to 16 channels (zero weights) -> TMA-store path
             self._op(kind="conv", w=(wf, bf), cout=c2 + c3, k=3, s=1, act=True, inp=src, out=Ref(t1, 0, c2 + c3, H, W))
             # Each branch ends Conv(c,c,3) -> nn.Conv2d(c,n,1) (head.py:41-47).  Where the 64-channel halo kernel applies, the
-            # 1x1 runs inside the 3x3's epilogue (dy_conv_desc.weight2) and the intermediate tensor is never written.
+            # 1x1 runs inside the 3x3's epilogue (dy_conv_desc.weight2) and the intermediate tensor is never written; with
+            # fuse_decode the same epilogue also decodes the logits (dy_conv_desc.tail_decode) and the raw map is skipped too.
             halo_ok = self.fuse_tail and H * W / (-(-W // 8) * 8 * -(-H // 16) * 16) >= 0.8
+            branches = ((m.cv2[i][1], 0, c2, (wbx, bbx), 4 * m.reg_max, 0), (m.cv3[i][1], c2, c3, (wcl, bcl), ncp, 4 * m.reg_max))
+            fusable = [halo_ok and cw == 64 and cout1 <= 64 for (_, _, cw, _, cout1, _) in branches]
+            dec = self.fuse_decode and all(fusable) and m.nc <= 32 and W % 4 == 0 and a_off % 4 == 0
+            raw = None if dec else self._new_buf(m.raw_ld, H, W, esz=4)
             t2 = None
-            for (mod3, cin0, cw, (w1, b1), cout1, c0out) in ((m.cv2[i][1], 0, c2, (wbx, bbx), 4 * m.reg_max, 0),
-                                                            (m.cv3[i][1], c2, c3, (wcl, bcl), ncp, 4 * m.reg_max)):
-                if halo_ok and cw == 64 and cout1 <= 64:
-                    self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=None,
-                             tail=(w1, b1, cout1, Ref(raw, c0out, cout1, H, W)))
+            for bi, (mod3, cin0, cw, (w1, b1), cout1, c0out) in enumerate(branches):
+                if fusable[bi]:
+                    tail = ((w1, b1, cout1, None, (bi + 1, a_off, float(m.stride[i]))) if dec
+                            else (w1, b1, cout1, Ref(raw, c0out, cout1, H, W)))
+                    self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=None, tail=tail)
                 else:
                     if t2 is None:
                         t2 = self._new_buf(c2 + c3, H, W)
                     self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=Ref(t2, cin0, cw, H, W))
                     self._op(kind="conv", w=(w1, b1), cout=cout1, k=1, s=1, act=False, inp=Ref(t2, cin0, cw, H, W),
                              out=Ref(raw, c0out, cout1, H, W))
-            levels.append(Ref(raw, 0, m.no, H, W))
-        self._op(kind="decode", levels=levels, det=m)
-        self.raw_refs = levels
+            if not dec:
+                levels.append(Ref(raw, 0, m.no, H, W)); level_off.append(a_off); level_stride.append(float(m.stride[i]))
+            all_levels.append(None if dec else Ref(raw, 0, m.no, H, W))
+            a_off += H * W
+        if levels:
+            self._op(kind="decode", levels=levels, det=m, strides=level_stride,
+                     anchor_off=level_off if len(levels) < len(srcs) else None)
+        self.raw_refs = all_levels
 
     # ---------------------------------------------------------------------------------------------
     def _assign_arena(self):
@@ -285,9 +299,13 @@ class LayerPlan:
                 up = self.tensor(op["up"]) if op.get("up") is not None else None
                 tail = None
                 if op.get("tail") is not None:
-                    w2, b2, cout2, r2 = op["tail"]
+                    w2, b2, cout2, r2 = op["tail"][:4]
                     self.keep.append((w2, b2))
-                    tail = (w2, b2, cout2, self.tensor(r2))
+                    if r2 is None:                  # fused decode: (mode, first anchor, stride) -> the engine's prediction tensor
+                        mode, a0, st = op["tail"][4]
+                        tail = (w2, b2, cout2, None, (mode, y, a0, st))
+                    else:
+                        tail = (w2, b2, cout2, self.tensor(r2))
                 out_t = self.tensor(op["out"]) if op.get("out") is not None else None
                 d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, out_t, res, up, tail)
                 _C.check(lib.dy_program_add_conv(h, C.byref(d)), "add_conv")
@@ -312,7 +330,7 @@ class LayerPlan:
             elif kind == "decode":
                 det = op["det"]
                 levels = [self.tensor(r) for r in op["levels"]]
-                d = K.decode_desc(levels, [float(s) for s in det.stride.tolist()], det.nc, y)
+                d = K.decode_desc(levels, op["strides"], det.nc, y, op.get("anchor_off"))
                 d.B = mb
                 _C.check(lib.dy_program_add_decode(h, C.byref(d)), "add_decode")
             else:
@@ -324,6 +342,9 @@ class LayerPlan:
 
     def raw_maps(self):
         """The raw head maps of the LAST replayed micro-batch, as the reference's (mb, no, H, W) views."""
+        if any(r is None for r in self.raw_refs):
+            raise _C.DroneYoloError("raw head maps are not materialised when the Detect decode is fused into the conv tails "
+                                    "(build the Engine with fuse_decode=False to inspect them)")
         return [self.tensor(r) for r in self.raw_refs]
 
     def __del__(self):

@@ -109,14 +109,26 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
         d.up_out, d.up_ld = up, uld
     else:
         d.up_out, d.up_ld = None, 0
+    d.tail_decode, d.y, d.y_A, d.y_nc, d.y_anchor_off, d.y_stride = 0, None, 0, 0, 0, 0.0
     if tail is not None:
-        w2, b2, cout2, out2 = tail
-        o2, o2ld, B2, H2, W2, C2 = nhwc_view(out2, "conv tail output")
-        if (B2, H2, W2, C2) != (B, eh, ew, cout2) or out2.dtype != torch.float32:
-            raise _C.DroneYoloError("conv tail output must be fp32 (B, Cout2, Ho, Wo)")
+        w2, b2, cout2, out2 = tail[:4]
+        dec = tail[4] if len(tail) > 4 else None
         if w2.shape != (1, _ceil(cout2, 16), _ceil(cout, BLOCK_K)) or w2.dtype != torch.bfloat16:
             raise _C.DroneYoloError(f"packed tail weight shape {tuple(w2.shape)} does not match {cout}->{cout2}")
-        d.weight2, d.bias2, d.Cout2, d.out2, d.out2_ld = w2.data_ptr(), b2.data_ptr(), cout2, o2, o2ld
+        d.weight2, d.bias2, d.Cout2 = w2.data_ptr(), b2.data_ptr(), cout2
+        if dec is not None:
+            # fused Detect decode: dec = (mode 1 box | 2 class, y (B, 4+nc, A) fp32 contiguous, first anchor of the level, stride)
+            mode, y, anchor_off, stride = dec
+            _C.require_cuda(y)
+            if y.dtype != torch.float32 or not y.is_contiguous() or y.dim() != 3 or y.shape[0] != B:
+                raise _C.DroneYoloError("conv tail decode: y must be a contiguous fp32 (B, 4+nc, A) tensor")
+            d.out2, d.out2_ld = None, 0
+            d.tail_decode, d.y, d.y_A, d.y_nc, d.y_anchor_off, d.y_stride = mode, y.data_ptr(), y.shape[2], y.shape[1] - 4, anchor_off, float(stride)
+        else:
+            o2, o2ld, B2, H2, W2, C2 = nhwc_view(out2, "conv tail output")
+            if (B2, H2, W2, C2) != (B, eh, ew, cout2) or out2.dtype != torch.float32:
+                raise _C.DroneYoloError("conv tail output must be fp32 (B, Cout2, Ho, Wo)")
+            d.out2, d.out2_ld = o2, o2ld
     else:
         d.weight2, d.bias2, d.Cout2, d.out2, d.out2_ld = None, None, 0, None, 0
     return d
@@ -132,7 +144,9 @@ def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, resid
         out = empty_nhwc(B, cout, (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1, x.device, out_dtype)
     d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual, up_out, tail)
     _C.check(_C.lib().dy_conv2d(C.byref(d), _C.stream_ptr(x.device)), "dy_conv2d")
-    return tail[3] if tail is not None else out
+    if tail is not None:
+        return tail[4][1] if len(tail) > 4 and tail[4] is not None else tail[3]
+    return out
 
 
 def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -185,7 +199,8 @@ def dwconv3x3s2(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optio
     return out
 
 
-def decode_desc(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: int, out: torch.Tensor) -> _C.DecodeDesc:
+def decode_desc(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: int, out: torch.Tensor,
+                anchor_off: Optional[Sequence[int]] = None) -> _C.DecodeDesc:
     """levels: per-level raw maps (B, 64+nc, H, W); contiguous NCHW or channels-last (slice), fp32 or bf16."""
     d = _C.DecodeDesc()
     no = 64 + nc
@@ -216,6 +231,11 @@ def decode_desc(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: in
     d.dtype = _C.DY_F32 if dt == torch.float32 else _C.DY_BF16
     d.layout = layouts.pop()
     d.out = out.data_ptr()
+    d.A_total = 0
+    if anchor_off is not None:                      # some levels are decoded elsewhere (fused Detect tails): explicit placement
+        d.A_total = out.shape[2]
+        for i, a in enumerate(anchor_off):
+            d.anchor_off[i] = int(a)
     return d
 
 

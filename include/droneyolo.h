@@ -64,6 +64,10 @@ int dy_device_check(int device);            /* DY_OK iff `device` is compute cap
  *           [ceil16(Cout2)], out2 an fp32 NHWC [B,Ho,Wo,Cout2] slice with pixel stride out2_ld.  Requires ksize 3,
  *           stride 1, 32 < Cin <= 64, Cout == 64, Cout2 <= 64 and a map the 8x16 halo tiles cover well; anything else
  *           returns DY_ERR_UNSUPPORTED (run the two convs separately).
+ * tail_decode : with weight2, decode the tail's logits in the epilogue instead of writing them (Detect._inference,
+ *           head.py:100-131, for this level and branch): 1 = box branch (Cout2 == 64: DFL expectation, dist2bbox, * stride
+ *           -> rows 0..3 of y), 2 = class branch (sigmoid -> rows 4..4+y_nc-1 of y).  y = fp32 [B, 4+y_nc, y_A] (the
+ *           dy_detect_decode output layout), y_anchor_off = first anchor of this level; out2 is then unused.
  * ksize in {1,3}; stride in {1,2} (stride 2 needs even H and W); no dilation, no groups.
  */
 typedef struct dy_conv_desc {
@@ -77,6 +81,7 @@ typedef struct dy_conv_desc {
   void* up_out;        int32_t up_ld;
   const void* weight2; const float* bias2;
   int32_t Cout2;       void* out2;      int32_t out2_ld;
+  int32_t tail_decode; float* y;        int32_t y_A, y_nc, y_anchor_off; float y_stride;
 } dy_conv_desc;
 
 int dy_conv2d(const dy_conv_desc* d, void* stream);
@@ -124,6 +129,8 @@ typedef struct dy_decode_desc {
   const void* lvl[4]; int32_t ld[4]; int32_t H[4]; int32_t W[4]; float stride[4];
   int32_t nl, B, nc, dtype /* dy_dtype */, layout /* dy_layout */;
   float* out;
+  int32_t A_total;          /* anchors per image in `out`; 0 = the sum over the levels given                 */
+  int32_t anchor_off[4];    /* first anchor of each level in `out` when A_total != 0 (levels decoded elsewhere) */
 } dy_decode_desc;
 
 int dy_detect_decode(const dy_decode_desc* d, void* stream);

@@ -388,9 +388,14 @@ def test_model_vs_reference_golden(dev, golden_dir, tag, path):
     if path == "modules":                      # layer-by-layer drop-in modules (un-fused: BN folded on the fly)
         y, raw = m(x)
     else:                                      # fused model through the compiled layer plan + CUDA graph
-        eng = Engine(m.fuse(verbose=False), int(g["B"]), int(g["imgsz"]), dev, conf=0.001, iou=0.7)
+        eng = Engine(m.fuse(verbose=False), int(g["B"]), int(g["imgsz"]), dev, conf=0.001, iou=0.7, fuse_decode=False)
         eng(x)
         y, raw = eng.y, eng.raw_maps()
+        if tag.startswith("s_"):               # the default engine decodes inside the Detect tails (no raw maps): same prediction
+            fused = Engine(m, int(g["B"]), int(g["imgsz"]), dev, conf=0.001, iou=0.7)
+            assert any(r is None for r in fused.plan.raw_refs), "s scale: Detect decode should be fused into the conv tails"
+            fused(x)
+            close(fused.y, y, 1e-5, 1e-4)
     for i, r in enumerate(raw):
         close(r, torch.from_numpy(g[f"raw{i}"].astype(np.float32)), 2e-2, 2e-2)      # north_star: rtol 2e-2
     assert float((y[:, :4].cpu() - torch.from_numpy(g["y"][:, :4])).abs().max()) < 0.5   # north_star: 0.5 px
@@ -412,7 +417,8 @@ def test_engine_vs_cpu_oracle(dev, scale, imgsz, B, mb):
     cpu.eval()
     x = recipe.images(B, imgsz, imgsz)
     y_ref, raw_ref = torch_ref.forward(cpu, x)
-    eng = Engine(copy.deepcopy(cpu).to(dev).fuse(verbose=False), B, imgsz, dev, micro_batch=mb, conf=0.001, iou=0.7)
+    gm = copy.deepcopy(cpu).to(dev).fuse(verbose=False)
+    eng = Engine(gm, B, imgsz, dev, micro_batch=mb, conf=0.001, iou=0.7, fuse_decode=False)
     out, counts = eng(x.to(dev))
     y = eng.y.cpu().numpy()
     for r, rr in zip(eng.raw_maps(), raw_ref):                      # raw maps of the LAST micro-batch
@@ -422,6 +428,15 @@ def test_engine_vs_cpu_oracle(dev, scale, imgsz, B, mb):
     assert_nms_equal(out.cpu().numpy(), counts.cpu().numpy(), eng.nms_bufs.kept.cpu().numpy(), ref_out, ref_kept)
     out2, counts2 = eng(x.to(dev))                                  # graph replay is deterministic
     assert torch.equal(out2, out) and torch.equal(counts2, counts)
+    # default engine (whole batch per replay, Detect decode fused into the conv tails where the kernels allow it): boxes
+    # against the CPU oracle, NMS bit-exact against the oracle run on ITS pre-NMS tensor
+    fused = Engine(gm, B, imgsz, dev, conf=0.001, iou=0.7)
+    fo, fc = fused(x.to(dev))
+    fy = fused.y.cpu().numpy()
+    assert np.abs(fy[:, :4] - y_ref[:, :4]).max() < 0.5
+    np.testing.assert_allclose(fy[:, 4:], y_ref[:, 4:], rtol=2e-2, atol=1e-4)
+    f_ref, f_kept = nms_np.non_max_suppression(fy, return_kept=True, conf_thres=0.001, iou_thres=0.7, max_det=300)
+    assert_nms_equal(fo.cpu().numpy(), fc.cpu().numpy(), fused.nms_bufs.kept.cpu().numpy(), f_ref, f_kept)
 
 
 def test_predict_api_matches_engine(dev):

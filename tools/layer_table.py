@@ -27,6 +27,7 @@ def plan_ops(scale, imgsz, batch):
     lp.bufs, lp.ops, lp.keep = [], [], []
     lp.fuse_upsample = True
     lp.fuse_tail = True
+    lp.fuse_decode = False
     lp._build_symbolic()
     rows = []
     for op in lp.ops:
