@@ -28,6 +28,7 @@ static constexpr int kK = 512;                 // candidates per greedy round (=
 static constexpr int kWords = kK / 32;
 static constexpr int kBins = 2048;
 static constexpr int kBig = 4096;               // keys selected + sorted per super-round
+static constexpr int kFirst = 2048;             // ... of the first super-round (half the select + sort cost)
 static constexpr int kMaxPasses = 8;
 static constexpr int kMaxClassWords = 32;      // class filter bitmask: nc <= 1024
 
@@ -173,8 +174,26 @@ __device__ __forceinline__ bool iou_suppresses(const float4& a, float area_a, co
   const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
   const float inter = __fmul_rn(w, h);
   if (!(inter > 0.f)) return false;           // 0/x == 0 and 0/0 == NaN never exceed a threshold in [0,1]
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  // The IEEE division costs ~10 instructions; the approximate quotient (2 ulp) decides every pair that is not within a
+  // relative 1e-5 of the threshold, the exact one only the rest (same result as always dividing exactly).
+  const float q = __fdividef(inter, uni);
+  if (q > thr * 1.00001f) return true;
+  if (q < thr * 0.99999f) return false;
+  const float ovr = __fdiv_rn(inter, uni);
   return inclusive ? (ovr >= thr) : (ovr > thr);
+}
+
+// Branch-free form for the two hot loops (several independent tests in flight per thread: the loops were latency-bound on
+// one LDS -> compare -> branch chain per box): returns 1 = suppresses, 0 = does not, 2 = within 1e-5 of the threshold
+// (the caller then decides with the exact division of iou_suppresses).
+__device__ __forceinline__ int iou_class(const float4& a, float area_a, const float4& b, float area_b, float thr_lo, float thr_hi) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  const float q = __fdividef(inter, uni);          // inter == 0 -> 0 (or NaN for 0/0): never above the threshold
+  return (q > thr_hi) ? 1 : ((q >= thr_lo) ? 2 : 0);  // NaN compares false twice -> 0, as the exact test gives
 }
 
 struct SelShared {
@@ -225,6 +244,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   const int limit = min(n, p.max_nms);
   if (tid == 0) s.kept = 0;
   __syncthreads();
+  const float thr_lo = p.iou_f * 0.99999f, thr_hi = p.iou_f * 1.00001f;
 
   int processed = 0;
   unsigned long long prev_T = 0ull;            // keys taken so far are exactly the keys <= prev_T
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   bool done = false;
   while (processed < limit && !done) {
     // =============== super-round: the next SK (<= 4096) smallest keys, selected once and sorted in shared memory ===============
-    const int SK = min(kBig, limit - processed);
+    const int SK = min(first ? kFirst : kBig, limit - processed);   // most images reach max_det inside the first ~2000 ranks
     unsigned long long prefix_val = 0ull, prefix_mask = 0ull;
     unsigned int k_rem = static_cast<unsigned>(SK);
     const bool take_all = (n - processed) <= SK;          // everything left fits: no selection needed
@@ -346,7 +366,23 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       bool dead = !have;
       const int kept0 = s.kept;
       if (have) {
-        for (int i = 0; i < kept0 && !dead; ++i) dead = iou_suppresses(kbox[i], karea[i], mybox, myarea, p.iou_f, p.iou_inclusive);
+        // four kept boxes per trip, tested independently (kbox / karea have max_det entries; kept0 <= max_det)
+        for (int i = 0; i < kept0 && !dead; i += 4) {
+          int c[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ii = min(i + u, kept0 - 1);
+            c[u] = iou_class(kbox[ii], karea[ii], mybox, myarea, thr_lo, thr_hi);
+          }
+          if ((c[0] | c[1] | c[2] | c[3]) & 1) dead = true;
+          else if ((c[0] | c[1] | c[2] | c[3]) & 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int ii = min(i + u, kept0 - 1);
+              if (c[u] == 2 && iou_suppresses(kbox[ii], karea[ii], mybox, myarea, p.iou_f, p.iou_inclusive)) dead = true;
+            }
+          }
+        }
       }
       const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
       if (lane == 0) s.remv[warp] = dead_bits;
@@ -371,11 +407,19 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
             if (i >= j0) todo &= ~((2u << (i - j0)) - 1u);               // only j > i
             if (todo) {
               const float4 bi = s.box[i]; const float ai = s.area[i];
-              while (todo) {
-                const int jj = __ffs(todo) - 1;
-                todo &= todo - 1u;
-                const int j = j0 + jj;
-                if (iou_suppresses(bi, ai, s.box[j], s.area[j], p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+              // four columns per trip, tested independently and masked afterwards (s.box has kK entries: j < kK always)
+              for (int jj0 = 0; jj0 < 32; jj0 += 4) {
+                const unsigned m4 = (todo >> jj0) & 0xfu;
+                if (!m4) continue;
+                int c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) c[u] = iou_class(bi, ai, s.box[j0 + jj0 + u], s.area[j0 + jj0 + u], thr_lo, thr_hi);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (!((m4 >> u) & 1u)) continue;
+                  if (c[u] == 1 || (c[u] == 2 && iou_suppresses(bi, ai, s.box[j0 + jj0 + u], s.area[j0 + jj0 + u], p.iou_f, p.iou_inclusive)))
+                    bits |= 1u << (jj0 + u);
+                }
               }
             }
           }
