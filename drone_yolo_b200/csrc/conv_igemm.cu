@@ -524,11 +524,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         tc_fence_after();
         const uint32_t t2addr = d2_tmem + (static_cast<uint32_t>(q * 32) << 16);
         if (p.tail_decode) {
-          // ---- fused Detect decode (head.py:100-131): the logits never leave the SM.  Staging = [planes][16 rows][8 cols]
-          //      fp32 (512 B per plane), stored by TMA into the channel-planar prediction tensor (B, 4+nc, A) ----
+          // ---- fused Detect decode (head.py:100-131): the logits never leave the SM.  Each thread owns one anchor (its
+          //      accumulator row) and writes its values straight into the channel-planar prediction tensor (B, 4+nc, A):
+          //      a warp covers 4 tile rows x 8 columns = four full 32-byte sectors per plane and store instruction ----
           const float* b2 = s_bias + 512;
-          const uint32_t cell = stg + static_cast<uint32_t>(row) * 4u;
-          int nplanes;
+          const int w = w0 + (row & 7), h = h0 + (row >> 3);
+          const bool inside = (w < p.Wo) && (h < p.Ho);
+          float* yp = p.y + (static_cast<size_t>(b0) * (4 + p.y_nc)) * p.y_A + static_cast<size_t>(h) * p.Wo + w;
           if (p.tail_decode == 1) {                  // box branch: 4 sides x 16 bins -> DFL expectation -> dist2bbox(xywh) * stride
             float dist[4];
 #pragma unroll
@@ -542,27 +544,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               dist[sd] = dfl_expect(x);
             }
             float bx[4];
-            dist2bbox_xywh(static_cast<float>(w0 + (row & 7)) + 0.5f, static_cast<float>(h0 + (row >> 3)) + 0.5f, dist, p.y_stride, bx);
+            dist2bbox_xywh(static_cast<float>(w) + 0.5f, static_cast<float>(h) + 0.5f, dist, p.y_stride, bx);
+            if (inside) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cell + c * 512), "f"(bx[c]) : "memory");
-            nplanes = 4;
-          } else {                                   // class branch: sigmoid
+              for (int c = 0; c < 4; ++c) yp[static_cast<size_t>(c) * p.y_A] = bx[c];
+            }
+          } else {                                   // class branch: sigmoid -> rows 4 .. 4+nc-1
             uint32_t r[32];
             tmem_ld_32x32b_x32(t2addr, r);
             tmem_ld_wait();
+            if (inside) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (c < p.y_nc) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cell + c * 512), "f"(sigmoid_fast(__uint_as_float(r[c]) + b2[c])) : "memory");
-            nplanes = p.y_nc;
+              for (int c = 0; c < 32; ++c)
+                if (c < p.y_nc) yp[static_cast<size_t>(4 + c) * p.y_A] = sigmoid_fast(__uint_as_float(r[c]) + b2[c]);
+            }
           }
-          (void)nplanes;
-          fence_proxy_async_smem();
-          tc_fence_before();
-          named_bar_sync(barid, 128);
-          if (leader) {
-            tma_store_4d_a(&p.tmO2, stg, w0, h0, 0, b0);
-            bulk_commit_group();
-          }
+          tc_fence_before();                         // D2 fully read before the next tile's tail GEMM overwrites it
         } else {
         const int nout = (p.N2 + 31) >> 5;           // 32-column fp32 output chunks (the last one may be ragged: TMA clips)
         for (int oc = 0; oc < nout; ++oc) {
@@ -1017,15 +1014,9 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
         if (rc) return rc;
       }
       if (d->tail_decode) {
-        // the level's window of the channel-planar prediction tensor (B, 4+nc, A): x fastest, then y, then channel plane
+        // the threads store straight into the level's window of the channel-planar prediction tensor (B, 4+nc, A)
         p->tail_decode = d->tail_decode; p->y_nc = d->y_nc; p->y_stride = d->y_stride;
-        const int planes = d->tail_decode == 1 ? 4 : d->y_nc;
-        const float* ybase = d->y + d->y_anchor_off + (d->tail_decode == 1 ? 0 : size_t(4) * d->y_A);
-        const uint64_t dims[4] = {uint64_t(Wo), uint64_t(Ho), uint64_t(planes), uint64_t(d->B)};
-        const uint64_t strides[3] = {uint64_t(Wo) * 4, uint64_t(d->y_A) * 4, uint64_t(4 + d->y_nc) * d->y_A * 4};
-        const uint32_t box[4] = {uint32_t(p->TW), uint32_t(p->TH), uint32_t(planes), 1};
-        int rc = encode_map(&p->tmO2, ybase, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
-        if (rc) return rc;
+        p->y = d->y + d->y_anchor_off; p->y_A = d->y_A;
       } else {
         const uint64_t dims[4] = {uint64_t(d->Cout2), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
         const uint64_t strides[3] = {uint64_t(d->out2_ld) * 4, uint64_t(Wo) * d->out2_ld * 4, uint64_t(Ho) * Wo * d->out2_ld * 4};

@@ -28,7 +28,7 @@ struct ConvParams {
   int has_up;
   int fuse2, N2;                       // fused 1x1 tail (Detect output conv): N2 = Cout2 padded to 16
   const float* bias2;
-  int tail_decode, y_nc; float y_stride;   // fused Detect decode of the tail's logits (tmO2 then maps the prediction tensor)
+  int tail_decode, y_nc, y_A; float y_stride; float* y;   // fused Detect decode of the tail's logits (tmO2 then maps the prediction tensor)
   int nbuf;                            // staging tiles per epilogue group (2, or 1 when shared memory is short)
   int dbg;
   unsigned long long* trace;           // debug builds only (DY_CONV_TRACE)
