@@ -834,14 +834,16 @@ static int pick_bn(int cout_pad, int m_tiles, int kiters, int max_bn) {
 // Pixel-tile shape (TW x TH x TB <= 128 rows) maximising the fraction of MMA rows that are real pixels.
 static void pick_tile(int Wo, int Ho, int B, int* TW, int* TH, int* TB) {
   double best = -1.0; int bw = 1, bh = 1, bb = 1;
+  const bool flat_ties = env_int("DY_TILE_FLAT", 0) != 0;
   for (int tw = 1; tw <= Wo && tw <= 128; ++tw) {
     for (int th = 1; th <= Ho && tw * th <= 128; ++th) {
       const int tb_max = 128 / (tw * th);                                // a tile may span several images
       for (int tb = 1; tb <= tb_max && tb <= B; ++tb) {
         const double tiles = double(ceil_div(Wo, tw)) * ceil_div(Ho, th) * ceil_div(B, tb);
         const double eff = double(Wo) * Ho * B / (tiles * 128.0);
-        // prefer wide boxes (longer contiguous runs for TMA) on ties
-        const double score = eff + 1e-6 * tw;
+        // ties: compact 2-D tiles first (a 16x8 tile re-reads 10 input rows per 8 output rows through its 3x3 taps, a
+        // 16x1x8 tile 3 per 1: same L2->SM traffic, but the re-reads miss L2 at batch 64), then wide boxes (long TMA runs)
+        const double score = eff + (flat_ties ? 0.0 : 1e-4 * (th < 8 ? th : 8) / 8.0) + 1e-6 * tw;
         if (score > best) { best = score; bw = tw; bh = th; bb = tb; }
       }
     }
