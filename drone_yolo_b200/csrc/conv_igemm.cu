@@ -752,7 +752,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       if (acc >= nacc) { acc -= nacc; acc_phase ^= 1u; }
       it = nx;
     }
-    if (CW > 0 && leader) bulk_wait_group<0>();     // all bulk stores complete before the CTA retires its smem
+    if (CW > 0 && leader) bulk_wait_group_read<0>();   // the bulk stores have READ the staging tiles (the CTA may retire its smem);
+                                                       // their global writes complete asynchronously, ordered by the kernel boundary
   }
 
   tc_fence_before();
@@ -912,7 +913,11 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   if (mode == 3 || mode == 4) {
     // halo: resident weights of ONE n tile per CTA (9 x BN rows); several n tiles -> static split of the grid
     const int m_tiles = ceil_div(Wo, kHaloTW) * ceil_div(Ho, kHaloTH) * d->B;
-    const int bn = fuse2 ? 64 : pick_bn(cout_pad, m_tiles, 9, mode == 4 ? 128 : 64);   // the fused tail contracts over all 64 channels of one tile
+    // 64 -> 128 (the merged first Detect convs): one N = 128 tile reads every activation row once for 128 outputs (64
+    // cycles per MMA, tensor- and smem-balanced) where two N = 64 halves read it twice (2 x 48): all 147 KB of weights stay
+    // resident, at the price of two halo stages and one staging tile per epilogue group.
+    const bool wide_halo = (mode == 3 && cout_pad == 128 && !fuse2 && !env_int("DY_HALO_NO_BN128", 0));
+    const int bn = fuse2 ? 64 : (wide_halo ? 128 : pick_bn(cout_pad, m_tiles, 9, mode == 4 ? 128 : 64));   // the fused tail contracts over all 64 channels of one tile
     if (cout_pad / bn > 4 || cout_pad / bn > sms) mode = 1;
     else { p->BN = bn; p->n_tiles = cout_pad / bn; p->n_split = p->n_tiles; }
   }
@@ -1072,7 +1077,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   // cover the activation tile.  Everything else streams B next to A.
   const int cw = p->use_tma_store;
   // K-heavy generic tiles: one staging tile per group (the epilogue has slack), the room goes to fatter pipeline stages
-  p->nbuf = (!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) ? 1 : 2;
+  p->nbuf = ((!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) || (mode == 3 && p->BN > 64)) ? 1 : 2;
   const int staging = 2 * p->nbuf * 128 * cw * out_esz;                     // 2 groups x nbuf tiles
   const int budget = kMaxDynSmem - 1024 - staging;
   const int b_tile = p->BN * rowb;

@@ -3,7 +3,7 @@
 //
 // The CUDA-core stem (aux_kernels.cu) was FP32-issue bound at 5-6x its HBM roofline.  Here the 27-deep contraction is
 // padded to K = 32 and runs as an M128 x N(Cout) x K32 tcgen05 GEMM per 32x4-pixel output tile:
-//   * warp 0 (one thread): TMA brings the [3 ch][9 rows][65+ cols] input patch of the tile (NCHW planes, element type u8 or
+//   * warps 0 and 2 (one thread each, alternate tiles): TMA brings the [3 ch][9 rows][65+ cols] input patch of the tile (NCHW planes, element type u8 or
 //     fp32; out-of-image coordinates are zero-filled = the conv padding);
 //   * warps 4..7 / 8..11 (two groups of 128 "builder" threads on alternate tiles, one output pixel each): im2col row of 27
 //     values from the patch -> bf16 -> one
@@ -98,20 +98,32 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
   const int tile_begin = static_cast<int>(blockIdx.x) * per + min(static_cast<int>(blockIdx.x), rem);
   const int my_tiles = per + (static_cast<int>(blockIdx.x) < rem ? 1 : 0);
 
-  if (warp == 0) {
-    // ===================== patch producer =====================
+  if (warp == 0 || warp == 2) {
+    // ===================== patch producers: two threads (warps 0 and 2) on alternate tiles.  One thread's per-tile chain
+    // (wait for the free slot, expect_tx, TMA issue, index arithmetic) is ~450 cycles, more than a tile is allowed to cost;
+    // np is even, so every slot always belongs to the same producer =====================
     if (elect_one()) {
-      int tw = tile_begin % p.tiles_w, th = (tile_begin / p.tiles_w) % p.tiles_h, tb = tile_begin / (p.tiles_w * p.tiles_h);
-      int s = 0; uint32_t ph = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(&pempty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&pfull[s], (p.dbg & 4) ? 0u : static_cast<uint32_t>(p.patch_bytes));
+      const int pi = warp == 0 ? 0 : 1;
+      const int t0 = tile_begin + pi;
+      int tw = t0 % p.tiles_w, th = (t0 / p.tiles_w) % p.tiles_h, tb = t0 / (p.tiles_w * p.tiles_h);
+      int s = pi; uint32_t ph = 0;
+      const uint32_t pf0 = smem_u32(&pfull[0]), pe0 = smem_u32(&pempty[0]);
+      const uint32_t tx = (p.dbg & 4) ? 0u : static_cast<uint32_t>(p.patch_bytes);
+      const int np = p.np, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+      bool ok = mbar_try_wait_a(pe0 + s * 8, 1u);
+      for (int i = pi; i < my_tiles; i += 2) {
+        if (!ok) mbar_wait_a(pe0 + s * 8, ph ^ 1u);
+        mbar_arrive_expect_tx_a(pf0 + s * 8, tx);
+        int ns = s + 2; uint32_t nph = ph;
+        if (ns >= np) { ns -= np; nph ^= 1u; }
+        ok = mbar_try_wait_a(pe0 + ns * 8, nph ^ 1u);          // wait-ahead: resolved while the TMA issues
         if (!(p.dbg & 4)) asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(patch0 + s * patch_stride), "l"(reinterpret_cast<uint64_t>(&p.tmIn)), "r"(smem_u32(&pfull[s])),
+            ::"r"(patch0 + s * patch_stride), "l"(reinterpret_cast<uint64_t>(&p.tmIn)), "r"(pf0 + s * 8),
               "r"(2 * tw * kStemTW - (U8 ? kStemLeftU8 : kStemLeftF32)), "r"(2 * th * kStemTH - 1), "r"(3 * tb) : "memory");
-        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tb; } }
-        if (++s == p.np) { s = 0; ph ^= 1u; }
+        for (int k = 0; k < 2; ++k)                             // advance two tiles
+          if (++tw == tiles_w) { tw = 0; if (++th == tiles_h) { th = 0; ++tb; } }
+        s = ns; ph = nph;
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -290,7 +302,7 @@ int stem_tc_launch(const void* in, int in_dtype, int B, int H, int W, const floa
     int rc = encode_map(&p.tmO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     if (rc) return rc;
   }
-  p.np = u8 ? 16 : 12;
+  p.np = u8 ? 16 : 12;                                       // even: the two patch producers own alternate slots
   const int smem = 1024 + 8192 + kStemNA * kStemABytes + 4 * 8192 + p.np * ((p.patch_bytes + 1023) & ~1023);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   static bool attr_set[2] = {false, false};
