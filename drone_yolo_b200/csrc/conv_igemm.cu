@@ -535,12 +535,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             float dist[4];
 #pragma unroll
             for (int sd = 0; sd < 4; ++sd) {
+              float4 bq[4];                          // this side's 16 bias values: four 16-byte loads in flight with the TMEM load
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bq[i] = *reinterpret_cast<const float4*>(b2 + sd * 16 + 4 * i);
               uint32_t r[16];
               tmem_ld_32x32b_x16(t2addr + sd * 16, r);
               tmem_ld_wait();
               float x[kRegMax];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]) + b2[sd * 16 + i];
+              for (int i = 0; i < 4; ++i) {
+                x[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bq[i].x; x[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
+                x[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z; x[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
+              }
               dist[sd] = dfl_expect(x);
             }
             float bx[4];
@@ -550,13 +556,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               for (int c = 0; c < 4; ++c) yp[static_cast<size_t>(c) * p.y_A] = bx[c];
             }
           } else {                                   // class branch: sigmoid -> rows 4 .. 4+nc-1
+            float4 bq[4];                            // N2 <= 32 here; the model's class heads have nc <= 16 logits per anchor
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bq[i] = *reinterpret_cast<const float4*>(b2 + 4 * i);
             uint32_t r[32];
-            tmem_ld_32x32b_x32(t2addr, r);
+            tmem_ld_32x32b_x16(t2addr, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+            if (p.N2 > 16) tmem_ld_32x32b_x16(t2addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
             tmem_ld_wait();
             if (inside) {
+              const float bl[16] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w,
+                                    bq[2].x, bq[2].y, bq[2].z, bq[2].w, bq[3].x, bq[3].y, bq[3].z, bq[3].w};
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (c < p.y_nc) yp[static_cast<size_t>(4 + c) * p.y_A] = sigmoid_fast(__uint_as_float(r[c]) + b2[c]);
+              for (int c = 0; c < 16; ++c)
+                if (c < p.y_nc) yp[static_cast<size_t>(4 + c) * p.y_A] = sigmoid_fast(__uint_as_float(r[c]) + bl[c]);
+              if (p.y_nc > 16) {
+#pragma unroll
+                for (int c = 16; c < 32; ++c)
+                  if (c < p.y_nc) yp[static_cast<size_t>(4 + c) * p.y_A] = sigmoid_fast(__uint_as_float(r[c]) + b2[c]);
+              }
             }
           }
           tc_fence_before();                         // D2 fully read before the next tile's tail GEMM overwrites it
