@@ -27,7 +27,7 @@ def plan_ops(scale, imgsz, batch):
     lp.bufs, lp.ops, lp.keep = [], [], []
     lp.fuse_upsample = True
     lp.fuse_tail = True
-    lp.fuse_decode = False
+    lp.fuse_decode = True
     lp._build_symbolic()
     rows = []
     for op in lp.ops:
@@ -40,19 +40,22 @@ def plan_ops(scale, imgsz, batch):
             inp, out = op["inp"], op["out"]
             cin = inp.c
             tail = op.get("tail")
+            dec = bool(tail) and len(tail) > 4
             if out is None:
-                out = tail[3]
+                out = tail[3] if not dec else inp
             M = batch * out.H * out.W
             flops = 2.0 * M * cout * k * k * cin
-            oes = lp.bufs[out.buf].esz
-            byts = batch * inp.H * inp.W * cin * 2 + M * (tail[2] if tail else cout) * oes + k * k * cin * cout * 2
+            oes = 4 if dec else lp.bufs[out.buf].esz
+            # fused decode writes 4 box values (box tail) or nc class scores (class tail) per anchor instead of the raw map
+            ocols = (4 if tail[4][0] == 1 else lp.model.model[-1].nc) if dec else (tail[2] if tail else cout)
+            byts = batch * inp.H * inp.W * cin * 2 + M * ocols * oes + k * k * cin * cout * 2
             if tail:
                 flops += 2.0 * M * cout * tail[2]
             if op.get("res") is not None:
                 byts += M * cout * 2
             if op.get("up") is not None:
                 byts += 4 * M * cout * 2
-            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (f" +1x1->{op['tail'][2]}" if op.get("tail") else "") + (" f32" if oes == 4 else ""),
+            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (f" +1x1->{op['tail'][2]}" if op.get("tail") else "") + (" +decode" if dec else "") + (" f32" if oes == 4 else ""),
                              flops=flops, bytes=byts))
         elif kind == "stem":
             out = op["out"]
@@ -70,7 +73,8 @@ def plan_ops(scale, imgsz, batch):
                              bytes=batch * (inp.H * inp.W * inp.c + out.H * out.W * out.c) * 2))
         elif kind == "decode":
             A = sum(r.H * r.W for r in op["levels"])
-            rows.append(dict(name=f"decode A={A}", flops=0, bytes=batch * A * (80 * 4 + 14 * 4)))
+            nc = op["det"].nc
+            rows.append(dict(name=f"decode A={A}", flops=0, bytes=batch * A * ((64 + nc + (-nc) % 16) * 4 + (4 + nc) * 4)))
     return rows
 
 
