@@ -139,6 +139,11 @@ __device__ __forceinline__ bool umma_bf16_ss_x4_waitahead_p(uint32_t lead, uint3
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared (src, dst and bytes multiples of 16), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

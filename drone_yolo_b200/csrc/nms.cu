@@ -36,6 +36,7 @@ struct NmsParams {
   const float* pred; float* pred_rw;
   int B, nc, A, nchunks;
   float conf; float iou_f; int iou_inclusive;
+  float iou_c;                                 // (1 - 2e-5) * thr / (1 + thr): screening factor, see box_inter / iou_decide (NaN: always decide exactly)
   int max_det, max_nms; float max_wh;
   int agnostic, multi_label, in_place, has_class_filter;
   uint32_t class_mask[kMaxClassWords];
@@ -184,24 +185,52 @@ __device__ __forceinline__ bool iou_suppresses(const float4& a, float area_a, co
   return inclusive ? (ovr >= thr) : (ovr > thr);
 }
 
-// Branch-free form for the two hot loops (several independent tests in flight per thread: the loops were latency-bound on
-// one LDS -> compare -> branch chain per box): returns 1 = suppresses, 0 = does not, 2 = within 1e-5 of the threshold
-// (the caller then decides with the exact division of iou_suppresses).
-__device__ __forceinline__ int iou_class(const float4& a, float area_a, const float4& b, float area_b, float thr_lo, float thr_hi) {
+// Division-free screening for the two hot loops (they are instruction-issue-bound: 512 threads share one SM).
+//   IoU > thr  <=>  inter > thr * (area_a + area_b - inter)  <=>  inter > c * (area_a + area_b),  c = thr / (1 + thr).
+// Every box carries sl = c * (1 - 2e-5) * area (NaN when the area is not a positive finite number), so one add gives the
+// lower bound S of the undecided band.  inter < S: the pair certainly does not suppress (11 instructions per pair).
+// Otherwise (rare) iou_decide looks again: inter > S * (1 + 4e-5) certainly suppresses; inside the band, or when S is NaN
+// (degenerate boxes, thr ~ 0), the exact IEEE division of iou_suppresses decides.  The rounding of S, of c and of the
+// reference's own fp32 quotient are all below 1e-6 relative, so outside the band the exact test gives the same answer.
+static constexpr float kScreenLo = 0.99998f, kScreenHiOverLo = 1.00004f;
+
+__device__ __forceinline__ float box_inter(const float4& a, const float4& b) {
   const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
   const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-  const float inter = __fmul_rn(w, h);
-  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-  const float q = __fdividef(inter, uni);          // inter == 0 -> 0 (or NaN for 0/0): never above the threshold
-  return (q > thr_hi) ? 1 : ((q >= thr_lo) ? 2 : 0);  // NaN compares false twice -> 0, as the exact test gives
+  return __fmul_rn(w, h);
 }
+
+__device__ __forceinline__ float screen_area(float area, float c_lo) {
+  return (area > 0.f && area < 3.0e38f) ? __fmul_rn(area, c_lo) : __int_as_float(0x7fc00000);
+}
+
+// second look at a pair the screen could not rule out
+__device__ __forceinline__ bool iou_decide(const float4& a, float area_a, const float4& b, float area_b, float inter, float S,
+                                           float thr, int inclusive) {
+  if (inter > __fmul_rn(S, kScreenHiOverLo)) return true;
+  return iou_suppresses(a, area_a, b, area_b, thr, inclusive);
+}
+
+#ifdef DY_CONV_DEBUG
+// debug builds only: per-image clock totals of the select kernel's phases (tools/trace_nms.py)
+__device__ unsigned long long g_nms_trace[1024 * 16];
+#define NMS_T0() long long t_ph = clock64()
+#define NMS_TP(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_now = clock64(); g_nms_trace[(blockIdx.x & 1023) * 16 + (k)] += t_now - t_ph; t_ph = t_now; } } while (0)
+#define NMS_TC(k, v) do { if (threadIdx.x == 0) g_nms_trace[(blockIdx.x & 1023) * 16 + (k)] += (v); } while (0)
+#else
+#define NMS_T0()
+#define NMS_TP(k)
+#define NMS_TC(k, v)
+#endif
 
 struct SelShared {
   float4 box[kK];
   float area[kK];
+  float sarea[kK];                 // iou_c * area (screening form); 16-byte aligned
   unsigned int hist[kBins];
   unsigned int mask[kWords * (kK + 1)];
   unsigned int remv[kWords];
+  unsigned int undw[kWords], keptw[kWords];   // greedy fixed point: undecided / kept candidates, one word per warp
   int scan_tmp[kSelThreads / 32];
   unsigned short kidx[kK];
   int sel_count;
@@ -210,6 +239,8 @@ struct SelShared {
 };
 
 static constexpr size_t kSelSharedBytes = (sizeof(SelShared) + 15) & ~size_t(15);
+__host__ __device__ inline int kept_pad(int max_det) { return (max_det + 4 + 3) & ~3; }
+__host__ __device__ inline size_t kept_bytes(int max_det) { return (static_cast<size_t>(kept_pad(max_det)) * (16 + 4 + 4 + 4 + 8) + 15) & ~size_t(15); }
 
 __device__ __forceinline__ void load_offset_box(const NmsParams& p, const float* img, unsigned long long key,
                                                 float4* box, float* area) {
@@ -230,12 +261,15 @@ __device__ __forceinline__ void load_offset_box(const NmsParams& p, const float*
 __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_constant__ NmsParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SelShared& s = *reinterpret_cast<SelShared*>(smem_raw);
-  // kept-box state lives behind SelShared: boxes, areas, keys, ranks (max_det entries each)
+  // kept-box state lives behind SelShared: boxes, screening areas, areas, ranks, keys (mdp entries each; the entries past
+  // the kept count hold a zero box and sarea = +inf, which the screen always rules out: the loop below reads 4 at a time)
+  const int mdp = kept_pad(p.max_det);
   float4* kbox = reinterpret_cast<float4*>(smem_raw + kSelSharedBytes);
-  unsigned long long* kkey = reinterpret_cast<unsigned long long*>(kbox + p.max_det);
-  float* karea = reinterpret_cast<float*>(kkey + p.max_det);
-  int* krank = reinterpret_cast<int*>(karea + p.max_det);
-  unsigned long long* big = reinterpret_cast<unsigned long long*>(smem_raw + kSelSharedBytes + ((static_cast<size_t>(p.max_det) * 32 + 15) & ~size_t(15)));
+  float* ksarea = reinterpret_cast<float*>(kbox + mdp);
+  float* karea = ksarea + mdp;
+  int* krank = reinterpret_cast<int*>(karea + mdp);
+  unsigned long long* kkey = reinterpret_cast<unsigned long long*>(krank + mdp);
+  unsigned long long* big = reinterpret_cast<unsigned long long*>(smem_raw + kSelSharedBytes + kept_bytes(p.max_det));
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.img_count[b];
@@ -243,9 +277,11 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   const unsigned long long* keys = p.keys + static_cast<size_t>(b) * p.cap;
   const int limit = min(n, p.max_nms);
   if (tid == 0) s.kept = 0;
+  for (int i = tid; i < mdp; i += kSelThreads) { kbox[i] = make_float4(0.f, 0.f, 0.f, 0.f); ksarea[i] = __int_as_float(0x7f800000); }
   __syncthreads();
-  const float thr_lo = p.iou_f * 0.99999f, thr_hi = p.iou_f * 1.00001f;
 
+  NMS_T0();
+  NMS_TC(11, n);
   int processed = 0;
   unsigned long long prev_T = 0ull;            // keys taken so far are exactly the keys <= prev_T
   bool first = true;
@@ -316,6 +352,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       }
     }
     const unsigned long long T = take_all ? ~0ull : prefix_val;
+    NMS_TP(0); NMS_TC(9, 1);
 
     // ---- gather keys in (prev_T, T] into big[] and bitonic-sort them ascending ----
     int npow = kK;                                   // sort size: next power of two >= SK (>= 512)
@@ -341,8 +378,13 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       }
     }
     __syncthreads();
+    NMS_TP(1);
+    // bitonic network, two strides per barrier: a thread takes the four elements {i, i+h, i+2h, i+3h} through the
+    // compare-exchanges of strides 2h and h in registers (36 shared-memory round trips for 2048 keys instead of 66);
+    // a stage with an odd number of strides starts with one plain pair step.
     for (int size = 2; size <= npow; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      int stride = size >> 1;
+      if (__popc(size - 1) & 1) {
         for (int t = tid; t < (npow >> 1); t += kSelThreads) {
           const int lo = 2 * t - (t & (stride - 1));
           const int hi = lo + stride;
@@ -351,47 +393,74 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
           if ((x > y) == up) { big[lo] = y; big[hi] = x; }
         }
         __syncthreads();
+        stride >>= 1;
+      }
+      for (; stride >= 2; stride >>= 2) {
+        const int h = stride >> 1;
+        for (int g = tid; g < (npow >> 2); g += kSelThreads) {
+          const int i0 = ((g & ~(h - 1)) << 2) | (g & (h - 1));
+          unsigned long long a = big[i0], b = big[i0 + h], c = big[i0 + 2 * h], d = big[i0 + 3 * h];
+          const bool up = (i0 & size) == 0;
+          unsigned long long t;
+          if ((a > c) == up) { t = a; a = c; c = t; }
+          if ((b > d) == up) { t = b; b = d; d = t; }
+          if ((a > b) == up) { t = a; a = b; b = t; }
+          if ((c > d) == up) { t = c; c = d; d = t; }
+          big[i0] = a; big[i0 + h] = b; big[i0 + 2 * h] = c; big[i0 + 3 * h] = d;
+        }
+        __syncthreads();
       }
     }
-
+    NMS_TP(2);
     // =============== greedy rounds of 512 candidates in sorted order ===============
     for (int off = 0; off < SK; off += kK) {
       const int K = min(kK, SK - off);
+      NMS_TC(10, 1);
       // ---- (c) class-offset boxes ----
       const bool have = tid < K;
       const unsigned long long mykey = have ? big[off + tid] : ~0ull;
       float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f); float myarea = 0.f;
-      if (have) { load_offset_box(p, img, mykey, &mybox, &myarea); s.box[tid] = mybox; s.area[tid] = myarea; }
+      float mysa = 0.f;
+      if (have) {
+        load_offset_box(p, img, mykey, &mybox, &myarea);
+        mysa = screen_area(myarea, p.iou_c);
+        s.box[tid] = mybox; s.area[tid] = myarea; s.sarea[tid] = mysa;
+      }
+      NMS_TP(3);
       // ---- (d) suppress against boxes kept in earlier rounds ----
       bool dead = !have;
       const int kept0 = s.kept;
       if (have) {
-        // four kept boxes per trip, tested independently (kbox / karea have max_det entries; kept0 <= max_det)
+        // four kept boxes per trip, screened independently (the arrays are padded: no bounds test)
         for (int i = 0; i < kept0 && !dead; i += 4) {
-          int c[4];
+          const float4 sl4 = *reinterpret_cast<const float4*>(&ksarea[i]);
+          const float sl[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
+          float inter[4], S[4];
+          bool maybe = false;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int ii = min(i + u, kept0 - 1);
-            c[u] = iou_class(kbox[ii], karea[ii], mybox, myarea, thr_lo, thr_hi);
+            inter[u] = box_inter(kbox[i + u], mybox);
+            S[u] = __fadd_rn(sl[u], mysa);
+            maybe |= !(inter[u] < S[u]);
           }
-          if ((c[0] | c[1] | c[2] | c[3]) & 1) dead = true;
-          else if ((c[0] | c[1] | c[2] | c[3]) & 2) {
+          if (maybe) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int ii = min(i + u, kept0 - 1);
-              if (c[u] == 2 && iou_suppresses(kbox[ii], karea[ii], mybox, myarea, p.iou_f, p.iou_inclusive)) dead = true;
-            }
+            for (int u = 0; u < 4; ++u)
+              if (!(inter[u] < S[u]) && i + u < kept0 &&
+                  iou_decide(kbox[i + u], karea[i + u], mybox, myarea, inter[u], S[u], p.iou_f, p.iou_inclusive)) dead = true;
           }
         }
       }
       const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
-      if (lane == 0) s.remv[warp] = dead_bits;
+      if (lane == 0) { s.remv[warp] = dead_bits; s.undw[warp] = ~dead_bits; s.keptw[warp] = 0u; }
+      for (int i = tid; i < kWords * (kK + 1); i += kSelThreads) s.mask[i] = 0u;
       __syncthreads();
-      // ---- (e) upper-triangular suppression bitmask, mask[w][i] covers columns j in [32w, 32w+32) of row i (j > i only).
-      //      Only candidates that survived (d) matter, as rows and as columns.  The triangle is cut into (row, 32-column word)
-      //      units, word-major: word w has rows 0 .. 32w+31, i.e. 16w(w+1) units precede it.  Units are dealt round-robin, so
-      //      every thread gets the same amount of IoU work (one row per thread left thread 0 with 511 tests and thread 511
-      //      with none: half of the block idled at the barrier).
+      NMS_TP(4);
+      // ---- (e) suppression pairs (i suppresses j, i < j) among the candidates that survived (d), stored by COLUMN:
+      //      bit (i & 31) of mask[i >> 5][j] says "row i suppresses j" (what the fixed point of (f) needs).  The triangle is
+      //      cut into (row, 32-column word) units, word-major: word w has rows 0 .. 32w+31, i.e. 16w(w+1) units precede
+      //      it.  Units are dealt round-robin, so every thread gets the same amount of IoU work (one row per thread left
+      //      thread 0 with 511 tests and thread 511 with none: half of the block idled at the barrier).
       {
         const int nwords = (K + 31) / 32;
         const int units = 16 * nwords * (nwords + 1);
@@ -406,60 +475,88 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
             if (K - j0 < 32) todo &= (1u << (K - j0)) - 1u;
             if (i >= j0) todo &= ~((2u << (i - j0)) - 1u);               // only j > i
             if (todo) {
-              const float4 bi = s.box[i]; const float ai = s.area[i];
-              // four columns per trip, tested independently and masked afterwards (s.box has kK entries: j < kK always)
-              for (int jj0 = 0; jj0 < 32; jj0 += 4) {
-                const unsigned m4 = (todo >> jj0) & 0xfu;
-                if (!m4) continue;
-                int c[4];
+              const float4 bi = s.box[i]; const float sli = s.sarea[i];
+              // screen the 32 columns four at a time (s.box / s.sarea have kK entries: j < kK always), then look again at
+              // the few pairs that were not ruled out
+              unsigned int maybe = 0u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) c[u] = iou_class(bi, ai, s.box[j0 + jj0 + u], s.area[j0 + jj0 + u], thr_lo, thr_hi);
+              for (int g = 0; g < 8; ++g) {
+                if (!((todo >> (4 * g)) & 0xfu)) continue;
+                const float4 sl4 = *reinterpret_cast<const float4*>(&s.sarea[j0 + 4 * g]);
+                const float sl[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  if (!((m4 >> u) & 1u)) continue;
-                  if (c[u] == 1 || (c[u] == 2 && iou_suppresses(bi, ai, s.box[j0 + jj0 + u], s.area[j0 + jj0 + u], p.iou_f, p.iou_inclusive)))
-                    bits |= 1u << (jj0 + u);
+                  const float inter = box_inter(bi, s.box[j0 + 4 * g + u]);
+                  if (!(inter < __fadd_rn(sli, sl[u]))) maybe |= 1u << (4 * g + u);
                 }
+              }
+              maybe &= todo;
+              while (maybe) {
+                const int jj = __ffs(maybe) - 1;
+                maybe &= maybe - 1u;
+                const float4 bj = s.box[j0 + jj];
+                if (iou_decide(bi, s.area[i], bj, s.area[j0 + jj], box_inter(bi, bj), __fadd_rn(sli, s.sarea[j0 + jj]),
+                               p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
               }
             }
           }
-          if (i < kK) s.mask[w * (kK + 1) + i] = bits;
-        }
-      }
-      __syncthreads();
-      // ---- (f) greedy scan by warp 0: lane w holds remv word w; only the index of each kept candidate is recorded here,
-      //      the box data is copied by all threads afterwards ----
-      if (warp == 0) {
-        unsigned int remv = lane < kWords ? s.remv[lane] : 0xffffffffu;
-        int kept = kept0;
-        const int nwords = (K + 31) / 32;
-        for (int wi = 0; wi < nwords && kept < p.max_det; ++wi) {
-          unsigned int cur = __shfl_sync(0xffffffffu, remv, wi);
-          const int nb = min(32, K - wi * 32);
-          const unsigned int range = (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-          unsigned int avail = ~cur & range;
-          while (avail && kept < p.max_det) {
-            const int bit = __ffs(avail) - 1;
-            const int i = wi * 32 + bit;
-            if (lane == 0) s.kidx[kept - kept0] = static_cast<unsigned short>(i);
-            kept++;
-            if (lane < kWords && lane >= wi) remv |= s.mask[lane * (kK + 1) + i];   // words below the diagonal are never written
-            cur = __shfl_sync(0xffffffffu, remv, wi);
-            avail = ~cur & range & ~((2u << bit) - 1u);    // only bits above the one just taken
+          while (bits) {                                                  // sparse: a few suppressed columns per row
+            const int jj = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            atomicOr(&s.mask[(i >> 5) * (kK + 1) + j0 + jj], 1u << (i & 31));
           }
         }
-        if (lane == 0) s.kept = kept;
       }
       __syncthreads();
+      NMS_TP(5);
+      // ---- (f) greedy choice as a fixed point, all 512 candidates at once (the bit-serial scan by one warp was 20 % of the
+      //      kernel).  Candidate j is KEPT once no lower candidate that could still be kept suppresses it, and DEAD once a
+      //      kept one does; every step decides at least the lowest undecided candidate, a step costs two barriers, and
+      //      the number of steps is the depth of the longest suppression chain (a handful).  Warp w owns word w of the
+      //      undecided / kept sets, so no atomics.  The max_det cut is applied to the ranks afterwards: the choice of a
+      //      candidate never depends on later ones ----
+      {
+        unsigned int colr[kWords];                           // rows that suppress me, by word (only words <= mine are non-zero)
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) colr[w] = (w <= warp) ? s.mask[w * (kK + 1) + tid] : 0u;
+        bool und = !dead;
+        bool iskept = false;
+        while (true) {
+          bool nk = false, nd = false;
+          if (und) {
+            unsigned int anyK = 0u, anyU = 0u;
+#pragma unroll
+            for (int w = 0; w < kWords; ++w)
+              if (colr[w]) { anyK |= colr[w] & s.keptw[w]; anyU |= colr[w] & s.undw[w]; }
+            nd = anyK != 0u;
+            nk = !nd && anyU == 0u;
+          }
+          __syncthreads();                                   // every thread has read the sets
+          const unsigned int bk = __ballot_sync(0xffffffffu, nk), bd = __ballot_sync(0xffffffffu, nd);
+          if (lane == 0 && (bk | bd)) { s.keptw[warp] |= bk; s.undw[warp] &= ~(bk | bd); }
+          iskept |= nk;
+          und = und && !nk && !nd;
+          if (!__syncthreads_or(und)) break;
+        }
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) { const int c = __popc(s.keptw[w]); total += c; if (w < warp) before += c; }
+        const int rank = before + __popc(s.keptw[warp] & ((1u << lane) - 1u));
+        if (iskept && kept0 + rank < p.max_det) s.kidx[rank] = static_cast<unsigned short>(tid);
+        if (tid == 0) s.kept = min(p.max_det, kept0 + total);
+      }
+      __syncthreads();
+      NMS_TP(6);
       {
         const int newly = s.kept - kept0;
         if (tid < newly) {
           const int i = s.kidx[tid];
-          kbox[kept0 + tid] = s.box[i]; karea[kept0 + tid] = s.area[i];
+          kbox[kept0 + tid] = s.box[i]; karea[kept0 + tid] = s.area[i]; ksarea[kept0 + tid] = s.sarea[i];
           kkey[kept0 + tid] = big[off + i]; krank[kept0 + tid] = processed + off + i;
         }
       }
       __syncthreads();
+      NMS_TP(7);
       if (s.kept >= p.max_det) { done = true; break; }
     }
     processed += SK;
@@ -542,6 +639,7 @@ int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
   p.conf = d->conf_thres;
   const float f = static_cast<float>(d->iou_thres);
   p.iou_f = f; p.iou_inclusive = static_cast<double>(f) > d->iou_thres ? 1 : 0;
+  p.iou_c = f > 1e-6f ? static_cast<float>(static_cast<double>(kScreenLo) * static_cast<double>(f) / (1.0 + static_cast<double>(f))) : nanf("");
   p.max_det = d->max_det; p.max_nms = d->max_nms; p.max_wh = d->max_wh;
   p.agnostic = d->agnostic; p.multi_label = ml; p.in_place = d->xyxy_in_place;
   p.has_class_filter = 0;
@@ -576,7 +674,7 @@ int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
   nms_filter_kernel<<<fgrid, kFilterThreads, 0, stream>>>(p);
   int rc = launch_status("nms_filter_kernel");
   if (rc) return rc;
-  const size_t smem = kSelSharedBytes + ((static_cast<size_t>(d->max_det) * (16 + 8 + 4 + 4) + 15) & ~size_t(15)) + static_cast<size_t>(kBig) * 8;
+  const size_t smem = kSelSharedBytes + kept_bytes(d->max_det) + static_cast<size_t>(kBig) * 8;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     DY_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -594,3 +692,15 @@ extern "C" size_t dy_nms_workspace_bytes(int B, int nc, int A, int multi_label) 
 }
 
 extern "C" int dy_nms(const dy_nms_desc* d, void* stream) { return dy::nms_launch(d, static_cast<cudaStream_t>(stream)); }
+
+#ifdef DY_CONV_DEBUG
+// debug builds only: copy out (and clear) the select kernel's per-image phase clocks; 16 counters per image
+extern "C" int dy_nms_trace_read(unsigned long long* host, int images) {
+  if (images > 1024) images = 1024;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, dy::g_nms_trace, sizeof(unsigned long long) * 16 * images);
+  static unsigned long long zeros[1024 * 16];
+  cudaMemcpyToSymbol(dy::g_nms_trace, zeros, sizeof(zeros));
+  return 0;
+}
+#endif

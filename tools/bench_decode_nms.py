@@ -1,0 +1,84 @@
+"""BASELINE config 4: isolated Detect decode + NMS, B=256, nc=10, 34 000 / 136 000 anchors, conf .001, iou .7, max_det 300.
+
+    python tools/bench_decode_nms.py [--batch 256] [--imgsz 640 1280] [--iters 20]
+
+Raw maps follow SURVEY 8(d) config 4 (box logits 1.5 N(0,1), class logits N(mu, 1.5^2); mu = -11 sparse, -10 val-like,
+-7.5 dense) but are drawn on the GPU (torch.randn, seed 1234): the CPU recipe would need 10 GB of host randoms.
+Times are CUDA events over `iters` back-to-back launches after 3 warm-ups; every input is far larger than L2.
+GB/s are ALGORITHMIC bytes (decode: no*sizeof(raw) + (4+nc)*4 per anchor; NMS: (4+nc)*4 per anchor + 7.2 KB per image)
+over the measured time, against MEASURED_PEAKS.json's copy bandwidth.  One JSON line per case."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from drone_yolo_b200 import kernels as K  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--imgsz", type=int, nargs="+", default=[640, 1280])
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--nc", type=int, default=10)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+bw = float(peaks.get("hbm_gbs", 6553.6))
+B, nc = a.batch, a.nc
+no = 64 + nc
+ld = (no + 15) // 16 * 16
+
+
+def timed(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / a.iters
+
+
+for imgsz in a.imgsz:
+    shapes = [(imgsz // s, imgsz // s) for s in (4, 8, 16, 32)]
+    A = sum(h * w for h, w in shapes)
+    strides = [4.0, 8.0, 16.0, 32.0]
+    for mu, regime in ((-11.0, "sparse"), (-10.0, "val-like"), (-7.5, "dense")):
+        g = torch.Generator(device=dev).manual_seed(1234)
+        bufs = []
+        for h, w in shapes:                              # NHWC fp32, pixel stride `ld` (the engine's raw-map layout)
+            t = torch.zeros((B, h, w, ld), device=dev, dtype=torch.float32)
+            t[..., :64] = 1.5 * torch.randn((B, h, w, 64), device=dev, generator=g)
+            t[..., 64:no] = mu + 1.5 * torch.randn((B, h, w, nc), device=dev, generator=g)
+            bufs.append(t)
+        y = torch.empty((B, 4 + nc, A), device=dev, dtype=torch.float32)
+        for layout in (("nhwc_f32", "nhwc_bf16", "nchw_f32") if regime == "val-like" else ("nhwc_f32",)):
+            if layout == "nhwc_f32":
+                lv = [t.permute(0, 3, 1, 2)[:, :no] for t in bufs]; esz = 4
+            elif layout == "nhwc_bf16":
+                lv = [t.to(torch.bfloat16).permute(0, 3, 1, 2)[:, :no] for t in bufs]; esz = 2
+            else:
+                lv = [t.permute(0, 3, 1, 2)[:, :no].contiguous() for t in bufs]; esz = 4
+            ms = timed(lambda: K.detect_decode(lv, strides, nc, out=y))
+            gb = B * A * (no * esz + (4 + nc) * 4) / 1e9
+            print(json.dumps({"case": "decode", "layout": layout, "imgsz": imgsz, "B": B, "A": A, "regime": regime,
+                              "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "frac_of_measured_hbm": round(gb / ms * 1e3 / bw, 3)}))
+            del lv
+        K.detect_decode([t.permute(0, 3, 1, 2)[:, :no] for t in bufs], strides, nc, out=y)
+        for ml in (False, True):
+            nb = K.NmsBuffers(B, nc, A, 300, ml, dev)
+            ms = timed(lambda: K.nms(y, 0.001, 0.7, max_det=300, multi_label=ml, bufs=nb))
+            gb = (B * A * (4 + nc) * 4 + B * (300 * 24 + 4)) / 1e9
+            cand = float((y[:, 4:].amax(1) > 0.001).sum()) / B
+            print(json.dumps({"case": "nms", "multi_label": ml, "imgsz": imgsz, "B": B, "A": A, "regime": regime,
+                              "candidates_per_image": round(cand), "kept_per_image": round(float(nb.counts.float().mean()), 1),
+                              "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "frac_of_measured_hbm": round(gb / ms * 1e3 / bw, 3)}))
+            del nb
+        del bufs, y
+        torch.cuda.empty_cache()
