@@ -178,9 +178,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we touch
-  // memory it produced.  Let our own dependents start their prologue right away.
-  grid_dep_wait();
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  Only the roles that touch
+  // memory the previous kernels produced (or still read: the arena reuses buffers) wait for them - the A producer before
+  // its first activation load, the epilogue warps before their first residual load / output store.  The weight and
+  // bias loads (constants) and the MMA issuer do not wait, so a CTA that lands on a free SM during the previous
+  // kernel's tail already has its resident weights on the way.  Our own dependents may start their prologue now.
   grid_dep_launch();
 
   if (warp == 0) {
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int TW = opaque(p.TW), TH = opaque(p.TH), TB = opaque(p.TB);
       TileIter it(p, blockIdx.x, gridDim.x);
       bool ok = mbar_try_wait_a(empty0, 1u);
+      grid_dep_wait();
       [[maybe_unused]] const int kit = opaque(kiters), kps_r = opaque(kps), kcmax = opaque(kblocks * kBlockK);
       [[maybe_unused]] const uint32_t e_minus_f = empty0 - full0;
       [[maybe_unused]] uint32_t fullb = full0, dst = stage0;
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       if constexpr (FUSE2) { for (int i = threadIdx.x - 128; i < 64; i += 256) s_bias[512 + i] = i < p.N2 ? __ldg(p.bias2 + i) : 0.f; }
       named_bar_sync(3, 256);
     }
+    grid_dep_wait();
     [[maybe_unused]] int trt = 0;
     [[maybe_unused]] const int trole = (lane == 0 && q == 0) ? 3 + g : 99;
 #ifdef DY_CONV_DEBUG

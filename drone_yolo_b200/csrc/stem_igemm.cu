@@ -43,7 +43,14 @@ struct StemParams {
   int tiles_w, tiles_h, B, total_tiles;
   int patch_bytes, np;     // bytes per patch, patch stages
   int dbg;                 // DY_STEM_DBG knock-outs (bring-up): 1 no TMA store, 2 no MMA, 4 no TMA load, 8 no TMEM load
+  unsigned long long* trace;   // debug builds only (DY_CONV_TRACE): clock64 stamps of CTA 0, [role 8][iteration 96][event 8]
 };
+
+#ifdef DY_CONV_DEBUG
+#define ST_TR(role, it, ev) do { if (p.trace && blockIdx.x == 0 && (it) < 96) p.trace[((role) * 96 + (it)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define ST_TR(role, it, ev) do { } while (0)
+#endif
 
 template <bool U8>
 __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __grid_constant__ StemParams p) {
@@ -112,7 +119,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
       const int np = p.np, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
       bool ok = mbar_try_wait_a(pe0 + s * 8, 1u);
       for (int i = pi; i < my_tiles; i += 2) {
+        ST_TR(pi, i >> 1, 0);
         if (!ok) mbar_wait_a(pe0 + s * 8, ph ^ 1u);
+        ST_TR(pi, i >> 1, 1);
         mbar_arrive_expect_tx_a(pf0 + s * 8, tx);
         int ns = s + 2; uint32_t nph = ph;
         if (ns >= np) { ns -= np; nph ^= 1u; }
@@ -121,6 +130,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
             ::"r"(patch0 + s * patch_stride), "l"(reinterpret_cast<uint64_t>(&p.tmIn)), "r"(pf0 + s * 8),
               "r"(2 * tw * kStemTW - (U8 ? kStemLeftU8 : kStemLeftF32)), "r"(2 * th * kStemTH - 1), "r"(3 * tb) : "memory");
+        ST_TR(pi, i >> 1, 2);
         for (int k = 0; k < 2; ++k)                             // advance two tiles
           if (++tw == tiles_w) { tw = 0; if (++th == tiles_h) { th = 0; ++tb; } }
         s = ns; ph = nph;
@@ -137,8 +147,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
       const uint32_t b_lo = lo_const | ((b_tile & 0x3ffffu) >> 4);
       for (int i = mi; i < my_tiles; i += 2) {
         const int s = i % kStemNA, a = i % kStemNAcc;
+        ST_TR(2 + mi, i >> 1, 0);
         mbar_wait(&tempty[a], ((i / kStemNAcc) & 1) ^ 1);
+        ST_TR(2 + mi, i >> 1, 1);
         mbar_wait(&afull[s], (i / kStemNA) & 1);
+        ST_TR(2 + mi, i >> 1, 2);
         tc_fence_after();
         const uint32_t a_lo = lo_const | (((a_tile0 + s * kStemABytes) & 0x3ffffu) >> 4);
         const uint32_t d = tmem_base + static_cast<uint32_t>(a * N);
@@ -148,6 +161,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
         }
         umma_commit(&aempty[s]);
         umma_commit(&tfull[a]);
+        ST_TR(2 + mi, i >> 1, 3);
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -158,7 +172,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
     const uint32_t row_off = static_cast<uint32_t>(m) * 64, sw = static_cast<uint32_t>((m >> 1) & 3);
     for (int i = bg; i < my_tiles; i += 2) {
       const int ps = i % p.np, as = i % kStemNA;
+      if (m == 0) ST_TR(4 + bg, i >> 1, 0);
       mbar_wait(&pfull[ps], (i / p.np) & 1);
+      if (m == 0) ST_TR(4 + bg, i >> 1, 1);
       // first needed column of this pixel = left margin - 1 + 2*px; the uint8 path reads aligned 16-bit pairs from one byte earlier
       const uint32_t pb = patch0 + ps * patch_stride + static_cast<uint32_t>(2 * py) * PROW +
                           (U8 ? static_cast<uint32_t>(kStemLeftU8 - 2 + 2 * px) : static_cast<uint32_t>(kStemLeftF32 - 1 + 2 * px) * 4u);
@@ -185,7 +201,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
             hv[k + 0] = __float_as_uint(f0); hv[k + 1] = __float_as_uint(f1); hv[k + 2] = __float_as_uint(f2);
           }
         }
+      if (m == 0) ST_TR(4 + bg, i >> 1, 2);
       mbar_wait(&aempty[as], ((i / kStemNA) & 1) ^ 1);
+      if (m == 0) ST_TR(4 + bg, i >> 1, 3);
       const uint32_t arow = a_tile0 + as * kStemABytes + row_off;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -206,6 +224,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
       fence_proxy_async_smem();
       mbar_arrive(&afull[as]);
       mbar_arrive(&pempty[ps]);
+      if (m == 0) ST_TR(4 + bg, i >> 1, 4);
     }
   } else if (warp >= 12) {
     // ===================== epilogue groups =====================
@@ -216,51 +235,73 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
     const float hscale = 0.5f * p.in_scale;               // SiLU: h = 0.5*(acc*scale + bias)
     const int nchunks = (N + 31) >> 5;
     uint32_t sctr = 0;
-    for (int i = g; i < my_tiles; i += 2) {
-      const int t = tile_begin + i;
-      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, tb = t / (p.tiles_w * p.tiles_h);
-      const int a = i % kStemNAcc;
-      mbar_wait(&tfull[a], (i / kStemNAcc) & 1);
+    // Flattened (tile, 32-column chunk) items.  The TMEM load of the NEXT item is issued as soon as this item's values are
+    // packed, so its latency (~600 cycles with eight epilogue warps contending) hides behind the fence / barrier / store
+    // hand-off instead of heading every item; tile coordinates advance by carry (three divisions per tile were ~150 cycles).
+    int tw, th, tb;
+    { const int t0 = tile_begin + g; tw = t0 % p.tiles_w; th = (t0 / p.tiles_w) % p.tiles_h; tb = t0 / (p.tiles_w * p.tiles_h); }
+    const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t r[32];
+    int i = g, c = 0;
+    bool valid = i < my_tiles;
+    if (valid) {
+      mbar_wait(&tfull[i % kStemNAcc], (i / kStemNAcc) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * N);
-      for (int c = 0; c < nchunks; ++c) {
-        const uint32_t st = stg + (sctr & 1) * 8192u;
-        float4 hb[8];
+      if (!(p.dbg & 8)) tmem_ld_32x32b_x32(tlane + static_cast<uint32_t>((i % kStemNAcc) * N), r);
+    }
+    while (valid) {
+      const int a = i % kStemNAcc;
+      const uint32_t st = stg + (sctr & 1) * 8192u;
+      float4 hb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) hb[e] = *reinterpret_cast<const float4*>(s_bias + 32 * c + 4 * e);
-        uint32_t r[32];
-        if (!(p.dbg & 8)) {
-          tmem_ld_32x32b_x32(taddr + 32 * c, r);
-          tmem_ld_wait();
-        }
-        if (c == nchunks - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[a]);
-        }
-        const uint32_t rowp = st + row * 64;
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 b4 = hb[2 * gi + (e >> 2)];
-            const float bb = (e & 3) == 0 ? b4.x : (e & 3) == 1 ? b4.y : (e & 3) == 2 ? b4.z : b4.w;
-            const float h = fmaf(__uint_as_float(r[8 * gi + e]), hscale, bb);
-            v[e] = fmaf(h, tanh_fast(h), h);
-          }
-          sts128(rowp + ((static_cast<uint32_t>(gi) ^ static_cast<uint32_t>((row >> 1) & 3)) << 4),
-                 make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
-        }
-        fence_proxy_async_smem();
-        if (leader) bulk_wait_group_read<0>();
-        named_bar_sync(1 + g, 128);
-        if (leader && !(p.dbg & 1)) {
-          tma_store_4d_a(&p.tmO, st, 32 * c, tw * kStemTW, th * kStemTH, tb);
-          bulk_commit_group();
-        }
-        ++sctr;
+      for (int e = 0; e < 8; ++e) hb[e] = *reinterpret_cast<const float4*>(s_bias + 32 * c + 4 * e);
+      if (leader) ST_TR(6 + g, i >> 1, 1);
+      tmem_ld_wait();
+      if (leader) ST_TR(6 + g, i >> 1, 2);
+      if (c == nchunks - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
       }
+      const uint32_t rowp = st + row * 64;
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 b4 = hb[2 * gi + (e >> 2)];
+          const float bb = (e & 3) == 0 ? b4.x : (e & 3) == 1 ? b4.y : (e & 3) == 2 ? b4.z : b4.w;
+          const float h = fmaf(__uint_as_float(r[8 * gi + e]), hscale, bb);
+          v[e] = fmaf(h, tanh_fast(h), h);
+        }
+        sts128(rowp + ((static_cast<uint32_t>(gi) ^ static_cast<uint32_t>((row >> 1) & 3)) << 4),
+               make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+      }
+      if (leader) ST_TR(6 + g, i >> 1, 3);
+      int ni = i, nc = c + 1;
+      if (nc == nchunks) { nc = 0; ni = i + 2; }
+      const bool nvalid = ni < my_tiles;
+      if (nvalid) {
+        const int na = ni % kStemNAcc;
+        if (nc == 0) { mbar_wait(&tfull[na], (ni / kStemNAcc) & 1); tc_fence_after(); }
+        if (!(p.dbg & 8)) tmem_ld_32x32b_x32(tlane + static_cast<uint32_t>(na * N + 32 * nc), r);
+      }
+      if (leader) ST_TR(6 + g, i >> 1, 4);
+      fence_proxy_async_smem();
+      if (leader) bulk_wait_group_read<0>();
+      named_bar_sync(1 + g, 128);
+      if (leader) ST_TR(6 + g, i >> 1, 5);
+      if (leader && !(p.dbg & 1)) {
+        tma_store_4d_a(&p.tmO, st, 32 * c, tw * kStemTW, th * kStemTH, tb);
+        bulk_commit_group();
+      }
+      if (leader) ST_TR(6 + g, i >> 1, 6);
+      ++sctr;
+      if (ni != i)
+        for (int k = 0; k < 2; ++k)
+          if (++tw == tiles_w) { tw = 0; if (++th == tiles_h) { th = 0; ++tb; } }
+      i = ni; c = nc; valid = nvalid;
     }
     if (leader) bulk_wait_group<0>();
   }
@@ -287,6 +328,7 @@ int stem_tc_launch(const void* in, int in_dtype, int B, int H, int W, const floa
   const int pw = u8 ? kStemPWu8 : kStemPWf32, esz = u8 ? 1 : 4;
   p.patch_bytes = 3 * kStemPH * pw * esz;
   { const char* e = getenv("DY_STEM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("DY_CONV_TRACE"); p.trace = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   {
     const uint64_t dims[3] = {uint64_t(W), uint64_t(H), uint64_t(B) * 3};
     const uint64_t strides[2] = {uint64_t(W) * esz, uint64_t(W) * H * esz};
