@@ -137,48 +137,59 @@ __device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
   return r;
 }
 
+// One CTA = one image x NV*8 consecutive channels, the whole HxW map in shared memory.  NV = 4 (64 contiguous bytes per
+// pixel: full 32-byte sectors on both the strided reads and the three strided writes) when the map fits, else 2 or 1.
+template <int NV>
 __global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(__nv_bfloat16* buf, int H, int W, int C, int ld) {
   extern __shared__ __align__(16) uint8_t pool_smem[];
-  const int hw = H * W;
+  const int hw = H * W, n = hw * NV;
   uint4* X = reinterpret_cast<uint4*>(pool_smem);
-  uint4* T = X + hw;
-  const int groups = C / 8;
+  uint4* T = X + n;
+  const int groups = C / (8 * NV);
   const int b = blockIdx.x / groups, g = blockIdx.x % groups;
-  __nv_bfloat16* base = buf + static_cast<size_t>(b) * hw * ld + g * 8;
-  for (int i = threadIdx.x; i < hw; i += kPoolThreads) X[i] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i) * ld);
+  __nv_bfloat16* base = buf + static_cast<size_t>(b) * hw * ld + g * 8 * NV;
+  for (int i = threadIdx.x; i < n; i += kPoolThreads)
+    X[i] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i / NV) * ld + (i % NV) * 8);
   __syncthreads();
   for (int rep = 1; rep <= 3; ++rep) {
-    for (int i = threadIdx.x; i < hw; i += kPoolThreads) {
-      const int y = i / W, x = i - y * W;
+    for (int i = threadIdx.x; i < n; i += kPoolThreads) {
+      const int px = i / NV, x = px % W;
       uint4 m = X[i];
-      for (int dx = -2; dx <= 2; ++dx) { const int xx = x + dx; if (dx != 0 && xx >= 0 && xx < W) m = max_bf16x8(m, X[y * W + xx]); }
+      for (int dx = -2; dx <= 2; ++dx) { const int xx = x + dx; if (dx != 0 && xx >= 0 && xx < W) m = max_bf16x8(m, X[i + dx * NV]); }
       T[i] = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < hw; i += kPoolThreads) {
-      const int y = i / W, x = i - y * W;
+    for (int i = threadIdx.x; i < n; i += kPoolThreads) {
+      const int px = i / NV, y = px / W;
       uint4 m = T[i];
-      for (int dy = -2; dy <= 2; ++dy) { const int yy = y + dy; if (dy != 0 && yy >= 0 && yy < H) m = max_bf16x8(m, T[yy * W + x]); }
-      *reinterpret_cast<uint4*>(base + static_cast<size_t>(i) * ld + rep * C) = m;
+      for (int dy = -2; dy <= 2; ++dy) { const int yy = y + dy; if (dy != 0 && yy >= 0 && yy < H) m = max_bf16x8(m, T[i + dy * W * NV]); }
+      *reinterpret_cast<uint4*>(base + static_cast<size_t>(px) * ld + rep * C + (i % NV) * 8) = m;
       X[i] = m;     // only this thread reads/writes X[i] in this phase; T is the cross-thread source
     }
     __syncthreads();
   }
 }
 
+template <int NV>
+static int sppf_pool_launch_nv(void* buf, int B, int H, int W, int C, int ld, size_t smem, cudaStream_t stream) {
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    DY_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  sppf_pool_kernel<NV><<<B * (C / (8 * NV)), kPoolThreads, smem, stream>>>(static_cast<__nv_bfloat16*>(buf), H, W, C, ld);
+  return launch_status("sppf_pool_kernel");
+}
+
 int sppf_pool_launch(void* buf, int B, int H, int W, int C, int ld, cudaStream_t stream) {
   DY_CHECK_ARG(buf && B > 0 && H > 0 && W > 0 && C > 0, "sppf_pool: bad argument");
   DY_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ld >= 4 * C && (reinterpret_cast<uintptr_t>(buf) & 15) == 0,
                "sppf_pool: C, ld must be multiples of 8 with ld >= 4*C");
-  const size_t smem = static_cast<size_t>(H) * W * 16 * 2;
-  DY_CHECK_ARG(smem <= 220 * 1024, "sppf_pool: %dx%d map does not fit shared memory", H, W);
-  static size_t smem_set = 48 * 1024;
-  if (smem > smem_set) {
-    DY_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
-  }
-  sppf_pool_kernel<<<B * (C / 8), kPoolThreads, smem, stream>>>(static_cast<__nv_bfloat16*>(buf), H, W, C, ld);
-  return launch_status("sppf_pool_kernel");
+  const size_t smem1 = static_cast<size_t>(H) * W * 16 * 2;
+  DY_CHECK_ARG(smem1 <= 220 * 1024, "sppf_pool: %dx%d map does not fit shared memory", H, W);
+  if (C % 32 == 0 && smem1 * 4 <= 100 * 1024) return sppf_pool_launch_nv<4>(buf, B, H, W, C, ld, smem1 * 4, stream);
+  if (C % 16 == 0 && smem1 * 2 <= 100 * 1024) return sppf_pool_launch_nv<2>(buf, B, H, W, C, ld, smem1 * 2, stream);
+  return sppf_pool_launch_nv<1>(buf, B, H, W, C, ld, smem1, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -926,7 +926,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   if (mode == 2 && d->Cin <= 32 && !env_int("DY_NO_K32", 0)) mode = 5;          // stride 2 with 64-byte rows: half the MMA / smem / L2 work
   if (k == 3 && s == 1 && !env_int("DY_NO_HALO", 0)) {
     const double eff = double(Wo) * Ho / (double(ceil_div(Wo, kHaloTW)) * kHaloTW * ceil_div(Ho, kHaloTH) * kHaloTH);
-    if (eff >= 0.8) {
+    if (eff >= 0.8 || fuse2) {                    // a caller asking for the fused tail accepts ragged tiles (small maps are launch-bound)
       if (d->Cin <= 32 && !env_int("DY_NO_K32", 0)) mode = 4;
       else if (cin_pad == kBlockK) mode = 3;
     }
@@ -942,7 +942,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (cout_pad / bn > 4 || cout_pad / bn > sms) mode = 1;
     else { p->BN = bn; p->n_tiles = cout_pad / bn; p->n_split = p->n_tiles; }
   }
-  if (fuse2 && mode != 3) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs a map the 8x16 halo tiles cover (>= 80 %%)");
+  if (fuse2 && mode != 3) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs the 64-channel halo mode");
   const bool halo = (mode == 3 || mode == 4);
   const int rowb = (mode == 4 || mode == 5) ? 64 : 128;
   const int a_blk = kBlockM * rowb;

@@ -215,7 +215,8 @@ class LayerPlan:
             # Each branch ends Conv(c,c,3) -> nn.Conv2d(c,n,1) (head.py:41-47).  Where the 64-channel halo kernel applies, the
             # 1x1 runs inside the 3x3's epilogue (dy_conv_desc.weight2) and the intermediate tensor is never written; with
             # fuse_decode the same epilogue also decodes the logits (dy_conv_desc.tail_decode) and the raw map is skipped too.
-            halo_ok = self.fuse_tail and H * W / (-(-W // 8) * 8 * -(-H // 16) * 16) >= 0.8
+            # ragged 8x16 tiles waste MMA rows, but a level this small is launch-bound: three launches less win
+            halo_ok = self.fuse_tail and (H * W / (-(-W // 8) * 8 * -(-H // 16) * 16) >= 0.8 or self.mb * H * W <= 65536)
             branches = ((m.cv2[i][1], 0, c2, (wbx, bbx), 4 * m.reg_max, 0), (m.cv3[i][1], c2, c3, (wcl, bcl), ncp, 4 * m.reg_max))
             fusable = [halo_ok and cw == 64 and cout1 <= 64 for (_, _, cw, _, cout1, _) in branches]
             dec = self.fuse_decode and all(fusable) and m.nc <= 32 and W % 4 == 0 and a_off % 4 == 0

@@ -12,3 +12,4 @@ echo "launch list exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_igemm -s 57 -c 3 \
     -f -o gpurun_out/${tag}_conv_full python tools/profile_step.py --micro-batch 64 > gpurun_out/${tag}_ncu2.log 2>&1
 echo "full capture exit $?"
+timeout 600 python tools/bench_decode_nms.py > gpurun_out/${tag}_config4.jsonl 2>gpurun_out/${tag}_config4.err; echo "config 4 exit $?"
