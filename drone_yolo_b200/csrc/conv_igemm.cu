@@ -35,7 +35,7 @@ static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 384;          // 4 control warps + 2 x 4 epilogue warps
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxBias = 1024;
-static constexpr int kMaxDynSmem = 227 * 1024 - 6 * 1024;   // static part: barriers + 4 KB of bias
+static constexpr int kMaxDynSmem = 227 * 1024 - 1024;       // static part: barriers (< 0.5 KB); the bias table lives in the dynamic part
 static constexpr int kHaloTW = 8, kHaloTH = 16;             // halo modes: 8x16 output pixels per tile
 static constexpr int kHaloRows = kHaloTH + 2;
 static constexpr int kMaxAcc = 8;             // accumulator stages in TMEM: min(8, 512 / BN), BN columns apart
@@ -117,8 +117,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __shared__ __align__(8) uint64_t d2_bar[2];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float s_bias[kMaxBias];
-
   constexpr int NTAPS = MODE == 0 ? 1 : 9;
   constexpr bool HALO = (MODE == 3 || MODE == 4);
   constexpr bool S2 = (MODE == 2 || MODE == 5);         // stride 2: four parity views
@@ -147,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   // `opaque` pins loop invariants in registers: without it the compiler re-derives the shared-window addresses
   // and re-reads kernel parameters inside the single-thread loops, whose cost is pure latency.
   const uint32_t smem_base = opaque(smem_u32(smem));
+  float* const s_bias = reinterpret_cast<float*>(smem + p.bias_off);   // [Cout padded + 64] (+ the tail's bias at 512 when FUSE2)
   const uint32_t stage0 = opaque(smem_base + bres_bytes);  // first pipeline stage (1024-aligned: bres_bytes is a multiple of 1024)
   const uint32_t full0 = opaque(smem_u32(&full_bar[0])), empty0 = opaque(smem_u32(&empty_bar[0]));
   const uint32_t tfull0 = opaque(smem_u32(&tfull_bar[0])), tempty0 = opaque(smem_u32(&tempty_bar[0]));
@@ -1099,10 +1098,17 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int cw = p->use_tma_store;
   // K-heavy generic tiles: one staging tile per group (the epilogue has slack), the room goes to fatter pipeline stages
   p->nbuf = ((!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) || (mode == 3 && p->BN > 64)) ? 1 : 2;
-  const int staging = 2 * p->nbuf * 128 * cw * out_esz;                     // 2 groups x nbuf tiles
-  const int budget = kMaxDynSmem - 1024 - staging;
   const int b_tile = p->BN * rowb;
   const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
+  const int bias_bytes = (fuse2 ? 576 : round_up(p->n_tiles * p->BN + 64, 4)) * 4;
+  int staging = 2 * p->nbuf * 128 * cw * out_esz;                           // 2 groups x nbuf tiles
+  if (p->nbuf == 1 && halo && !env_int("DY_CONV_NBUF1", 0)) {
+    // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
+    // previous chunk's store (~1700 cycles per 32-column chunk); take the second one whenever two halo stages still fit
+    const int halo_stage = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
+    if (kMaxDynSmem - 1024 - 2 * staging - bias_bytes - b_all >= 2 * halo_stage) { p->nbuf = 2; staging *= 2; }
+  }
+  const int budget = kMaxDynSmem - 1024 - staging - bias_bytes;
   if (halo) {
     p->b_resident = 1;
     p->stage_bytes = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
@@ -1141,7 +1147,8 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;
   }
-  l->smem_bytes = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + staging + 1024;
+  p->bias_off = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + staging;
+  l->smem_bytes = p->bias_off + bias_bytes + 1024;
   const int total = p->m_tiles * p->n_tiles;
   if (p->n_split > 1) {
     const int per = sms / p->n_split < p->m_tiles ? sms / p->n_split : p->m_tiles;
@@ -1162,7 +1169,7 @@ template <int MODE, int CW, bool F32, bool FUSE2 = false>
 static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   static int max_smem_set = 0;
   if (max_smem_set < l->smem_bytes) {
-    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part is < 6 KB
+    // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part (barriers) is < 1 KB
     DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32, FUSE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     max_smem_set = kMaxDynSmem;
   }
