@@ -93,6 +93,27 @@ def nms_padded(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnost
                  multi_label=ml, classes=classes, in_place=in_place, bufs=bufs)
 
 
+def _append_labels(pred: torch.Tensor, labels, nc: int) -> torch.Tensor:
+    """(B, 4+nc, A) -> (B, 4+nc, A + L): label rows (cls, cx, cy, w, h) of image i as columns A.. of image i."""
+    B, ch, A = pred.shape
+    if len(labels) != B:
+        raise DroneYoloError(f"non_max_suppression: {len(labels)} label lists for a batch of {B}")
+    L = max(len(lb) for lb in labels)
+    aug = torch.zeros((B, ch, A + (L + 3) // 4 * 4), device=pred.device, dtype=torch.float32)
+    aug[:, :, :A] = pred
+    for i, lb in enumerate(labels):
+        if not len(lb):
+            continue
+        lb = torch.as_tensor(lb, dtype=torch.float32, device=pred.device).reshape(-1, 5)
+        cls = lb[:, 0].long()
+        if int(cls.min()) < 0 or int(cls.max()) >= nc:
+            raise DroneYoloError("non_max_suppression: label class outside [0, nc)")
+        cols = A + torch.arange(lb.shape[0], device=pred.device)
+        aug[i, :4, cols] = lb[:, 1:5].t()
+        aug[i, 4 + cls, cols] = 1.0
+    return aug
+
+
 def non_max_suppression(
     prediction,
     conf_thres=0.25,
@@ -122,18 +143,28 @@ def non_max_suppression(
         prediction = prediction[0]
     if rotated or end2end or prediction.shape[-1] == 6:
         raise DroneYoloError("non_max_suppression: rotated / end2end inputs are outside the Drone-YOLO detect path")
-    if labels and any(len(lb) for lb in labels):
-        raise DroneYoloError("non_max_suppression: a-priori `labels` (autolabelling) are not implemented")
     if not prediction.is_cuda:
         raise DroneYoloError("non_max_suppression runs on CUDA tensors only; there is no CPU fallback")
 
     work = prediction
     if work.dtype != torch.float32 or not work.is_contiguous():
         work = prediction.float().contiguous()
-    out, counts, _ = nms_padded(work, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nc, max_nms,
-                                max_wh, in_place=in_place)
-    if in_place and work is not prediction:   # keep the reference's side effect on the caller's tensor (:259-260)
-        prediction[:, :4] = work[:, :4].to(prediction.dtype)
+    if labels and any(len(lb) for lb in labels):
+        # A-priori labels (autolabelling, the validator's `save_hybrid` path; reference ops.py:272-277): every label row
+        # (cls, cx, cy, w, h) joins its image's candidates behind the anchors with score 1.0 for its class.  Here they
+        # become extra anchor columns of a widened copy (unused columns score 0 and never pass `conf`), so candidate
+        # order, tie order and kept indices are the reference's.
+        work = _append_labels(work, labels, nc or work.shape[1] - 4)
+        out, counts, _ = nms_padded(work, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nc, max_nms,
+                                    max_wh, in_place=False)
+        if in_place:                              # the caller's tensor still turns xywh -> xyxy (:259-260)
+            xy, wh = prediction[:, :2].float(), prediction[:, 2:4].float() / 2
+            prediction[:, :2], prediction[:, 2:4] = (xy - wh).to(prediction.dtype), (xy + wh).to(prediction.dtype)
+    else:
+        out, counts, _ = nms_padded(work, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nc, max_nms,
+                                    max_wh, in_place=in_place)
+        if in_place and work is not prediction:   # keep the reference's side effect on the caller's tensor (:259-260)
+            prediction[:, :4] = work[:, :4].to(prediction.dtype)
     n = counts.tolist()                       # the one host sync: per-image row counts
     out = out.clone()
     return [out[i, : n[i]] for i in range(out.shape[0])]

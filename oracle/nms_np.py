@@ -55,7 +55,7 @@ def nms_greedy(boxes, scores, iou_threshold):
 
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-                        max_det=300, nc=0, max_nms=30000, max_wh=7680, nms_fn=None, return_kept=False):
+                        max_det=300, nc=0, max_nms=30000, max_wh=7680, nms_fn=None, return_kept=False, labels=()):
     """prediction: (B, 4+nc, A) float32.  Returns a list of (k_i, 6) float32 arrays [x1,y1,x2,y2,conf,cls]
     (and, with return_kept, the list of kept index arrays into the candidate list `x`, as torchvision returns)."""
     assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
@@ -72,6 +72,12 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     output, kept_all = [], []
     for xi in range(bs):                                      # :266
         x = pred[xi][xc[xi]]                                  # :269
+        if labels and len(labels[xi]):                        # a-priori labels (autolabelling), :272-277
+            lb = np.asarray(labels[xi], dtype=f32).reshape(-1, 5)
+            v = np.zeros((lb.shape[0], mi), f32)
+            v[:, :4] = xywh2xyxy(lb[:, 1:5])
+            v[np.arange(lb.shape[0]), lb[:, 0].astype(np.int64) + 4] = 1.0
+            x = np.concatenate((x, v), 0)
         if not x.shape[0]:
             output.append(np.zeros((0, 6), f32)); kept_all.append(np.zeros((0,), np.int64)); continue
         box, cls = x[:, :4], x[:, 4:mi]

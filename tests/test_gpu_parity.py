@@ -367,6 +367,24 @@ def test_ops_non_max_suppression_signature_and_side_effects(dev, golden_dir):
     assert all(torch.equal(a, b) for a, b in zip(res, res2))
 
 
+@pytest.mark.parametrize("regime", ["sparse", "vallike", "dense"])
+def test_ops_nms_apriori_labels_vs_reference_golden(dev, golden_dir, regime):
+    """`labels=` (autolabelling; the validator's save_hybrid path, ops.py:272-277): rows bit-exact vs the real reference,
+    and the in_place side effect on the caller's tensor is kept."""
+    from drone_yolo_b200.utils import ops
+
+    labels = [[[3.0, 40.0, 52.0, 30.0, 22.0], [7.0, 90.5, 30.25, 12.0, 44.0], [3.0, 41.0, 51.0, 28.0, 24.0]], []]
+    g = np.load(golden_dir / f"decode_nms_{regime}.npz")
+    pred = torch.from_numpy(g["y"]).to(dev)
+    before = pred.clone()
+    lbs = [torch.tensor(lb, dtype=torch.float32, device=dev).reshape(-1, 5) for lb in labels]
+    res = ops.non_max_suppression(pred, 0.001, 0.7, multi_label=True, labels=lbs, max_det=300)
+    for b, r in enumerate(res):
+        assert np.array_equal(r.cpu().numpy().view(np.uint32), g[f"labels_out{b}"].view(np.uint32)), (regime, b)
+    exp = nms_np.xywh2xyxy(before[:, :4].permute(0, 2, 1).cpu().numpy()).transpose(0, 2, 1)
+    assert np.array_equal(pred[:, :4].cpu().numpy(), exp) and torch.equal(pred[:, 4:], before[:, 4:])
+
+
 # ---------------------------------------------------------------------------------------------- whole model
 def build(g, dev):
     from drone_yolo_b200.nn.tasks import DetectionModel

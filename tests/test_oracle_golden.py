@@ -50,6 +50,21 @@ def test_nms_oracle_bit_exact_vs_reference(golden_dir, regime, case):
         assert np.array_equal(kept[b], ref_kept), (regime, case, b)                                   # and kept indices
 
 
+LABELS = [[[3.0, 40.0, 52.0, 30.0, 22.0], [7.0, 90.5, 30.25, 12.0, 44.0], [3.0, 41.0, 51.0, 28.0, 24.0]], []]   # tools/make_golden.py
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+def test_nms_oracle_apriori_labels_vs_reference(golden_dir, regime):
+    """Validator form (multi_label) with a-priori labels appended to the candidates (ops.py:272-277)."""
+    g = np.load(golden_dir / f"decode_nms_{regime}.npz")
+    out, kept = nms_np.non_max_suppression(g["y"], 0.001, 0.7, multi_label=True, max_det=300, labels=LABELS, return_kept=True)
+    for b in range(int(g["B"])):
+        assert np.array_equal(out[b].view(np.uint32), g[f"labels_out{b}"].view(np.uint32)), (regime, b)
+        assert np.array_equal(kept[b], g[f"labels_kept{b}"]), (regime, b)
+    if regime != "dense":                       # the two score-1.0 labels of image 0 that survive NMS lead its rows
+        assert out[0][0, 4] == 1.0 and out[0][0, 5] in (3.0, 7.0)
+
+
 def test_nms_restatement_equals_installed_torchvision(golden_dir):
     import torchvision
 

@@ -44,6 +44,9 @@ def convstack_fixture(tasks, yaml_name, imgsz, B, tag):
     print(tag, "y", tuple(y.shape), "digest", digest_unfused[:12])
 
 
+LABELS = [[[3.0, 40.0, 52.0, 30.0, 22.0], [7.0, 90.5, 30.25, 12.0, 44.0], [3.0, 41.0, 51.0, 28.0, 24.0]], []]
+
+
 def decode_nms_fixture(tasks, mu, tag, imgsz=128, B=2, nc=10):
     import torchvision
     from ultralytics.utils import ops
@@ -63,6 +66,8 @@ def decode_nms_fixture(tasks, mu, tag, imgsz=128, B=2, nc=10):
         "classes": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, classes=[1, 3, 7]),
         "maxnms": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=200),
         "predict": dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+        # validator with a-priori labels (autolabelling, ops.py:272-277): rows (cls, cx, cy, w, h); image 1 has none
+        "labels": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, multi_label=True, labels=LABELS),
     }
     real_nms = torchvision.ops.nms
     for name, kw in cases.items():
@@ -75,6 +80,9 @@ def decode_nms_fixture(tasks, mu, tag, imgsz=128, B=2, nc=10):
 
         torchvision.ops.nms = recording_nms
         try:
+            kw = dict(kw)
+            if "labels" in kw:
+                kw["labels"] = [torch.tensor(lb, dtype=torch.float32).reshape(-1, 5) for lb in kw["labels"]]
             res = ops.non_max_suppression(y.clone(), max_time_img=1e9, **kw)
             # H1: assert the reference's UNSTABLE pre-sort did not matter for this vector
             if kw.get("max_nms"):
