@@ -10,7 +10,7 @@
 //     64-byte row of the A tile in the 64B-swizzled K-major layout (uint8 0..255 is exact in bf16; 1/255 is applied in fp32
 //     in the epilogue); fence.proxy.async; arrive on the stage's barrier;
 //   * warps 1 and 3 (one thread each, alternate tiles): two K16 tcgen05.mma per tile into a TMEM accumulator stage;
-//   * warps 12..15 / 16..19: two epilogue groups on alternate tiles: tcgen05.ld -> scale, bias, SiLU -> bf16 -> 64B-swizzled
+//   * warps 12..15 / 16..19 / 20..23: three epilogue groups on every third tile: tcgen05.ld -> scale, bias, SiLU -> bf16 -> 64B-swizzled
 //     staging tile -> TMA store into the NHWC output slice.
 // Persistent, one CTA per SM.
 #include "dy_common.cuh"
@@ -28,10 +28,11 @@ static constexpr int kStemPH = 2 * kStemTH + 1;                 // input rows pe
 // 16 bytes (16 uint8 / 4 fp32 columns) left of the tile instead of 1 column: 16 + 64 + 1 (4 + 64 + 1) columns, padded to 16 B.
 static constexpr int kStemPWu8 = 96, kStemPWf32 = 72;
 static constexpr int kStemLeftU8 = 16, kStemLeftF32 = 4;
-static constexpr int kStemMaxNP = 16, kStemNA = 4, kStemNAcc = 4;   // patch stages (HBM latency x bandwidth: >= 12 tiles in flight per SM), A stages, accumulator stages
-static constexpr int kStemThreads = 640;                        // 4 control warps + 2 x 4 builder warps + 2 x 4 epilogue warps
+static constexpr int kStemEG = 3;                                // epilogue groups (the in-kernel timeline shows the epilogue chain, ~2100 cycles per tile and group, as the limiter)
+static constexpr int kStemMaxNP = 16, kStemNA = 4, kStemNAcc = 6;   // patch stages (HBM latency x bandwidth: >= 12 tiles in flight per SM), A stages, accumulator stages (even: two MMA issuers; multiple of kStemEG)
+static constexpr int kStemThreads = 128 + 256 + 128 * kStemEG;  // 4 control warps + 2 x 4 builder warps + kStemEG x 4 epilogue warps
 static constexpr int kStemABytes = 128 * 64;                    // A tile: 128 rows x 32 bf16
-static constexpr int kStemMaxN = 112;                           // kStemNAcc * N + 16 columns of ragged read must fit 512
+static constexpr int kStemMaxN = 80;                            // kStemNAcc * N + 16 columns of ragged read must fit 512
 
 struct StemParams {
   CUtensorMap tmIn;        // input planes [B*3][H][W]
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t b_tile = smem_base;                                            // weights: N rows x 64 B (<= 8 KB)
   const uint32_t a_tile0 = smem_base + 8192;                                    // kStemNA x 8 KB
-  const uint32_t stg0 = a_tile0 + kStemNA * kStemABytes;                        // 2 groups x 2 x 8 KB
-  const uint32_t patch0 = stg0 + 4 * 8192;                                      // np x patch_bytes (1 KB multiples)
+  const uint32_t stg0 = a_tile0 + kStemNA * kStemABytes;                        // kStemEG groups x 2 x 8 KB
+  const uint32_t patch0 = stg0 + 2 * kStemEG * 8192;                                      // np x patch_bytes (1 KB multiples)
   const uint32_t patch_stride = static_cast<uint32_t>((p.patch_bytes + 1023) & ~1023);
 
   if (warp == 0 && elect_one()) { prefetch_tmap(&p.tmIn); prefetch_tmap(&p.tmO); }
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
     // packed, so its latency (~600 cycles with eight epilogue warps contending) hides behind the fence / barrier / store
     // hand-off instead of heading every item; tile coordinates advance by carry (three divisions per tile were ~150 cycles).
     int tw, th, tb;
-    { const int t0 = tile_begin + g; tw = t0 % p.tiles_w; th = (t0 / p.tiles_w) % p.tiles_h; tb = t0 / (p.tiles_w * p.tiles_h); }
+    { const int t0 = min(tile_begin + g, p.total_tiles - 1); tw = t0 % p.tiles_w; th = (t0 / p.tiles_w) % p.tiles_h; tb = t0 / (p.tiles_w * p.tiles_h); }
     const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t r[32];
@@ -253,12 +254,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
     while (valid) {
       const int a = i % kStemNAcc;
       const uint32_t st = stg + (sctr & 1) * 8192u;
-      float4 hb[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) hb[e] = *reinterpret_cast<const float4*>(s_bias + 32 * c + 4 * e);
-      if (leader) ST_TR(6 + g, i >> 1, 1);
+      if (leader) ST_TR(6 + g, i / kStemEG, 1);
       tmem_ld_wait();
-      if (leader) ST_TR(6 + g, i >> 1, 2);
+      if (leader) ST_TR(6 + g, i / kStemEG, 2);
       if (c == nchunks - 1) {
         tc_fence_before();
         __syncwarp();
@@ -269,8 +267,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
       for (int gi = 0; gi < 4; ++gi) {
         float v[8];
 #pragma unroll
+        const float4 hb0 = *reinterpret_cast<const float4*>(s_bias + 32 * c + 8 * gi);   // 80-register budget: bias per 8 columns
+        const float4 hb1 = *reinterpret_cast<const float4*>(s_bias + 32 * c + 8 * gi + 4);
+#pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float4 b4 = hb[2 * gi + (e >> 2)];
+          const float4 b4 = (e >> 2) ? hb1 : hb0;
           const float bb = (e & 3) == 0 ? b4.x : (e & 3) == 1 ? b4.y : (e & 3) == 2 ? b4.z : b4.w;
           const float h = fmaf(__uint_as_float(r[8 * gi + e]), hscale, bb);
           v[e] = fmaf(h, tanh_fast(h), h);
@@ -278,28 +279,28 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_igemm_kernel(const __gri
         sts128(rowp + ((static_cast<uint32_t>(gi) ^ static_cast<uint32_t>((row >> 1) & 3)) << 4),
                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
       }
-      if (leader) ST_TR(6 + g, i >> 1, 3);
+      if (leader) ST_TR(6 + g, i / kStemEG, 3);
       int ni = i, nc = c + 1;
-      if (nc == nchunks) { nc = 0; ni = i + 2; }
+      if (nc == nchunks) { nc = 0; ni = i + kStemEG; }
       const bool nvalid = ni < my_tiles;
       if (nvalid) {
         const int na = ni % kStemNAcc;
         if (nc == 0) { mbar_wait(&tfull[na], (ni / kStemNAcc) & 1); tc_fence_after(); }
         if (!(p.dbg & 8)) tmem_ld_32x32b_x32(tlane + static_cast<uint32_t>(na * N + 32 * nc), r);
       }
-      if (leader) ST_TR(6 + g, i >> 1, 4);
+      if (leader) ST_TR(6 + g, i / kStemEG, 4);
       fence_proxy_async_smem();
       if (leader) bulk_wait_group_read<0>();
       named_bar_sync(1 + g, 128);
-      if (leader) ST_TR(6 + g, i >> 1, 5);
+      if (leader) ST_TR(6 + g, i / kStemEG, 5);
       if (leader && !(p.dbg & 1)) {
         tma_store_4d_a(&p.tmO, st, 32 * c, tw * kStemTW, th * kStemTH, tb);
         bulk_commit_group();
       }
-      if (leader) ST_TR(6 + g, i >> 1, 6);
+      if (leader) ST_TR(6 + g, i / kStemEG, 6);
       ++sctr;
       if (ni != i)
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < kStemEG; ++k)
           if (++tw == tiles_w) { tw = 0; if (++th == tiles_h) { th = 0; ++tb; } }
       i = ni; c = nc; valid = nvalid;
     }
@@ -345,7 +346,7 @@ int stem_tc_launch(const void* in, int in_dtype, int B, int H, int W, const floa
     if (rc) return rc;
   }
   p.np = u8 ? 16 : 12;                                       // even: the two patch producers own alternate slots
-  const int smem = 1024 + 8192 + kStemNA * kStemABytes + 4 * 8192 + p.np * ((p.patch_bytes + 1023) & ~1023);
+  const int smem = 1024 + 8192 + kStemNA * kStemABytes + 2 * kStemEG * 8192 + p.np * ((p.patch_bytes + 1023) & ~1023);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   static bool attr_set[2] = {false, false};
   if (!attr_set[u8]) {
