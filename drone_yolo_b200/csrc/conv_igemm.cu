@@ -32,7 +32,7 @@ static constexpr int kBlockM = 128;           // UMMA M
 static constexpr int kBlockK = 64;            // bf16 per 128B swizzle row
 static constexpr int kABytes = kBlockM * 128; // one 64-channel A block
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 384;          // 4 control warps + 2 x 4 epilogue warps
+static constexpr int kThreads = 384;          // 4 control warps + 2 x 4 epilogue warps (EG = 3: 512, three epilogue groups)
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxBias = 1024;
 static constexpr int kMaxDynSmem = 227 * 1024 - 1024;       // static part: barriers (< 0.5 KB); the bias table lives in the dynamic part
@@ -105,15 +105,17 @@ __device__ __forceinline__ float act1(uint32_t acc, float hb, bool silu) {
 // FUSE2 (MODE 3, CW 32 only): the Detect branch tail.  The SiLU output tile never leaves the SM: its two 32-channel bf16
 // staging chunks ARE the K-major A operand of a second GEMM (x W2[N2,64]^T, issued by the epilogue group's leader into a
 // private TMEM region); the fp32 result + bias2 goes out through the same staging memory and a TMA store.
-template <int MODE, int CW, bool F32, bool FUSE2 = false>
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+// EG = epilogue groups (4 warps each, tiles dealt round-robin).  The 32-channel layers are bound by the per-tile epilogue
+// chain (~3000 cycles per group and tile against a ~950-cycle mainloop): they run with three groups.
+template <int MODE, int CW, bool F32, bool FUSE2 = false, int EG = 2>
+__global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
-  __shared__ __align__(8) uint64_t res_bar[4];          // [group][staging buffer]: residual tile landed
+  __shared__ __align__(8) uint64_t res_bar[2 * EG];     // [group][staging buffer]: residual tile landed
   __shared__ __align__(8) uint64_t d2_bar[2];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_s;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const uint32_t producers = bres ? 1u : 2u;             // A thread (+ B thread) arrive on every full barrier
     for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
-    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2 * EG; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1);
     mbar_init(&bres_bar, 1);
     fence_mbar_init();
@@ -432,13 +434,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const float bscale = silu ? 0.5f : 1.0f;        // SiLU path keeps 0.5*bias: h = 0.5*acc + 0.5*b in one FFMA
     {
       const int nb = p.n_tiles * p.BN;              // == Cout padded to 16: the packed bias has that many entries
-      for (int i = threadIdx.x - 128; i < nb; i += 256) s_bias[i] = bscale * __ldg(p.bias + i);
-      if constexpr (FUSE2) { for (int i = threadIdx.x - 128; i < 64; i += 256) s_bias[512 + i] = i < p.N2 ? __ldg(p.bias2 + i) : 0.f; }
-      named_bar_sync(3, 256);
+      for (int i = threadIdx.x - 128; i < nb; i += 128 * EG) s_bias[i] = bscale * __ldg(p.bias + i);
+      if constexpr (FUSE2) { for (int i = threadIdx.x - 128; i < 64; i += 128 * EG) s_bias[512 + i] = i < p.N2 ? __ldg(p.bias2 + i) : 0.f; }
+      named_bar_sync(1 + EG, 128 * EG);          // ids 1 .. EG are the groups' own barriers
     }
     grid_dep_wait();
     [[maybe_unused]] int trt = 0;
-    [[maybe_unused]] const int trole = (lane == 0 && q == 0) ? 3 + g : 99;
+    [[maybe_unused]] const int trole = (lane == 0 && q == 0 && g < 2) ? 3 + g : 99;
 #ifdef DY_CONV_DEBUG
 #define DY_TRE(ev) do { if (trole < 99) DY_TR(trole, trt, ev); } while (0)
 #else
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const bool has_res = CW > 0 && !F32 && p.has_res_tma != 0;
     const uint32_t res_tx = static_cast<uint32_t>(rows_valid) * CW * 2u;
     TileIter it(p, blockIdx.x, gridDim.x);
-    if (g) it.next(n_iter, p.tiles_w, p.tiles_h);
+    for (int k = 0; k < g; ++k) it.next(n_iter, p.tiles_w, p.tiles_h);
     int acc = g % nacc; uint32_t acc_phase = static_cast<uint32_t>(g / nacc) & 1u;
     uint32_t sctr = 0;
     const int nbuf = p.nbuf;
@@ -461,9 +463,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     while (it.valid()) {
       const int w0 = it.tw_i * p.TW, h0 = it.th_i * p.TH, b0 = it.tb_i * p.TB;
       const int n0 = it.n_tile * p.BN;
-      TileIter nx = it;                              // this group's next tile (two ahead)
-      nx.next(n_iter, p.tiles_w, p.tiles_h);
-      nx.next(n_iter, p.tiles_w, p.tiles_h);
+      TileIter nx = it;                              // this group's next tile (EG ahead)
+#pragma unroll
+      for (int k = 0; k < EG; ++k) nx.next(n_iter, p.tiles_w, p.tiles_h);
 
       DY_TRE(0);
       mbar_wait_a(tfull0 + acc * 8, acc_phase);
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
       }
       DY_TRE(7); ++trt;
-      acc += 2;
+      acc += EG;
       if (acc >= nacc) { acc -= nacc; acc_phase ^= 1u; }
       it = nx;
     }
@@ -1101,7 +1103,8 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int b_tile = p->BN * rowb;
   const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
   const int bias_bytes = (fuse2 ? 576 : round_up(p->n_tiles * p->BN + 64, 4)) * 4;
-  int staging = 2 * p->nbuf * 128 * cw * out_esz;                           // 2 groups x nbuf tiles
+  p->eg = (mode == 4 && cw == 32 && !f32 && p->BN <= 64 && !env_int("DY_CONV_EG2", 0)) ? 3 : 2;   // epilogue groups
+  int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
   if (p->nbuf == 1 && halo && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
     // previous chunk's store (~1700 cycles per 32-column chunk); take the second one whenever two halo stages still fit
@@ -1144,6 +1147,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (nacc > kMaxAcc) nacc = kMaxAcc;
     if (fuse2 && nacc > (kTmemCols - 128) / p->BN) nacc = (kTmemCols - 128) / p->BN;   // the last 128 columns hold the two tail accumulators
     if (halo) nacc &= ~1;
+    if (p->eg == 3) nacc = nacc >= 6 ? 6 : 0;                               // even (two MMA issuers) and a multiple of the three groups
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;
   }
@@ -1165,18 +1169,18 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   return DY_OK;
 }
 
-template <int MODE, int CW, bool F32, bool FUSE2 = false>
+template <int MODE, int CW, bool F32, bool FUSE2 = false, int EG = 2>
 static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
   static int max_smem_set = 0;
   if (max_smem_set < l->smem_bytes) {
     // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part (barriers) is < 1 KB
-    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32, FUSE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32, FUSE2, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     max_smem_set = kMaxDynSmem;
   }
   static const bool use_pdl = (getenv("DY_NO_PDL") == nullptr);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(l->grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(128 + 128 * EG);
   cfg.dynamicSmemBytes = l->smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1184,7 +1188,7 @@ static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<MODE, CW, F32, FUSE2>, *p));
+  DY_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<MODE, CW, F32, FUSE2, EG>, *p));
   return launch_status("conv_igemm_kernel");
 }
 
@@ -1202,7 +1206,7 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 1: return conv_launch_m<1>(p, l, stream);
     case 2: return conv_launch_m<2>(p, l, stream);
     case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream) : conv_launch_m<3>(p, l, stream);
-    case 4: return conv_launch_m<4>(p, l, stream);
+    case 4: return p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream);
     default: return conv_launch_m<5>(p, l, stream);
   }
 }

@@ -31,6 +31,7 @@ struct ConvParams {
   int tail_decode, y_nc, y_A; float y_stride; float* y;   // fused Detect decode of the tail's logits (tmO2 then maps the prediction tensor)
   int nbuf;                            // staging tiles per epilogue group (2, or 1 when shared memory is short)
   int bias_off;                        // byte offset of the bias table behind the staging tiles
+  int eg;                              // epilogue groups: 2, or 3 for the 32-channel halo layers
   int dbg;
   unsigned long long* trace;           // debug builds only (DY_CONV_TRACE)
   void* out; int out_ld; int out_f32;
