@@ -1103,7 +1103,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int b_tile = p->BN * rowb;
   const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
   const int bias_bytes = (fuse2 ? 576 : round_up(p->n_tiles * p->BN + 64, 4)) * 4;
-  p->eg = (mode == 4 && cw == 32 && !f32 && p->BN <= 64 && !env_int("DY_CONV_EG2", 0)) ? 3 : 2;   // epilogue groups
+  p->eg = ((mode == 4 || (mode == 3 && !fuse2 && env_int("DY_CONV_EG3_M3", 1))) && cw == 32 && !f32 && p->BN <= 64 && !env_int("DY_CONV_EG2", 0)) ? 3 : 2;   // epilogue groups
   int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
   if (p->nbuf == 1 && halo && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
@@ -1205,7 +1205,8 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 0: return conv_launch_m<0>(p, l, stream);
     case 1: return conv_launch_m<1>(p, l, stream);
     case 2: return conv_launch_m<2>(p, l, stream);
-    case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream) : conv_launch_m<3>(p, l, stream);
+    case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream)
+                            : (p->eg == 3 ? conv_launch_t<3, 32, false, false, 3>(p, l, stream) : conv_launch_m<3>(p, l, stream));
     case 4: return p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream);
     default: return conv_launch_m<5>(p, l, stream);
   }
