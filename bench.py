@@ -214,21 +214,25 @@ def run_ours(a):
     # image sources (engine/predictor.py:127-135: uint8 -> .to(device) -> .float() -> /255 on the device).  H2D of batch
     # i+1 runs on a copy stream while batch i computes; each step ends with the D2H read of its padded detections.
     eng8 = Engine(model, a.batch, a.imgsz, dev, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou, max_det=a.max_det,
-                  cuda_graph=not a.no_graph, input_dtype=torch.uint8)
+                  cuda_graph=not a.no_graph, input_dtype=torch.uint8, input_slots=2)
     host8 = (host * 255.0).round().to(torch.uint8).pin_memory()
-    staging = [torch.empty_like(host8, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     slot_free = [torch.cuda.Event() for _ in range(2)]
+    d2h_done = [torch.cuda.Event() for _ in range(2)]
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    cnt_hosts = [cnt_host, torch.empty_like(cnt_host).pin_memory()]
     e2e_state = {"i": 0, "primed": False}
 
     def enqueue_h2d(i):
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(slot_free[i % 2])
-            staging[i % 2].copy_(host8, non_blocking=True)
+            copy_stream.wait_event(slot_free[i % 2])              # the step that last read this slot is done with it
+            eng8.image_slots[i % 2].copy_(host8, non_blocking=True)
             h2d_done[i % 2].record(copy_stream)
 
     def step_e2e():
+        # The engine reads its input slot in place (no device-side hand-over copy).  The host runs one step ahead of the
+        # device: it waits for the D2H of step i-1 while step i is already enqueued, so launch latency never idles the GPU.
         i = e2e_state["i"]
         cur = torch.cuda.current_stream(dev)
         if not e2e_state["primed"]:
@@ -238,14 +242,15 @@ def run_ours(a):
             e2e_state["primed"] = True
         enqueue_h2d(i + 1)                                         # next batch's H2D overlaps this batch's compute
         cur.wait_event(h2d_done[i % 2])
-        eng8.images.copy_(staging[i % 2], non_blocking=True)       # device-side hand-over into the graph's static input
+        out, counts = eng8.step(slot=i % 2)
         slot_free[i % 2].record(cur)
-        out, counts = eng8.step()
         oa, ca = gather.gather(out, counts)
         if rank == 0:                                             # D2H of the step's result
-            out_host.copy_(oa, non_blocking=True)
-            cnt_host.copy_(ca, non_blocking=True)
-        cur.synchronize()
+            out_hosts[i % 2].copy_(oa, non_blocking=True)
+            cnt_hosts[i % 2].copy_(ca, non_blocking=True)
+        d2h_done[i % 2].record(cur)
+        if i > 0:
+            d2h_done[(i - 1) % 2].synchronize()                   # step i-1's detections are on the host
         e2e_state["i"] = i + 1
 
     def timed(fn, steps):
@@ -335,7 +340,7 @@ def run_ours(a):
                          f"arena {eng.plan.arena_bytes / 1e6:.0f} MB per micro-batch"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host8.numel() * world,
                 "d2h_bytes_per_step": out_host.numel() * 4 + cnt_host.numel() * 4,
-                "input": "pinned uint8 NCHW batch (as the reference's predictor uploads image sources), H2D of batch i+1 overlapped with compute of batch i"},
+                "input": "pinned uint8 NCHW batch (as the reference's predictor uploads image sources) copied straight into one of the engine's two input slots; H2D of batch i+1 overlaps the compute of batch i, the host waits for step i-1's detections while step i runs"},
         "gpu_launches": eng.launches_per_step * a.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv stack plan: stem + 78 tcgen05 convs + pool/upsample + decode)",

@@ -33,7 +33,7 @@ class Engine:
     def __init__(self, model, batch: int, imgsz, device, micro_batch: int = 0, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
                  max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True,
-                 input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True):
+                 input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True, input_slots: int = 1):
         device = torch.device(device)
         if device.type != "cuda":
             raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
@@ -47,9 +47,14 @@ class Engine:
         with torch.cuda.device(device):
             if input_dtype not in (torch.float32, torch.uint8):
                 raise _C.DroneYoloError("engine input must be float32 in [0,1] or uint8 0..255")
-            self.images = torch.zeros((batch, 3, H, W), device=device, dtype=input_dtype)
+            # `input_slots` > 1: several resident input batches in one allocation, so that the upload of batch i+1 can land
+            # while batch i computes and `step(slot)` reads it in place (no device-side hand-over copy); one graph per slot
+            self.input_slots = max(1, int(input_slots))
+            self._all_images = torch.zeros((self.input_slots * batch, 3, H, W), device=device, dtype=input_dtype)
+            self.image_slots = [self._all_images[k * batch:(k + 1) * batch] for k in range(self.input_slots)]
+            self.images = self.image_slots[0]
             self.y = torch.empty((batch, 4 + self.nc, self.A), device=device, dtype=torch.float32)
-            self.plan = LayerPlan(model, self.mb, H, W, device, self.images, self.y, fuse_decode=fuse_decode)
+            self.plan = LayerPlan(model, self.mb, H, W, device, self._all_images, self.y, fuse_decode=fuse_decode)
             ml = bool(multi_label) and self.nc > 1
             self.nms_bufs = K.NmsBuffers(batch, self.nc, self.A, max_det, ml, device)
             self.nms_cfg = dict(conf=conf, iou=iou, max_det=max_det, classes=classes, agnostic=agnostic, multi_label=ml,
@@ -62,30 +67,34 @@ class Engine:
             _C.check(_C.lib().dy_program_add_nms(h, C.byref(d)), "dy_program_add_nms")
             self.launches_per_step = self.plan.launches * (batch // self.mb) + _C.lib().dy_program_num_launches(h)
             self.graph: Optional[torch.cuda.CUDAGraph] = None
+            self.graphs: list = []
             self.enqueue()                       # eager warm-up (sets kernel attributes, pages in code)
             torch.cuda.synchronize(device)
             if cuda_graph:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.enqueue()
-                self.graph = g
+                for k in range(self.input_slots):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self.enqueue(slot=k)
+                    self.graphs.append(g)
+                self.graph = self.graphs[0]
 
-    def enqueue(self, stream: Optional[int] = None, nms: bool = True):
-        """Enqueue the whole step on `stream` (default: torch's current stream)."""
+    def enqueue(self, stream: Optional[int] = None, nms: bool = True, slot: int = 0):
+        """Enqueue the whole step on `stream` (default: torch's current stream), reading input slot `slot`."""
         s = _C.stream_ptr(self.device) if stream is None else stream
         in_bytes = self.mb * 3 * self.H * self.W * self.images.element_size()
         out_bytes = self.mb * (4 + self.nc) * self.A * 4
+        slot_bytes = self.batch * 3 * self.H * self.W * self.images.element_size()
         for m in range(self.batch // self.mb):
-            self.plan.run(m * in_bytes, m * out_bytes, s)
+            self.plan.run(slot * slot_bytes + m * in_bytes, m * out_bytes, s)
         if nms:
             _C.check(_C.lib().dy_program_run(self._nms_prog, 0, 0, s), "dy_program_run(nms)")
 
-    def step(self):
-        """Run conv stack + decode + NMS on the resident `images`; results in y / nms_bufs (no host sync)."""
-        if self.graph is not None:
-            self.graph.replay()
+    def step(self, slot: int = 0):
+        """Run conv stack + decode + NMS on the resident batch of input slot `slot`; results in y / nms_bufs (no host sync)."""
+        if self.graphs:
+            self.graphs[slot].replay()
         else:
-            self.enqueue()
+            self.enqueue(slot=slot)
         return self.nms_bufs.out, self.nms_bufs.counts
 
     def __call__(self, images: Optional[torch.Tensor] = None):

@@ -455,6 +455,17 @@ def test_engine_vs_cpu_oracle(dev, scale, imgsz, B, mb):
     np.testing.assert_allclose(fy[:, 4:], y_ref[:, 4:], rtol=2e-2, atol=1e-4)
     f_ref, f_kept = nms_np.non_max_suppression(fy, return_kept=True, conf_thres=0.001, iou_thres=0.7, max_det=300)
     assert_nms_equal(fo.cpu().numpy(), fc.cpu().numpy(), fused.nms_bufs.kept.cpu().numpy(), f_ref, f_kept)
+    # two resident input slots (uint8 upload form): a step reads its slot in place, slots do not disturb each other
+    x8 = (x * 255).round().to(torch.uint8).to(dev)
+    two = Engine(gm, B, imgsz, dev, conf=0.001, iou=0.7, input_dtype=torch.uint8, input_slots=2)
+    two.image_slots[0].copy_(x8)
+    two.image_slots[1].copy_(x8.flip(0))
+    o0 = [t.clone() for t in two.step(slot=0)]
+    y0 = two.y.clone()
+    two.step(slot=1)
+    assert torch.equal(two.y, y0.flip(0))
+    o0b = two.step(slot=0)
+    assert torch.equal(o0b[0], o0[0]) and torch.equal(o0b[1], o0[1])
 
 
 def test_predict_api_matches_engine(dev):
