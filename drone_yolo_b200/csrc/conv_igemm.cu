@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
 
       if constexpr (FUSE2) {
         // ---------------- fused Detect tail: SiLU tile (2 x 32 channels, bf16, 64B swizzle) -> second GEMM -> fp32 out ----------------
-        static_assert(!FUSE2 || (MODE == 3 && CW == 32 && !F32), "fused tail: 64-channel halo mode with 32-wide chunks");
+        static_assert(!FUSE2 || ((MODE == 3 || MODE == 5) && CW == 32 && !F32), "fused tail: 64 output channels, 32-wide chunks");
         const uint32_t d2b = smem_u32(&d2_bar[g]);
         const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(kTmemCols - 128 + 64 * g);       // this group's private columns
         if (leader) bulk_wait_group_read<0>();       // the previous tile's output stores have read the staging memory
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
         mbar_wait_a(d2b, sctr & 1u);                 // one tail GEMM per tile of this group
         tc_fence_after();
         const uint32_t t2addr = d2_tmem + (static_cast<uint32_t>(q * 32) << 16);
-        if (p.tail_decode) {
+        if (p.tail_decode == 1 || p.tail_decode == 2) {
           // ---- fused Detect decode (head.py:100-131): the logits never leave the SM.  Each thread owns one anchor (its
           //      accumulator row) and writes its values straight into the channel-planar prediction tensor (B, 4+nc, A):
           //      a warp covers 4 tile rows x 8 columns = four full 32-byte sectors per plane and store instruction ----
@@ -582,6 +582,37 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
             }
           }
           tc_fence_before();                         // D2 fully read before the next tile's tail GEMM overwrites it
+        } else if (p.tail_decode == 3) {
+          // ---- a hidden 1x1 Conv + SiLU as the tail (C2f.cv1 behind the stride-2 conv that feeds it, block.py:227-249):
+          //      SiLU(D2 + bias2) -> bf16 -> the two staging tiles (the tail GEMM has consumed them) -> two TMA stores ----
+          const int nout = (p.N2 + 31) >> 5;
+          for (int oc = 0; oc < nout; ++oc) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t2addr + oc * 32, r);
+            const float* b2 = s_bias + 512 + oc * 32;
+            float4 hb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hb[i] = *reinterpret_cast<const float4*>(b2 + 4 * i);
+            tmem_ld_wait();
+            const uint32_t rowp = stg + oc * STG_BYTES + row * 64;
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              const float4 h0 = hb[2 * gi], h1 = hb[2 * gi + 1];
+              uint4 o;
+              o.x = pack_bf16(act1(r[8 * gi + 0], 0.5f * h0.x, true), act1(r[8 * gi + 1], 0.5f * h0.y, true));
+              o.y = pack_bf16(act1(r[8 * gi + 2], 0.5f * h0.z, true), act1(r[8 * gi + 3], 0.5f * h0.w, true));
+              o.z = pack_bf16(act1(r[8 * gi + 4], 0.5f * h1.x, true), act1(r[8 * gi + 5], 0.5f * h1.y, true));
+              o.w = pack_bf16(act1(r[8 * gi + 6], 0.5f * h1.z, true), act1(r[8 * gi + 7], 0.5f * h1.w, true));
+              sts128(rowp + ((gi ^ ((row >> 1) & 3)) << 4), o);
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          named_bar_sync(barid, 128);
+          if (leader) {
+            for (int oc = 0; oc < nout; ++oc) tma_store_4d_a(&p.tmO2, stg + oc * STG_BYTES, oc * 32, w0, h0, b0);
+            bulk_commit_group();
+          }
         } else {
         const int nout = (p.N2 + 31) >> 5;           // 32-column fp32 output chunks (the last one may be ragged: TMA clips)
         for (int oc = 0; oc < nout; ++oc) {
@@ -892,20 +923,22 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const bool fuse2 = d->weight2 != nullptr;
   if (fuse2) {
     DY_CHECK_ARG(d->bias2 && d->Cout2 > 0, "conv: fused tail needs weight2, bias2 and Cout2");
-    DY_CHECK_ARG((d->tail_decode || ((d->out2_ld * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0)) &&
+    DY_CHECK_ARG(((d->tail_decode == 1 || d->tail_decode == 2) || ((d->out2_ld * (d->tail_decode == 3 ? 2 : 4)) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0)) &&
                  (reinterpret_cast<uintptr_t>(d->weight2) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->bias2) & 15) == 0,
                  "conv: fused tail tensors must be 16B aligned");
-    DY_CHECK_ARG(d->out2 || d->tail_decode, "conv: fused tail needs out2 (or tail_decode)");
-    if (d->tail_decode) {
-      DY_CHECK_ARG(d->tail_decode == 1 || d->tail_decode == 2, "conv: tail_decode must be 1 (box) or 2 (class)");
+    DY_CHECK_ARG(d->out2 || d->tail_decode == 1 || d->tail_decode == 2, "conv: fused tail needs out2 (or a decoding tail)");
+    DY_CHECK_ARG(d->tail_decode >= 0 && d->tail_decode <= 3, "conv: tail_decode must be 0 (raw fp32), 1 (box), 2 (class) or 3 (SiLU, bf16)");
+    if (d->tail_decode == 1 || d->tail_decode == 2) {
       DY_CHECK_ARG(d->y && d->y_A > 0 && d->y_nc > 0 && d->y_anchor_off >= 0, "conv: tail_decode needs y, y_A, y_nc, y_anchor_off");
       if (!(d->y_nc <= 32 && (d->tail_decode == 1 ? d->Cout2 == 64 : d->Cout2 >= d->y_nc && d->Cout2 <= 32) && d->W % 4 == 0 && d->y_A % 4 == 0 &&
             d->y_anchor_off % 4 == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0))
         return fail(DY_ERR_UNSUPPORTED, "conv: tail_decode needs nc <= 32, W, A, anchor offset multiples of 4 and a 16B-aligned y");
     }
-    if (!(d->ksize == 3 && d->stride == 1 && d->Cin > 32 && d->Cin <= 64 && d->Cout == 64 && d->Cout2 <= 64 && d->Cout2 % 4 == 0 &&
+    const bool geom_halo = d->stride == 1 && d->Cin > 32 && d->Cin <= 64;                      // 64-channel halo mode
+    const bool geom_s2 = d->stride == 2 && d->Cin <= 32 && d->tail_decode == 3 && d->Cout2 % 8 == 0;   // 32-channel stride-2 mode
+    if (!(d->ksize == 3 && (geom_halo || geom_s2) && d->Cout == 64 && d->Cout2 <= 64 && d->Cout2 % 4 == 0 &&
           d->residual == nullptr && d->up_out == nullptr && d->act == DY_ACT_SILU))
-      return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs k3 s1, 32 < Cin <= 64, Cout 64, Cout2 <= 64, SiLU, no residual / upsample");
+      return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs k3 with (s1, 32 < Cin <= 64) or (s2, Cin <= 32, SiLU bf16 tail), Cout 64, Cout2 <= 64, SiLU, no residual / upsample");
   }
 
   memset(p, 0, sizeof(*p));
@@ -943,7 +976,8 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (cout_pad / bn > 4 || cout_pad / bn > sms) mode = 1;
     else { p->BN = bn; p->n_tiles = cout_pad / bn; p->n_split = p->n_tiles; }
   }
-  if (fuse2 && mode != 3) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs the 64-channel halo mode");
+  if (fuse2 && mode != 3 && !(mode == 5 && d->tail_decode == 3))
+    return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs the 64-channel halo mode (or the 32-channel stride-2 mode with a SiLU bf16 tail)");
   const bool halo = (mode == 3 || mode == 4);
   const int rowb = (mode == 4 || mode == 5) ? 64 : 128;
   const int a_blk = kBlockM * rowb;
@@ -969,7 +1003,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   p->tiles_h = ceil_div(p->Ho, p->TH);
   p->m_tiles = p->tiles_w * p->tiles_h * ceil_div(p->B, p->TB);
   if (!halo) {
-    p->BN = pick_bn(cout_pad, p->m_tiles, kiters, env_int("DY_CONV_MAXBN", 256));
+    p->BN = fuse2 ? 64 : pick_bn(cout_pad, p->m_tiles, kiters, env_int("DY_CONV_MAXBN", 256));   // the fused tail contracts over all 64 channels of one tile
     p->n_tiles = cout_pad / p->BN;
   }
   p->halo_pitch = halo ? (env_int("DY_HALO_PITCH16", 0) ? 16 : kHaloTW + 2) : 0;
@@ -1042,10 +1076,17 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
         int rc = encode_map(&p->tmW2, d->weight2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
       }
-      if (d->tail_decode) {
+      if (d->tail_decode == 1 || d->tail_decode == 2) {
         // the threads store straight into the level's window of the channel-planar prediction tensor (B, 4+nc, A)
         p->tail_decode = d->tail_decode; p->y_nc = d->y_nc; p->y_stride = d->y_stride;
         p->y = d->y + d->y_anchor_off; p->y_A = d->y_A;
+      } else if (d->tail_decode == 3) {
+        p->tail_decode = 3;
+        const uint64_t dims[4] = {uint64_t(d->Cout2), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
+        const uint64_t strides[3] = {uint64_t(d->out2_ld) * 2, uint64_t(Wo) * d->out2_ld * 2, uint64_t(Ho) * Wo * d->out2_ld * 2};
+        const uint32_t box[4] = {32, uint32_t(p->TW), uint32_t(p->TH), uint32_t(p->TB)};
+        int rc = encode_map(&p->tmO2, d->out2, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
       } else {
         const uint64_t dims[4] = {uint64_t(d->Cout2), uint64_t(Wo), uint64_t(Ho), uint64_t(d->B)};
         const uint64_t strides[3] = {uint64_t(d->out2_ld) * 4, uint64_t(Wo) * d->out2_ld * 4, uint64_t(Ho) * Wo * d->out2_ld * 4};
@@ -1099,7 +1140,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   // cover the activation tile.  Everything else streams B next to A.
   const int cw = p->use_tma_store;
   // K-heavy generic tiles: one staging tile per group (the epilogue has slack), the room goes to fatter pipeline stages
-  p->nbuf = ((!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) || (mode == 3 && p->BN > 64)) ? 1 : 2;
+  p->nbuf = (!fuse2 && ((!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) || (mode == 3 && p->BN > 64))) ? 1 : 2;   // the fused tail stages two tiles
   const int b_tile = p->BN * rowb;
   const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
   const int bias_bytes = (fuse2 ? 576 : round_up(p->n_tiles * p->BN + 64, 4)) * 4;
@@ -1125,6 +1166,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     p->stages &= ~1;
   } else {
     p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes && !env_int("DY_NO_BRES", 0)) ? 1 : 0;   // leave room for >= 4 activation stages
+    if (fuse2 && !p->b_resident) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs resident weights");
     const int per_k = a_blk + (p->b_resident ? 0 : b_tile);
     const int avail = budget - (p->b_resident ? b_all : 0);
     // k-blocks per stage: the issuing thread pays ~300 cycles per stage (barrier wait, commit), a k-block is 4 x max(BN/2,
@@ -1208,7 +1250,7 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream)
                             : (p->eg == 3 ? conv_launch_t<3, 32, false, false, 3>(p, l, stream) : conv_launch_m<3>(p, l, stream));
     case 4: return p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream);
-    default: return conv_launch_m<5>(p, l, stream);
+    default: return p->fuse2 ? conv_launch_t<5, 32, false, true>(p, l, stream) : conv_launch_m<5>(p, l, stream);
   }
 }
 

@@ -50,6 +50,7 @@ class LayerPlan:
         self.fuse_tail = not os.environ.get("DY_NO_FUSE_TAIL")
         # decode inside the Detect tails: the raw maps of those levels are never materialised (Engine.raw_maps() is then
         # unavailable); needs the whole batch in one replay because the prediction tensor's address is baked into tensor maps
+        self.fuse_cv1 = not os.environ.get("DY_NO_FUSE_CV1")
         self.fuse_decode = (bool(fuse_decode) and self.fuse_tail and not os.environ.get("DY_NO_FUSE_DECODE")
                             and y is not None and mb == y.shape[0])
         self._build_symbolic()
@@ -140,7 +141,11 @@ class LayerPlan:
                 self._op(kind="conv", mod=m, inp=src, out=out)
             elif isinstance(m, C2f):
                 out = dest(i, m.cv2.conv.out_channels, src.H, src.W)
-                self._emit_c2f(m, src, out)
+                # the layer in front feeds only this C2f: its output can stay on the SM (see _emit_c2f)
+                j = i - 1 if f == -1 else f
+                private = (self.fuse_cv1 and isinstance(f, int) and j not in home and j not in getattr(self.model, "save", ())
+                           and self.ops and self.ops[-1]["kind"] == "conv" and self.ops[-1].get("out") == src)
+                self._emit_c2f(m, src, out, len(self.ops) - 1 if private else None)
             elif isinstance(m, SPPF):
                 out = dest(i, m.cv2.conv.out_channels, src.H, src.W)
                 c_ = m.cv1.conv.out_channels
@@ -189,11 +194,30 @@ class LayerPlan:
         cout, s = m._geom()
         return cout, 3, s
 
-    def _emit_c2f(self, m: C2f, src: Ref, out: Ref):
+    def _emit_c2f(self, m: C2f, src: Ref, out: Ref, prod: Optional[int] = None):
         c, n = m.c, len(m.m)
         H, W = src.H, src.W
         cat = self._new_buf((2 + n) * c, H, W)
-        self._op(kind="conv", mod=m.cv1, inp=src, out=Ref(cat, 0, 2 * c, H, W))
+        fused = False
+        if prod is not None:
+            # cv1 (1x1 Conv + SiLU, block.py:236) as the fused tail of the 3x3 stride-2 conv in front of it (the RepVGG
+            # downsample at P2 of the s scale: 32 -> 64, then 64 -> 64): the 64-channel tensor between them, 3.3 MB per
+            # image written and read back, never reaches HBM (dy_conv_desc.tail_decode == 3)
+            po = self.ops[prod]
+            cout, k, s_ = self._conv_geom(po["mod"]) if "mod" in po else (po["cout"], po["k"], po["s"])
+            act = isinstance(getattr(po.get("mod"), "act", getattr(po.get("mod"), "nonlinearity", None)), nn.SiLU) if "mod" in po else po["act"]
+            if (k == 3 and s_ == 2 and po["inp"].c <= 32 and cout == 64 and 2 * c <= 64 and (2 * c) % 8 == 0 and act
+                    and not any(key in po for key in ("up", "res", "tail")) and m.cv1.conv.kernel_size[0] == 1
+                    and isinstance(m.cv1.act, nn.SiLU)):
+                w1, b1 = m.cv1.packed()
+                po["tail"] = (w1, b1, 2 * c, Ref(cat, 0, 2 * c, H, W))
+                po["out"] = None
+                self.bufs[src.buf].C = 0                   # never materialised
+                cb = self.bufs[cat]
+                cb.first = min(cb.first, prod)
+                fused = True
+        if not fused:
+            self._op(kind="conv", mod=m.cv1, inp=src, out=Ref(cat, 0, 2 * c, H, W))
         for i, b in enumerate(m.m):
             xin = Ref(cat, (1 + i) * c, c, H, W)
             tmp = Ref(self._new_buf(b.cv1.conv.out_channels, H, W), 0, b.cv1.conv.out_channels, H, W)

@@ -66,7 +66,8 @@ def pack_conv_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
 def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, k: int, s: int, act: bool,
               out: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None, up_out: Optional[torch.Tensor] = None,
               tail=None) -> _C.ConvDesc:
-    """`tail` = (w2_packed, bias2, cout2, out2): fused 1x1 output conv (fp32, no activation); `out` may then be None."""
+    """`tail` = (w2_packed, bias2, cout2, out2): fused 1x1 conv behind this one; `out` may then be None.  out2 fp32 = raw
+    output conv (no activation; Detect), out2 bf16 = Conv + SiLU (C2f.cv1); a fifth element selects the fused decode."""
     xp, xld, B, H, W, Cin = nhwc_view(x, "conv input")
     if out is None:
         if tail is None:
@@ -126,9 +127,11 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
             d.tail_decode, d.y, d.y_A, d.y_nc, d.y_anchor_off, d.y_stride = mode, y.data_ptr(), y.shape[2], y.shape[1] - 4, anchor_off, float(stride)
         else:
             o2, o2ld, B2, H2, W2, C2 = nhwc_view(out2, "conv tail output")
-            if (B2, H2, W2, C2) != (B, eh, ew, cout2) or out2.dtype != torch.float32:
-                raise _C.DroneYoloError("conv tail output must be fp32 (B, Cout2, Ho, Wo)")
+            if (B2, H2, W2, C2) != (B, eh, ew, cout2) or out2.dtype not in (torch.float32, torch.bfloat16):
+                raise _C.DroneYoloError("conv tail output must be fp32 (raw logits) or bf16 (SiLU tail) (B, Cout2, Ho, Wo)")
             d.out2, d.out2_ld = o2, o2ld
+            if out2.dtype == torch.bfloat16:        # hidden Conv + SiLU as the tail (dy_conv_desc.tail_decode == 3)
+                d.tail_decode = 3
     else:
         d.weight2, d.bias2, d.Cout2, d.out2, d.out2_ld = None, None, 0, None, 0
     return d

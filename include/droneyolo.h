@@ -68,6 +68,8 @@ int dy_device_check(int device);            /* DY_OK iff `device` is compute cap
  *           head.py:100-131, for this level and branch): 1 = box branch (Cout2 == 64: DFL expectation, dist2bbox, * stride
  *           -> rows 0..3 of y), 2 = class branch (sigmoid -> rows 4..4+y_nc-1 of y).  y = fp32 [B, 4+y_nc, y_A] (the
  *           dy_detect_decode output layout), y_anchor_off = first anchor of this level; out2 is then unused.
+ *           3 = the tail is a hidden Conv + SiLU (C2f.cv1 behind the stride-2 conv that feeds it, nn/modules/block.py:227-249):
+ *           out2 = SiLU(conv1x1(...) + bias2) as a bf16 NHWC slice; also accepted for ksize 3, stride 2, Cin <= 32, Cout == 64.
  * ksize in {1,3}; stride in {1,2} (stride 2 needs even H and W); no dilation, no groups.
  */
 typedef struct dy_conv_desc {

@@ -156,6 +156,27 @@ def test_conv_fused_detect_tail(K, dev, B, H, W, cout2):
     assert bool((raw[..., :16] == -3.0).all()) and bool((raw[..., 16 + c2p:] == -3.0).all()), "wrote outside its slice"
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout2", [(2, 64, 64, 32, 64), (3, 40, 72, 32, 64), (1, 96, 32, 16, 32)])
+def test_conv_fused_silu_tail(K, dev, B, H, W, cin, cout2):
+    """C2f.cv1 (1x1 Conv + SiLU, nn/modules/block.py:236) fused behind the 3x3 stride-2 conv that feeds it: the bf16 result
+    lands in a channel slice of the C2f concat buffer; compared with the two-kernel path and with fp32 PyTorch."""
+    g = torch.Generator().manual_seed(B * 100 + cout2)
+    x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w1 = (torch.randn(64, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)).to(dev); b1 = torch.randn(64, generator=g).to(dev)
+    w2 = (torch.randn(cout2, 64, 1, 1, generator=g) / 8.0).to(dev); b2 = torch.randn(cout2, generator=g).to(dev)
+    w1p, b1p = K.pack_conv_weight(w1, b1)
+    w2p, b2p = K.pack_conv_weight(w2, b2)
+    cat = torch.full((B, H // 2, W // 2, cout2 + 32), 7.0, device=dev, dtype=torch.bfloat16)       # cv1's slice + a bottleneck slice
+    out2 = cat.permute(0, 3, 1, 2)[:, :cout2]
+    K.conv2d(x, w1p, b1p, 64, 3, 2, True, tail=(w2p, b2p, cout2, out2))
+    mid = K.conv2d(x, w1p, b1p, 64, 3, 2, True)                       # two-kernel path
+    two = K.conv2d(mid, w2p, b2p, cout2, 1, 1, True)
+    close(out2, two, 1e-2, 1e-2)                                      # same bf16 intermediate and weights; bf16 output rounding
+    ref = F.silu(F.conv2d(F.silu(F.conv2d(x.float(), w1.to(torch.bfloat16).float(), b1, stride=2, padding=1)), w2.to(torch.bfloat16).float(), b2))
+    close(out2, ref, 2e-2, 3e-2)
+    assert bool((cat[..., cout2:] == 7.0).all()), "wrote outside its slice"
+
+
 def test_conv_rejects_bad_arguments(K, dev):
     from drone_yolo_b200._C import DroneYoloError
 

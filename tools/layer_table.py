@@ -28,6 +28,7 @@ def plan_ops(scale, imgsz, batch):
     lp.fuse_upsample = True
     lp.fuse_tail = True
     lp.fuse_decode = True
+    lp.fuse_cv1 = True
     lp._build_symbolic()
     rows = []
     for op in lp.ops:
