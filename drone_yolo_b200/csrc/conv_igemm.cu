@@ -840,8 +840,18 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  // L2 promotion widens every DRAM fetch of a box row to 64 / 128 / 256 bytes.  256 is right when consecutive pixels are
+  // contiguous (the box spans the whole inner dimension of a dense tensor); for a channel SLICE of a wider buffer it drags in
+  // the neighbouring channels nobody asked for (measured: a 64-channel slice of a 128-channel buffer read 452 MB for 210,
+  // a 32-channel slice of a 96-channel concat buffer 222 MB for 105), so a slice is promoted to its own row length only.
+  const unsigned esz = dtype == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4u : (dtype == CU_TENSOR_MAP_DATA_TYPE_UINT8 ? 1u : 2u);
+  const unsigned long long row_bytes = static_cast<unsigned long long>(box[0]) * esz;
+  const bool dense_rows = rank > 1 && box[0] == dims[0] && strides_bytes[0] == dims[0] * esz;
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  static const bool narrow = getenv("DY_TMAP_PROMO256") == nullptr;
+  if (narrow && !dense_rows && row_bytes < 256) promo = row_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
   CUresult r = fn(m, dtype, rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(DY_ERR_CUDA,
