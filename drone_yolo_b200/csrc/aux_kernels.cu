@@ -193,6 +193,74 @@ int sppf_pool_launch(void* buf, int B, int H, int W, int C, int ld, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Letterbox: one thread per 4 consecutive output columns of one row (three 4-byte plane stores).  The resize is OpenCV's
+// 8-bit INTER_LINEAR: source coordinate (float)((d + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in double, 11-bit
+// fixed-point coefficients, horizontal pass in int, vertical pass ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+// ------------------------------------------------------------------------------------------------
+struct LbCoef { int i0, i1, a0, a1; };
+
+__device__ __forceinline__ LbCoef lb_coef(int d, double scale, int n_src) {
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int i = static_cast<int>(floorf(f));
+  f -= static_cast<float>(i);
+  if (i < 0) { i = 0; f = 0.f; }
+  if (i >= n_src - 1) { i = n_src - 1; f = 0.f; }
+  LbCoef c;
+  c.i0 = i; c.i1 = min(i + 1, n_src - 1);
+  c.a1 = __float2int_rn(f * 2048.f);
+  c.a0 = __float2int_rn((1.f - f) * 2048.f);
+  return c;
+}
+
+__global__ void __launch_bounds__(256) letterbox_u8_kernel(const uint8_t* __restrict__ src, int h, int w, int pitch,
+                                                           uint8_t* __restrict__ dst, int H, int W, int new_w, int new_h,
+                                                           int left, int top, int fill, double scale_x, double scale_y) {
+  const int wq = W >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wq * H) return;
+  const int y = idx / wq, x0 = (idx - y * wq) * 4;
+  uint32_t out[3] = {0u, 0u, 0u};
+  const int dy = y - top;
+  const bool row_in = dy >= 0 && dy < new_h;
+  LbCoef cy{};
+  if (row_in) cy = lb_coef(dy, scale_y, h);
+  const uint8_t* r0 = src + static_cast<size_t>(cy.i0) * pitch;
+  const uint8_t* r1 = src + static_cast<size_t>(cy.i1) * pitch;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dx = x0 + k - left;
+    uint32_t v[3] = {static_cast<uint32_t>(fill), static_cast<uint32_t>(fill), static_cast<uint32_t>(fill)};
+    if (row_in && dx >= 0 && dx < new_w) {
+      const LbCoef cx = lb_coef(dx, scale_x, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int t0 = r0[cx.i0 * 3 + c] * cx.a0 + r0[cx.i1 * 3 + c] * cx.a1;
+        const int t1 = r1[cx.i0 * 3 + c] * cx.a0 + r1[cx.i1 * 3 + c] * cx.a1;
+        v[2 - c] = static_cast<uint32_t>((((cy.a0 * (t0 >> 4)) >> 16) + ((cy.a1 * (t1 >> 4)) >> 16) + 2) >> 2);   // BGR -> RGB plane
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] |= (v[c] & 0xffu) << (8 * k);
+  }
+  const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t*>(dst + c * plane + static_cast<size_t>(y) * W + x0) = out[c];
+}
+
+int letterbox_u8_launch(const void* src, int h, int w, int pitch, void* dst, int H, int W, int new_w, int new_h, int left,
+                        int top, int fill, cudaStream_t stream) {
+  DY_CHECK_ARG(src && dst && h > 0 && w > 0 && H > 0 && W > 0 && pitch >= 3 * w, "letterbox: bad argument");
+  DY_CHECK_ARG(W % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0, "letterbox: W must be a multiple of 4 and dst 4B aligned");
+  DY_CHECK_ARG(new_w > 0 && new_h > 0 && left >= 0 && top >= 0 && left + new_w <= W && top + new_h <= H,
+               "letterbox: the resized image (%dx%d at %d,%d) does not fit the %dx%d canvas", new_w, new_h, left, top, W, H);
+  const double sx = 1.0 / (static_cast<double>(new_w) / w), sy = 1.0 / (static_cast<double>(new_h) / h);
+  const int n = (W >> 2) * H;
+  letterbox_u8_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(static_cast<const uint8_t*>(src), h, w, pitch, static_cast<uint8_t*>(dst),
+                                                          H, W, new_w, new_h, left, top, fill, sx, sy);
+  return launch_status("letterbox_u8_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2x nearest upsample: one thread per (output pixel, 8-channel vector).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int B, int H, int W,
@@ -292,6 +360,10 @@ int dwconv_launch(const void* in, int in_ld, int B, int H, int W, int Cin, const
 extern "C" int dy_stem_conv(const void* in, int in_dtype, int B, int H, int W, const float* weight, const float* bias, int Cout,
                             void* out, int out_ld, void* stream) {
   return dy::stem_launch(in, in_dtype, B, H, W, weight, bias, Cout, out, out_ld, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dy_letterbox_u8(const void* src, int h, int w, int src_pitch, void* dst, int H, int W, int new_w, int new_h,
+                               int left, int top, int fill, void* stream) {
+  return dy::letterbox_u8_launch(src, h, w, src_pitch, dst, H, W, new_w, new_h, left, top, fill, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dy_sppf_pool(void* buf, int B, int H, int W, int C, int ld, void* stream) {
   return dy::sppf_pool_launch(buf, B, H, W, C, ld, static_cast<cudaStream_t>(stream));

@@ -169,6 +169,21 @@ def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optio
     return out
 
 
+def letterbox_u8(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: int, left: int, top: int, fill: int = 114) -> torch.Tensor:
+    """One raw frame (h, w, 3) uint8 BGR on the device -> one (3, H, W) uint8 RGB image of the engine's input batch:
+    LetterBox (data/augment.py:1544-1610) + BGR->RGB + HWC->CHW in one kernel."""
+    _C.require_cuda(src)
+    _C.require_cuda(dst)
+    if src.dtype != torch.uint8 or dst.dtype != torch.uint8 or src.dim() != 3 or src.shape[2] != 3 or src.stride(2) != 1 or src.stride(1) != 3:
+        raise _C.DroneYoloError("letterbox: src must be a uint8 (h, w, 3) image with packed pixels")
+    if dst.dim() != 3 or dst.shape[0] != 3 or not dst.is_contiguous():
+        raise _C.DroneYoloError("letterbox: dst must be a contiguous uint8 (3, H, W) tensor")
+    _C.check(_C.lib().dy_letterbox_u8(src.data_ptr(), src.shape[0], src.shape[1], src.stride(0), dst.data_ptr(), dst.shape[1],
+                                      dst.shape[2], int(new_w), int(new_h), int(left), int(top), int(fill), _C.stream_ptr(dst.device)),
+             "dy_letterbox_u8")
+    return dst
+
+
 def sppf_pool(buf: torch.Tensor, c: int) -> torch.Tensor:
     """buf: bf16 NHWC (B,>=4c,H,W); fills channels [c,4c) with mp5, mp5∘mp5, mp5∘mp5∘mp5 of channels [0,c)."""
     p, ld, B, H, W, Cc = nhwc_view(buf, "sppf buffer")

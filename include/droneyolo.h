@@ -118,6 +118,18 @@ int dy_upsample2x(const void* in, int in_ld, int B, int H, int W, int C, void* o
 int dy_dwconv3x3s2(const void* in, int in_ld, int B, int H, int W, int Cin, const float* weight,
                    const float* bias, int Cout, void* out, int out_ld, void* stream);
 
+/* Letterbox preprocess of ONE image: bilinear resize + constant border + BGR->RGB + HWC->CHW, uint8 in, uint8 out.
+ * Replaces: LetterBox.__call__  data/augment.py:1544-1610 (cv2.resize(INTER_LINEAR) + cv2.copyMakeBorder(114)) and the
+ *           `[..., ::-1].transpose(0, 3, 1, 2)` of BasePredictor.preprocess  engine/predictor.py:127-131, fused.
+ * src     : uint8 HWC BGR [h][w][3] on the device, row pitch src_pitch bytes (the raw frame, uploaded as is)
+ * dst     : uint8 CHW RGB [3][H][W] on the device (one image of the engine's uint8 input batch)
+ * new_w/new_h : size of the resized image inside the canvas, left/top : its offset (the reference's rounding of dw, dh);
+ *           every other pixel is `fill` (114).  The resize follows OpenCV's 8-bit INTER_LINEAR fixed-point arithmetic
+ *           (11-bit coefficients): bit-exact with cv2 when shrinking, within 1 level on < 0.1 % of the pixels when enlarging.
+ */
+int dy_letterbox_u8(const void* src, int h, int w, int src_pitch, void* dst, int H, int W, int new_w, int new_h,
+                    int left, int top, int fill, void* stream);
+
 /* ----------------------------------------------------------------------------------------
  * Detect decode: DFL softmax-expectation + dist2bbox(xywh) + stride scaling + class sigmoid.
  * Replaces: Detect._inference  nn/modules/head.py:100-131, DFL.forward block.py:73-76,

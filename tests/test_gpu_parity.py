@@ -489,6 +489,38 @@ def test_engine_vs_cpu_oracle(dev, scale, imgsz, B, mb):
     assert torch.equal(o0b[0], o0[0]) and torch.equal(o0b[1], o0[1])
 
 
+@pytest.mark.parametrize("h,w,imgsz,auto", [(1080, 1920, 640, True), (720, 1280, 640, False), (480, 640, 640, True),
+                                            (375, 500, 640, False), (64, 48, 128, False)])
+def test_letterbox_kernel_vs_oracle(K, dev, h, w, imgsz, auto):
+    """dy_letterbox_u8 (resize + border + BGR->RGB + CHW in one kernel) bit-exact against the numpy restatement of the
+    reference's LetterBox + cv2 8-bit INTER_LINEAR (oracle/letterbox_np.py, pinned against cv2 in the CPU tests)."""
+    from oracle import letterbox_np
+
+    im = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    new_w, new_h, left, top, H, W = letterbox_np.geometry((h, w), (imgsz, imgsz), auto=auto)
+    dst = torch.zeros((3, H, W), dtype=torch.uint8, device=dev)
+    K.letterbox_u8(torch.from_numpy(im).to(dev), dst, new_w, new_h, left, top)
+    ref = letterbox_np.letterbox_chw_rgb(im, (imgsz, imgsz), auto=auto)
+    assert np.array_equal(dst.cpu().numpy(), ref)
+
+
+def test_predict_gpu_preprocess_matches_host_path(dev):
+    """List-of-frames source: the GPU letterbox path gives the same detections as the host cv2 path (shrinking: same pixels)."""
+    from drone_yolo_b200 import YOLO
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    frames = [np.random.default_rng(i).integers(0, 256, (360, 640, 3), dtype=np.uint8) for i in range(3)]
+    a = model.predict(frames, imgsz=320, conf=0.001, iou=0.7, device=dev, gpu_preprocess=True)
+    model.predictor = None
+    b = model.predict(frames, imgsz=320, conf=0.001, iou=0.7, device=dev, gpu_preprocess=False)
+    assert len(a) == len(b) == 3
+    for ra, rb in zip(a, b):
+        assert ra.orig_shape == rb.orig_shape == (360, 640)
+        assert torch.equal(torch.as_tensor(ra.boxes.data), torch.as_tensor(rb.boxes.data))
+
+
 def test_predict_api_matches_engine(dev):
     from drone_yolo_b200 import YOLO
     from drone_yolo_b200._C import DroneYoloError
