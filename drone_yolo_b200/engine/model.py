@@ -2,6 +2,7 @@
 models/yolo/model.py:11-59, detect row of the task map)."""
 from __future__ import annotations
 
+import pickle
 from pathlib import Path
 
 import torch
@@ -35,10 +36,20 @@ class Model(nn.Module):
     def _load(self, weights, nc=None):
         """Load `<name>.pt` holding {'yaml': cfg-name-or-dict, 'model': state_dict} or a bare state_dict next to a
         YAML named by `cfg` (engine/model.py:266-302; pickled reference checkpoints: tools/export_state_dict.py)."""
-        obj = torch.load(weights, map_location="cpu", weights_only=True)
-        cfg = obj.get("yaml") if isinstance(obj, dict) else None
-        if cfg is None:
-            raise ValueError(f"{weights}: expected a dict with keys 'yaml' and 'model' (state_dict)")
+        try:
+            obj = torch.load(weights, map_location="cpu", weights_only=True)
+        except pickle.UnpicklingError:
+            obj = None                                # not a plain tensor container: a pickled reference checkpoint
+        if not (isinstance(obj, dict) and obj.get("yaml") is not None and isinstance(obj.get("model"), dict)):
+            # the reference's own format: {'model': <pickled DetectionModel>, 'ema': ..., 'train_args': ...}
+            # (nn/tasks.py:786-926, attempt_load_one_weight), read without the reference package (nn/ckpt.py)
+            from ..nn.ckpt import load_reference_checkpoint
+
+            cfg, state, names, _ = load_reference_checkpoint(weights)
+            obj = {"yaml": cfg, "model": state, "nc": cfg.get("nc", nc)}
+            if names is not None:
+                obj["names"] = names
+        cfg = obj["yaml"]
         self.model = DetectionModel(cfg, nc=obj.get("nc", nc), verbose=False)
         self.model.load(obj["model"], verbose=False)
         if "names" in obj:

@@ -521,6 +521,28 @@ def test_predict_gpu_preprocess_matches_host_path(dev):
         assert torch.equal(torch.as_tensor(ra.boxes.data), torch.as_tensor(rb.boxes.data))
 
 
+def test_predict_from_reference_pickled_checkpoint(dev, golden_dir):
+    """YOLO('<reference>.pt').predict(...) (mix6.py:18,79-82): the pickled reference checkpoint gives the same detections as the
+    same weights loaded into a model built from its YAML."""
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200.nn.ckpt import load_reference_checkpoint
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    path = str(golden_dir / "ref_ckpt_tiny.pt")
+    a = YOLO(path)
+    cfg, state, _, _ = load_reference_checkpoint(path)
+    ref = DetectionModel(cfg, nc=10, verbose=False)
+    ref.load_state_dict(state)
+    b = YOLO(ref.eval())
+    x = recipe.images(2, 128, 128).to(dev)
+    ra = a.predict(x, conf=0.001, iou=0.7, device=dev)
+    rb = b.predict(x, conf=0.001, iou=0.7, device=dev)
+    assert len(ra) == len(rb) == 2
+    for u, v in zip(ra, rb):
+        assert torch.equal(torch.as_tensor(u.boxes.data), torch.as_tensor(v.boxes.data))
+    assert ra[0].names[3] == "cls3"
+
+
 def test_predict_api_matches_engine(dev):
     from drone_yolo_b200 import YOLO
     from drone_yolo_b200._C import DroneYoloError

@@ -149,6 +149,49 @@ def test_letterbox_oracle_vs_cv2(h, w, imgsz, auto):
         assert d.max() <= 1 and (d > 0).mean() < 1e-3
 
 
+def test_reference_pickled_checkpoint_ingestion(golden_dir):
+    """A `.pt` written by the REAL reference (tools/make_ckpt_fixture.py: torch.save of its DetectionModel, the format
+    mix6.py:18 loads) is read without the reference package: same YAML, names and weights (nn/tasks.py:786-926)."""
+    import hashlib
+    import json
+
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200.nn.ckpt import load_reference_checkpoint
+
+    meta = json.loads((golden_dir / "ref_ckpt_tiny.json").read_text())
+    cfg, state, names, train_args = load_reference_checkpoint(str(golden_dir / "ref_ckpt_tiny.pt"))
+    assert cfg["scale"] == "t" and cfg["nc"] == 10 and len(state) == meta["n_tensors"] and train_args["task"] == "detect"
+    assert {int(k): v for k, v in names.items()} == {int(k): v for k, v in meta["names"].items()}
+
+    def digest(sd):
+        h = hashlib.sha256()
+        for k in sorted(sd):
+            h.update(k.encode())
+            h.update(sd[k].detach().float().contiguous().numpy().tobytes())
+        return h.hexdigest()
+
+    assert digest(state) == meta["digest"]
+    model = YOLO(str(golden_dir / "ref_ckpt_tiny.pt"))                       # the user-facing path (engine/model.py:266-302)
+    assert digest(model.model.state_dict()) == meta["digest"]
+    assert model.names[3] == "cls3"
+    with pytest.raises(Exception):                                            # anything outside ultralytics / torch is refused
+        import io
+        import pickle
+
+        class Evil:
+            def __reduce__(self):
+                return (os.system, ("true",))
+
+        buf = io.BytesIO()
+        pickle.dump({"model": Evil()}, buf)
+        p = golden_dir.parent / "_evil_tmp.pt"
+        p.write_bytes(buf.getvalue())
+        try:
+            load_reference_checkpoint(str(p))
+        finally:
+            p.unlink()
+
+
 def test_cpu_tensors_fail_loudly():
     from drone_yolo_b200 import YOLO
     from drone_yolo_b200._C import DroneYoloError
