@@ -657,7 +657,8 @@ int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
   DY_CHECK_ARG(static_cast<unsigned long long>(d->A) * d->nc < (1ull << 32), "nms: A*nc must fit 32 bits");
   DY_CHECK_ARG(d->conf_thres >= 0.f && d->conf_thres <= 1.f, "nms: conf_thres outside [0,1]");
   DY_CHECK_ARG(d->iou_thres >= 0.0 && d->iou_thres <= 1.0, "nms: iou_thres outside [0,1]");
-  DY_CHECK_ARG(d->max_det > 0 && d->max_det <= 4096, "nms: max_det must be in [1,4096]");
+  DY_CHECK_ARG(d->max_det > 0 && kSelSharedBytes + kept_bytes(d->max_det) + static_cast<size_t>(kBig) * 8 <= 227 * 1024,
+               "nms: max_det %d does not fit the select kernel's shared memory (36 B of kept-box state per detection: max ~4000)", d->max_det);
   DY_CHECK_ARG(d->max_nms > 0, "nms: max_nms must be positive");
   const int ml = d->multi_label && d->nc > 1;
   const NmsWorkspace w = nms_workspace_layout(d->B, d->nc, d->A, ml);
