@@ -79,6 +79,8 @@ SYMBOLS = {
     "dy_detect_decode": (C.c_int, [C.POINTER(DecodeDesc), C.c_void_p]),
     "dy_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dy_nms": (C.c_int, [C.POINTER(NmsDesc), C.c_void_p]),
+    "dy_box_nms_f64_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "dy_box_nms_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dy_program_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "dy_program_destroy": (None, [C.c_void_p]),
     "dy_program_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),

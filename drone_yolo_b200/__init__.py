@@ -11,3 +11,4 @@ __version__ = "0.1.0"
 
 from .engine.model import YOLO  # noqa: E402,F401
 from .nn.tasks import DetectionModel  # noqa: E402,F401
+from .engine.slicer import InferenceSlicer  # noqa: E402,F401

@@ -24,7 +24,7 @@ from .results import Results
 
 DEFAULTS = dict(task="detect", mode="predict", imgsz=640, batch=1, device=None, conf=0.25, iou=0.7, max_det=300,
                 half=False, classes=None, agnostic_nms=False, augment=False, stream=False, verbose=False,
-                micro_batch=0, cuda_graph=True, multi_label=False, gpu_preprocess=True)
+                micro_batch=0, cuda_graph=True, multi_label=False, gpu_preprocess=True, engine_cache=8)
 EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end", "on_predict_end")
 
 
@@ -111,7 +111,7 @@ class DetectionPredictor:
         key = (B, H, W, dtype, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes else None, a.agnostic_nms, a.multi_label,
                a.micro_batch, a.cuda_graph)
         if key not in self.engines:
-            if len(self.engines) >= 4:
+            if len(self.engines) >= max(int(getattr(a, "engine_cache", 8)), 1):     # engines hold their arenas: bounded
                 self.engines.clear()
             self.engines[key] = Engine(self.model, B, (H, W), self.device, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou,
                                        max_det=a.max_det, classes=a.classes, agnostic=a.agnostic_nms,

@@ -323,6 +323,22 @@ def nms(pred: torch.Tensor, conf_thres: float, iou_thres: float, max_det: int = 
     return bufs.out, bufs.counts, bufs.kept
 
 
+def box_nms_f64(rows: torch.Tensor, iou_thres: float, class_agnostic: bool = False) -> torch.Tensor:
+    """Merge NMS of the tiled-frame dispatch (the overlap filter of supervision.InferenceSlicer, mix6.py:84-89):
+    rows (n, 6) float64 [x1, y1, x2, y2, conf, cls] on the device -> keep mask (n,) bool in the original row order."""
+    _C.require_cuda(rows)
+    if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[1] != 6 or not rows.is_contiguous():
+        raise _C.DroneYoloError("box_nms_f64: rows must be a contiguous float64 (n, 6) tensor")
+    n = rows.shape[0]
+    keep = torch.zeros((n,), dtype=torch.uint8, device=rows.device)
+    if n == 0:
+        return keep.bool()
+    ws = torch.empty((_C.lib().dy_box_nms_f64_workspace_bytes(n) + 7) // 8, dtype=torch.int64, device=rows.device)
+    _C.check(_C.lib().dy_box_nms_f64(rows.data_ptr(), n, float(iou_thres), int(bool(class_agnostic)), keep.data_ptr(),
+                                     ws.data_ptr(), ws.numel() * 8, _C.stream_ptr(rows.device)), "dy_box_nms_f64")
+    return keep.bool()
+
+
 def selftest_umma(n: int, k: int) -> float:
     err = C.c_float(float("nan"))
     _C.check(_C.lib().dy_selftest_umma(n, k, C.byref(err), _C.stream_ptr()), "dy_selftest_umma")

@@ -179,6 +179,20 @@ size_t dy_nms_workspace_bytes(int B, int nc, int A, int multi_label);
 int dy_nms(const dy_nms_desc* d, void* stream);
 
 /* ----------------------------------------------------------------------------------------
+ * Tile merge: category-aware greedy NMS over the detections of all tiles of ONE frame (frame coordinates, float64).
+ * Replaces: the overlap filter of supervision.InferenceSlicer as mix6.py:84-89 configures it (Detections.with_nms ->
+ *           box_non_max_suppression; third-party, not under the reference tree: restated in oracle/slicer_np.py).
+ * rows    : float64 [n, 6] on the device: x1,y1,x2,y2,conf,cls
+ * keep    : uint8 [n] on the device, ORIGINAL row order: 1 = survives
+ * Ranking by conf descending, equal conf: higher row first; a kept row suppresses later-ranked rows of the same cls
+ * (any cls when class_agnostic) with IoU > iou_thres (strict), IoU = inter / (area_a + area_b - inter) in float64.
+ * workspace: device scratch of dy_box_nms_f64_workspace_bytes(n) bytes (8B aligned); n <= 16384.
+ */
+size_t dy_box_nms_f64_workspace_bytes(int n);
+int dy_box_nms_f64(const double* rows, int n, double iou_thres, int class_agnostic, unsigned char* keep, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------
  * Program: a recorded sequence of the ops above with tensor maps encoded once, replayed per batch.
  * Replaces: the Python layer loop BaseModel._predict_once  nn/tasks.py:134-161 for a fixed
  *           (batch, H, W).  `dy_program_run` only enqueues kernels (capturable in a CUDA graph).

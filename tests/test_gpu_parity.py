@@ -566,3 +566,78 @@ def test_predict_api_matches_engine(dev):
         model.predict(torch.rand(1, 3, 100, 100, device=dev), device="cuda:0")
     with pytest.raises(DroneYoloError):
         model.predict(x, device="cuda:0", augment=True)
+
+
+# ---------------------------------------------------------------------------------------------- tiled frames (mix6.py:84-89)
+def _clustered_rows(n, seed, n_cls=3, ties=True):
+    """n float64 rows: boxes in clusters (heavy overlap), few categories, scores quantised so that ties occur."""
+    g = np.random.default_rng(seed)
+    centres = g.uniform(50, 3000, (max(n // 6, 1), 2))
+    c = centres[g.integers(0, len(centres), n)] + g.normal(0, 6, (n, 2))
+    wh = g.uniform(20, 80, (n, 2))
+    conf = g.uniform(0.05, 1.0, n)
+    if ties:
+        conf = np.round(conf * 50) / 50
+    rows = np.concatenate([c - wh / 2, c + wh / 2, conf[:, None], g.integers(0, n_cls, (n, 1)).astype(np.float64)], 1)
+    return np.ascontiguousarray(rows.astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.parametrize("agnostic", [False, True])
+@pytest.mark.parametrize("n", [0, 1, 2, 63, 64, 65, 129, 1000, 3000])
+def test_tile_merge_nms_vs_oracle(K, dev, n, agnostic):
+    from oracle import slicer_np
+
+    rows = _clustered_rows(n, seed=n + 7)
+    if n >= 64:                                                   # degenerate rows: zero area (NaN IoU), exact duplicates
+        rows[5, 2:4] = rows[5, 0:2]
+        rows[6] = rows[5]
+        rows[9] = rows[8]
+    want = slicer_np.box_nms_keep(rows, 0.5, agnostic)
+    got = K.box_nms_f64(torch.from_numpy(rows).to(dev), 0.5, agnostic).cpu().numpy()
+    assert got.dtype == bool and got.shape == (n,)
+    assert np.array_equal(got, want)
+    if n >= 1000:
+        assert 0 < got.sum() < n
+
+
+def test_tile_merge_rejects_bad_arguments(K, dev):
+    from drone_yolo_b200._C import DroneYoloError
+
+    with pytest.raises(DroneYoloError):
+        K.box_nms_f64(torch.zeros((4, 6), dtype=torch.float64), 0.5)                      # CPU tensor
+    with pytest.raises(DroneYoloError):
+        K.box_nms_f64(torch.zeros((4, 6), dtype=torch.float32, device=dev), 0.5)          # wrong dtype
+    with pytest.raises(DroneYoloError):
+        K.box_nms_f64(torch.zeros((4, 6), dtype=torch.float64, device=dev), 1.5)          # threshold outside [0, 1]
+    with pytest.raises(DroneYoloError):
+        K.box_nms_f64(torch.zeros((16385, 6), dtype=torch.float64, device=dev), 0.5)      # more rows than the scan CTA owns
+
+
+def test_inference_slicer_one_batch_matches_tile_list_predict(dev):
+    """A frame cut into 6 ragged tiles and run as ONE engine batch gives exactly the detections of predict(list of tiles)
+    (the reference predictor's semantics for a list of differently shaped images) merged by the oracle."""
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200.engine.slicer import InferenceSlicer, generate_offsets
+    from oracle import slicer_np
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    frame = np.random.default_rng(3).integers(0, 256, (700, 1100, 3), dtype=np.uint8)
+    kw = dict(imgsz=320, conf=0.001, iou=0.7, max_det=100, device=dev)
+    slicer = InferenceSlicer(model, slice_wh=(500, 500), overlap_ratio_wh=(0.2, 0.2), iou_threshold=0.7, **kw)
+    res = slicer(frame)
+    offsets = generate_offsets((1100, 700), (500, 500), (0.2, 0.2))
+    assert np.array_equal(offsets, slicer_np.generate_offsets((1100, 700), (500, 500), (0.2, 0.2))) and len(offsets) == 6
+    assert np.array_equal(res.tiles, offsets)
+    tiles = [np.ascontiguousarray(frame[y0:y1, x0:x1]) for x0, y0, x1, y1 in offsets.tolist()]
+    per_tile = model.predict(tiles, **kw)
+    assert sum(len(r) for r in per_tile) > 0
+    want = slicer_np.merge_tiles([np.asarray(r.boxes.data) for r in per_tile], offsets, 0.7)
+    got = np.asarray(res.boxes.data)
+    assert got.dtype == np.float64 and res.orig_shape == (700, 1100)
+    assert np.array_equal(got, want)
+    assert 0 < len(got) <= sum(len(r) for r in per_tile)
+    assert float(got[:, 2].max()) <= 1100 and float(got[:, 3].max()) <= 700 and float(got[:, :4].min()) >= 0
+    again = slicer(frame)                                          # cached engine, reused staging
+    assert np.array_equal(np.asarray(again.boxes.data), got)

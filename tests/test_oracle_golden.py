@@ -123,3 +123,47 @@ def test_fuse_reparameterisation_is_exact_enough(golden_dir, tag):
     for a, b in zip(raw0, raw1):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-3, atol=2e-3)
     np.testing.assert_allclose(y0[:, :4], y1[:, :4], atol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------- tiled frames (mix6.py:84-89)
+def test_slicer_offsets_known_answers():
+    """Hand-computed tile grids: the call site's own arguments on a 4K frame (mix6.py:84-87), and an exact-fit frame."""
+    from oracle import slicer_np
+    from drone_yolo_b200.engine.slicer import generate_offsets
+
+    want = [[0, 0, 2160, 2160], [1728, 0, 3840, 2160], [3456, 0, 3840, 2160],
+            [0, 1728, 2160, 2160], [1728, 1728, 3840, 2160], [3456, 1728, 3840, 2160]]      # stride 2160 - int(0.2 * 2160) = 1728
+    assert slicer_np.generate_offsets((3840, 2160), (2160, 2160), (0.2, 0.2)).tolist() == want
+    assert generate_offsets((3840, 2160), (2160, 2160), (0.2, 0.2)).tolist() == want
+    assert slicer_np.generate_offsets((640, 640), (640, 640), (0.0, 0.0)).tolist() == [[0, 0, 640, 640]]
+    g = np.random.default_rng(0)
+    for _ in range(50):
+        wh = (int(g.integers(1, 5000)), int(g.integers(1, 5000)))
+        sl = (int(g.integers(1, 3000)), int(g.integers(1, 3000)))
+        ov = (float(g.uniform(0, 0.9)), float(g.uniform(0, 0.9)))
+        a, b = slicer_np.generate_offsets(wh, sl, ov), generate_offsets(wh, sl, ov)
+        assert np.array_equal(a, b) and a.dtype == b.dtype == np.int64
+        assert a[:, 2].max() == wh[0] and a[:, 3].max() == wh[1] and (a[:, 2] > a[:, 0]).all() and (a[:, 3] > a[:, 1]).all()
+
+
+def test_slicer_merge_nms_known_answers():
+    from oracle import slicer_np
+
+    box = [10.0, 10.0, 50.0, 50.0]
+    rows = np.array([box + [0.5, 0], box + [0.9, 0], box + [0.8, 1], [200, 200, 240, 240, 0.1, 0]], dtype=np.float64)
+    assert slicer_np.box_nms_keep(rows, 0.5).tolist() == [False, True, True, True]          # same box: best of each category
+    assert slicer_np.box_nms_keep(rows, 0.5, class_agnostic=True).tolist() == [False, True, False, True]
+    tie = np.array([box + [0.7, 0], box + [0.7, 0]], dtype=np.float64)
+    assert slicer_np.box_nms_keep(tie, 0.5).tolist() == [False, True]                       # equal conf: the higher row ranks first
+    half = np.array([[0, 0, 10, 10, 0.9, 0], [0, 0, 10, 5, 0.8, 0]], dtype=np.float64)      # IoU exactly 0.5
+    assert slicer_np.box_nms_keep(half, 0.5).tolist() == [True, True]                       # strict >
+    assert slicer_np.box_nms_keep(half, 0.4999).tolist() == [True, False]
+    flat = np.array([[5, 5, 5, 5, 0.9, 0], [5, 5, 5, 5, 0.8, 0]], dtype=np.float64)         # zero area: IoU is NaN, nothing removed
+    assert slicer_np.box_nms_keep(flat, 0.5).tolist() == [True, True]
+    assert slicer_np.box_nms_keep(np.zeros((0, 6)), 0.5).shape == (0,)
+    # an object in the overlap of two tiles is found twice; after the move to frame coordinates the weaker copy goes
+    t0 = np.array([[1800, 100, 1900, 200, 0.8, 0]], dtype=np.float32)
+    t1 = np.array([[72.5, 100, 172, 200, 0.9, 0], [500, 500, 600, 600, 0.3, 2]], dtype=np.float32)
+    offs = slicer_np.generate_offsets((3840, 2160), (2160, 2160), (0.2, 0.2))
+    out = slicer_np.merge_tiles([t0, t1], offs[:2], 0.7)
+    assert out.dtype == np.float64 and out.tolist() == [[1800.5, 100, 1900, 200, np.float32(0.9), 0], [2228, 500, 2328, 600, np.float32(0.3), 2]]
