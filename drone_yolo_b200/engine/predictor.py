@@ -238,30 +238,26 @@ class DetectionPredictor:
         return eng.step()
 
     def postprocess(self, preds, img, orig_imgs, paths):
-        """Padded detections -> Results; boxes rescaled to the original image (detect/predict.py:37-73)."""
+        """Padded detections -> Results; boxes rescaled to the original image (detect/predict.py:37-73).  One D2H of
+        (B, max_det, 6), one batched rescale + clamp (the reference's per-image scale_boxes arithmetic, element for element);
+        each Results holds a view of its first counts[i] rows."""
         out, counts = preds
-        k = int(self.args.max_det)
-        host = torch.empty((out.shape[0], k * 6 + 1), dtype=torch.float32)
-        host[:, : k * 6] = out.reshape(out.shape[0], -1).cpu()     # one D2H of (B, max_det, 6)
+        B = out.shape[0]
+        host = out.cpu() if out.is_cuda else out.clone()
         n = counts.cpu().tolist()
         names = self.model.names
-        results = []
         in_shape = tuple(img.shape[2:])
-        for i in range(out.shape[0]):
-            rows = host[i, : n[i] * 6].reshape(n[i], 6).clone()
-            if isinstance(orig_imgs, torch.Tensor):
-                src = orig_imgs
-                oshape = in_shape
-
-                def lazy(j=i, t=src):
+        tensor_src = isinstance(orig_imgs, torch.Tensor)
+        oshapes = [in_shape] * B if tensor_src else [tuple(o.shape[:2]) for o in orig_imgs]
+        ops.scale_boxes_batch(in_shape, host[..., :4], oshapes)
+        results = []
+        for i in range(B):
+            if tensor_src:
+                def orig(j=i, t=orig_imgs):
                     return ops.convert_torch2numpy_batch(t[j:j + 1])[0]
-
-                orig = lazy
             else:
                 orig = orig_imgs[i]
-                oshape = orig.shape[:2]
-            rows[:, :4] = ops.scale_boxes(in_shape, rows[:, :4], oshape)
-            results.append(Results(orig, path=paths[i], names=names, boxes=rows, orig_shape=oshape))
+            results.append(Results(orig, path=paths[i], names=names, boxes=host[i, :n[i]], orig_shape=oshapes[i]))
         return results
 
     def predict_cli(self, source=None, model=None):

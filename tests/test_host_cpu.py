@@ -254,3 +254,33 @@ def test_two_rank_gather_over_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
+
+
+def test_batched_postprocess_equals_per_image_scale_boxes():
+    """DetectionPredictor.postprocess rescales the whole (B, max_det, 6) block at once; every row must equal the reference's
+    per-image scale_boxes arithmetic (ops.py:92-127) bit for bit: tensor source, same-shape frames and ragged frames."""
+    from types import SimpleNamespace
+
+    from drone_yolo_b200.engine.predictor import DetectionPredictor
+    from drone_yolo_b200.utils import ops
+
+    p = DetectionPredictor(overrides=dict(max_det=50))
+    p.model = SimpleNamespace(names={i: f"c{i}" for i in range(10)})
+    B = 9
+    torch.manual_seed(3)
+    out = torch.rand(B, 50, 6) * 700 - 30
+    counts = torch.tensor([0, 1, 50, 17, 3, 49, 50, 0, 25], dtype=torch.int32)
+    img = torch.zeros(B, 3, 640, 640, dtype=torch.uint8)
+    g = np.random.default_rng(0)
+    ragged = [np.zeros((int(g.integers(100, 3000)), int(g.integers(100, 3000)), 3), np.uint8) for _ in range(B)]
+    for orig in (img, [np.zeros((1080, 1920, 3), np.uint8)] * B, ragged):
+        keep = out.clone()
+        res = p.postprocess((out, counts), img, orig, [f"im{i}" for i in range(B)])
+        assert torch.equal(out, keep)                                        # the caller's tensor is not modified
+        for i, r in enumerate(res):
+            osh = (640, 640) if isinstance(orig, torch.Tensor) else orig[i].shape[:2]
+            rows = out[i, : int(counts[i])].clone()
+            rows[:, :4] = ops.scale_boxes((640, 640), rows[:, :4], osh)
+            assert torch.equal(rows, r.boxes.data) and r.orig_shape == tuple(osh) and len(r) == int(counts[i])
+            if len(r):
+                assert float(r.boxes.xyxy.min()) >= 0 and float(r.boxes.xyxy[:, [0, 2]].max()) <= osh[1]
