@@ -24,7 +24,9 @@ from .results import Results
 
 DEFAULTS = dict(task="detect", mode="predict", imgsz=640, batch=1, device=None, conf=0.25, iou=0.7, max_det=300,
                 half=False, classes=None, agnostic_nms=False, augment=False, stream=False, verbose=False,
-                micro_batch=0, cuda_graph=True, multi_label=False, gpu_preprocess=True, engine_cache=8)
+                micro_batch=0, cuda_graph=True, multi_label=False, gpu_preprocess=True, engine_cache=8, vid_stride=1)
+IMG_FORMATS = {"bmp", "dng", "jpeg", "jpg", "mpo", "png", "tif", "tiff", "webp", "pfm"}                       # data/utils.py:38 (heic needs pillow-heif: not read)
+VID_FORMATS = {"asf", "avi", "gif", "m4v", "mkv", "mov", "mp4", "mpeg", "mpg", "ts", "wmv", "webm"}           # data/utils.py:39
 EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end", "on_predict_end")
 
 
@@ -132,25 +134,93 @@ class DetectionPredictor:
             yield [f"image{i}.jpg" for i in range(im.shape[0])], None, im
             return
         items = source if isinstance(source, (list, tuple)) else [source]
+        if items and all(isinstance(s, (str, Path)) for s in items):
+            yield from self._file_batches(source)
+            return
         imgs, paths = [], []
         for i, s in enumerate(items):
             if isinstance(s, (str, Path)):
-                import cv2
-
-                im = cv2.imread(str(s))
-                if im is None:
-                    raise FileNotFoundError(f"image not found or unreadable: {s}")
-                imgs.append(im)
-                paths.append(str(s))
-            elif isinstance(s, np.ndarray):
+                raise TypeError("a list source holds either paths or in-memory images, not both (data/build.py:186-219)")
+            if isinstance(s, np.ndarray):
                 imgs.append(s)
                 paths.append(f"image{i}.jpg")
             else:  # PIL
                 imgs.append(np.asarray(s)[:, :, ::-1] if np.asarray(s).ndim == 3 else np.asarray(s))
                 paths.append(getattr(s, "filename", "") or f"image{i}.jpg")
-        bs = len(imgs) if not isinstance(items[0], (str, Path)) else max(int(self.args.batch), 1)
-        for i in range(0, len(imgs), bs):
-            yield paths[i:i + bs], imgs[i:i + bs], None
+        yield paths, imgs, None                                   # in-memory images: ONE batch (LoadPilAndNumpy, loaders.py:451-513)
+
+    def _file_batches(self, source):
+        """Paths -> batches of `args.batch` decoded frames (LoadImagesAndVideos, data/loaders.py:284-446): a `.txt` list, a
+        list (sorted), a glob, a directory (`*.*`) or a file; images first, then videos (frames every `vid_stride`, read as they
+        are needed); an image batch never runs into the videos; unreadable images are skipped with a warning."""
+        import glob
+        import os
+
+        import cv2
+
+        parent = None
+        if isinstance(source, (str, Path)) and Path(source).suffix == ".txt":
+            parent = Path(source).parent
+            source = Path(source).read_text().splitlines()
+        files = []
+        for s in sorted(str(x) for x in source) if isinstance(source, (list, tuple)) else [str(source)]:
+            a = str(Path(s).absolute())
+            if "*" in a:
+                files.extend(sorted(glob.glob(a, recursive=True)))
+            elif os.path.isdir(a):
+                files.extend(sorted(glob.glob(os.path.join(a, "*.*"))))
+            elif os.path.isfile(a):
+                files.append(a)
+            elif parent is not None and (parent / s).is_file():
+                files.append(str((parent / s).absolute()))
+            else:
+                raise FileNotFoundError(f"{s} does not exist")
+        ext = lambda f: f.rsplit(".", 1)[-1].lower()              # noqa: E731
+        images = [f for f in files if ext(f) in IMG_FORMATS]
+        videos = [f for f in files if ext(f) in VID_FORMATS]
+        if not images and not videos:
+            raise FileNotFoundError(f"No images or videos found in {source}")
+        bs = max(int(self.args.batch), 1)
+        stride = max(int(getattr(self.args, "vid_stride", 1)), 1)
+        paths, imgs = [], []
+        for f in images:
+            im = cv2.imread(f)
+            if im is None:
+                print(f"WARNING: image read error {f}")
+                continue
+            paths.append(f)
+            imgs.append(im)
+            if len(imgs) == bs:
+                yield paths, imgs, None
+                paths, imgs = [], []
+        if imgs:
+            yield paths, imgs, None
+            paths, imgs = [], []
+        for f in videos:
+            cap = cv2.VideoCapture(f)
+            if not cap.isOpened():
+                raise FileNotFoundError(f"Failed to open video {f}")
+            try:
+                while True:
+                    ok = False
+                    for _ in range(stride):
+                        ok = cap.grab()
+                        if not ok:
+                            break
+                    if not ok:
+                        break
+                    ok, im = cap.retrieve()
+                    if not ok:
+                        break
+                    paths.append(f)
+                    imgs.append(im)
+                    if len(imgs) == bs:
+                        yield paths, imgs, None
+                        paths, imgs = [], []
+            finally:
+                cap.release()
+        if imgs:
+            yield paths, imgs, None
 
     def preprocess(self, im0s):
         """uint8 HWC BGR list -> pinned uint8 (B,3,H,W) RGB (predictor.py:118-131, 147-163).  Like the reference, the

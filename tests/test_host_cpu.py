@@ -284,3 +284,53 @@ def test_batched_postprocess_equals_per_image_scale_boxes():
             assert torch.equal(rows, r.boxes.data) and r.orig_shape == tuple(osh) and len(r) == int(counts[i])
             if len(r):
                 assert float(r.boxes.xyxy.min()) >= 0 and float(r.boxes.xyxy[:, [0, 2]].max()) <= osh[1]
+
+
+def test_file_sources_follow_the_reference_loader(tmp_path):
+    """Directory / glob / .txt / list-of-paths / video sources (LoadImagesAndVideos, data/loaders.py:284-446): sorted files, images
+    before videos, batches of `batch`, an image batch never runs into a video, frames every `vid_stride`."""
+    import cv2
+
+    from drone_yolo_b200.engine.predictor import DetectionPredictor
+
+    g = np.random.default_rng(0)
+    for name, hw in (("b.png", (40, 60)), ("a.jpg", (50, 30)), ("c.bmp", (40, 60))):
+        assert cv2.imwrite(str(tmp_path / name), g.integers(0, 256, (*hw, 3), dtype=np.uint8))
+    (tmp_path / "notes.md").write_text("not an image")
+    p = DetectionPredictor(overrides=dict(batch=2))
+    got = list(p._batches(str(tmp_path)))
+    assert [[Path(x).name for x in b[0]] for b in got] == [["a.jpg", "b.png"], ["c.bmp"]]
+    assert got[0][1][0].shape == (50, 30, 3) and got[0][1][1].shape == (40, 60, 3) and got[0][2] is None
+    assert np.array_equal(got[1][1][0], cv2.imread(str(tmp_path / "c.bmp")))
+    assert [Path(x).name for b in p._batches(str(tmp_path / "*.png")) for x in b[0]] == ["b.png"]
+    assert [Path(x).name for b in p._batches([str(tmp_path / "c.bmp"), tmp_path / "a.jpg"]) for x in b[0]] == ["a.jpg", "c.bmp"]
+    (tmp_path / "list.txt").write_text("b.png\na.jpg\n")
+    assert [Path(x).name for b in p._batches(str(tmp_path / "list.txt")) for x in b[0]] == ["a.jpg", "b.png"]
+    with pytest.raises(FileNotFoundError):
+        list(p._batches(str(tmp_path / "missing.jpg")))
+    with pytest.raises(FileNotFoundError):
+        sub = tmp_path / "empty"
+        sub.mkdir()
+        (sub / "x.md").write_text("")
+        list(p._batches(str(sub)))
+    with pytest.raises(TypeError):
+        list(p._batches([str(tmp_path / "a.jpg"), np.zeros((8, 8, 3), np.uint8)]))
+    # in-memory images stay ONE batch whatever `batch` says (LoadPilAndNumpy)
+    arrs = [np.zeros((8, 8, 3), np.uint8)] * 5
+    assert [len(b[1]) for b in p._batches(arrs)] == [5]
+
+    vid = tmp_path / "clip.avi"
+    wr = cv2.VideoWriter(str(vid), cv2.VideoWriter_fourcc(*"MJPG"), 10, (64, 48))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build cannot write MJPG/avi")
+    for i in range(7):
+        wr.write(np.full((48, 64, 3), 30 * i, np.uint8))
+    wr.release()
+    got = list(p._batches(str(vid)))
+    assert [len(b[1]) for b in got] == [2, 2, 2, 1] and got[0][1][0].shape == (48, 64, 3)
+    assert abs(int(got[3][1][0].mean()) - 180) <= 3                          # the last frame is the 7th
+    got = list(p._batches(str(tmp_path)))                                    # images first, then the video; batches do not mix
+    assert [len(b[1]) for b in got] == [2, 1, 2, 2, 2, 1] and Path(got[2][0][0]).name == "clip.avi"
+    p3 = DetectionPredictor(overrides=dict(batch=4, vid_stride=3))
+    got = list(p3._batches(str(vid)))
+    assert [len(b[1]) for b in got] == [2] and abs(int(got[0][1][1].mean()) - 150) <= 3      # frames 3 and 6 (1-based)
