@@ -351,6 +351,29 @@ def run_ours(a):
                    "nms_hbm_gbs": nms_bytes / ms_nms / 1e6, "nms_frac_of_hbm": nms_bytes / ms_nms / 1e6 / hbm_peak,
                    "decode_algorithmic_bytes": dec_bytes},
     }
+    if world == 1:
+        # the call a user makes: YOLO.predict(list of B raw uint8 HWC BGR frames) -> Results, wall clock (host frames in, Results out:
+        # pinned staging + H2D + GPU letterbox + engine step + D2H + rescale on the host, nothing overlapped across calls)
+        try:
+            import numpy as np
+
+            from drone_yolo_b200 import YOLO
+            yolo = YOLO(model)
+            frames = list(host8.permute(0, 2, 3, 1).contiguous().numpy()[..., ::-1])       # RGB planes -> BGR HWC views
+            frames = [np.ascontiguousarray(f) for f in frames]
+            kw = dict(imgsz=a.imgsz, conf=a.conf, iou=a.iou, max_det=a.max_det, device=dev, micro_batch=a.micro_batch,
+                      cuda_graph=not a.no_graph)
+            for _ in range(2):
+                res = yolo.predict(frames, **kw)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                res = yolo.predict(frames, **kw)
+            dt_api = (time.perf_counter() - t0) / 5
+            line["e2e"]["predict_api"] = {"value": a.batch / dt_api, "unit": "images/s", "ms_per_call": dt_api * 1e3,
+                                          "call": f"YOLO.predict(list of {a.batch} uint8 {a.imgsz}x{a.imgsz} BGR frames) -> Results, wall clock, 5 calls",
+                                          "detections_first_image": len(res[0])}
+        except Exception as ex:  # noqa: BLE001
+            line["e2e"]["predict_api"] = {"value": None, "error": str(ex)[:200]}
     if world == 1 and not a.no_cpu_baseline:
         try:
             v, (dt, t_conv, t_nms), cores = cpu_port_images_per_sec(a, a.cpu_sample, passes=2, threads=os.cpu_count())

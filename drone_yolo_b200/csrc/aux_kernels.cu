@@ -214,7 +214,10 @@ __device__ __forceinline__ LbCoef lb_coef(int d, double scale, int n_src) {
 
 __global__ void __launch_bounds__(256) letterbox_u8_kernel(const uint8_t* __restrict__ src, int h, int w, int pitch,
                                                            uint8_t* __restrict__ dst, int H, int W, int new_w, int new_h,
-                                                           int left, int top, int fill, double scale_x, double scale_y) {
+                                                           int left, int top, int fill, double scale_x, double scale_y,
+                                                           size_t src_image_stride, size_t dst_image_stride) {
+  src += blockIdx.y * src_image_stride;          // blockIdx.y = frame of a same-geometry batch
+  dst += blockIdx.y * dst_image_stride;
   const int wq = W >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wq * H) return;
@@ -247,17 +250,26 @@ __global__ void __launch_bounds__(256) letterbox_u8_kernel(const uint8_t* __rest
   for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t*>(dst + c * plane + static_cast<size_t>(y) * W + x0) = out[c];
 }
 
-int letterbox_u8_launch(const void* src, int h, int w, int pitch, void* dst, int H, int W, int new_w, int new_h, int left,
-                        int top, int fill, cudaStream_t stream) {
+int letterbox_u8_batch_launch(const void* src, int n, size_t src_image_stride, int h, int w, int pitch, void* dst,
+                              size_t dst_image_stride, int H, int W, int new_w, int new_h, int left, int top, int fill,
+                              cudaStream_t stream) {
   DY_CHECK_ARG(src && dst && h > 0 && w > 0 && H > 0 && W > 0 && pitch >= 3 * w, "letterbox: bad argument");
-  DY_CHECK_ARG(W % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0, "letterbox: W must be a multiple of 4 and dst 4B aligned");
+  DY_CHECK_ARG(n >= 1 && n <= 65535, "letterbox: %d frames outside [1, 65535]", n);
+  DY_CHECK_ARG(W % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && dst_image_stride % 4 == 0,
+               "letterbox: W and the image stride of dst must be multiples of 4 and dst 4B aligned");
   DY_CHECK_ARG(new_w > 0 && new_h > 0 && left >= 0 && top >= 0 && left + new_w <= W && top + new_h <= H,
                "letterbox: the resized image (%dx%d at %d,%d) does not fit the %dx%d canvas", new_w, new_h, left, top, W, H);
   const double sx = 1.0 / (static_cast<double>(new_w) / w), sy = 1.0 / (static_cast<double>(new_h) / h);
-  const int n = (W >> 2) * H;
-  letterbox_u8_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(static_cast<const uint8_t*>(src), h, w, pitch, static_cast<uint8_t*>(dst),
-                                                          H, W, new_w, new_h, left, top, fill, sx, sy);
+  const int px = (W >> 2) * H;
+  letterbox_u8_kernel<<<dim3(ceil_div(px, 256), n), 256, 0, stream>>>(static_cast<const uint8_t*>(src), h, w, pitch,
+                                                                     static_cast<uint8_t*>(dst), H, W, new_w, new_h, left, top, fill,
+                                                                     sx, sy, src_image_stride, dst_image_stride);
   return launch_status("letterbox_u8_kernel");
+}
+
+int letterbox_u8_launch(const void* src, int h, int w, int pitch, void* dst, int H, int W, int new_w, int new_h, int left,
+                        int top, int fill, cudaStream_t stream) {
+  return letterbox_u8_batch_launch(src, 1, 0, h, w, pitch, dst, 0, H, W, new_w, new_h, left, top, fill, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +376,12 @@ extern "C" int dy_stem_conv(const void* in, int in_dtype, int B, int H, int W, c
 extern "C" int dy_letterbox_u8(const void* src, int h, int w, int src_pitch, void* dst, int H, int W, int new_w, int new_h,
                                int left, int top, int fill, void* stream) {
   return dy::letterbox_u8_launch(src, h, w, src_pitch, dst, H, W, new_w, new_h, left, top, fill, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dy_letterbox_u8_batch(const void* src, int n, size_t src_image_stride, int h, int w, int src_pitch, void* dst,
+                                     size_t dst_image_stride, int H, int W, int new_w, int new_h, int left, int top, int fill,
+                                     void* stream) {
+  return dy::letterbox_u8_batch_launch(src, n, src_image_stride, h, w, src_pitch, dst, dst_image_stride, H, W, new_w, new_h,
+                                       left, top, fill, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dy_sppf_pool(void* buf, int B, int H, int W, int C, int ld, void* stream) {
   return dy::sppf_pool_launch(buf, B, H, W, C, ld, static_cast<cudaStream_t>(stream));

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
 #define DY_TR(role, it, ev) do { if (p.trace && blockIdx.x == 0 && (it) < 96) p.trace[((role) * 96 + (it)) * 8 + (ev)] = clock64(); } while (0)
 #else
 #ifdef DY_CONV_DBG_CONST
-  constexpr int dbg = DY_CONV_DBG_CONST;   // compile-time knock-out build (tools/build_knockouts.sh): release-speed loops
+  constexpr int dbg = DY_CONV_DBG_CONST;   // compile-time knock-out build (tools/run_knockouts.sh): release-speed loops
 #else
   constexpr int dbg = 0;   // knock-outs and the timeline (DY_CONV_TRACE) compile away unless built with -DDY_CONV_DEBUG
 #endif

@@ -35,7 +35,7 @@ class Model(nn.Module):
 
     def _load(self, weights, nc=None):
         """Load `<name>.pt` holding {'yaml': cfg-name-or-dict, 'model': state_dict} or a bare state_dict next to a
-        YAML named by `cfg` (engine/model.py:266-302; pickled reference checkpoints: tools/export_state_dict.py)."""
+        YAML named by `cfg` (engine/model.py:266-302; pickled reference checkpoints: nn/ckpt.py)."""
         try:
             obj = torch.load(weights, map_location="cpu", weights_only=True)
         except pickle.UnpicklingError:

@@ -184,6 +184,20 @@ def letterbox_u8(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: int, l
     return dst
 
 
+def letterbox_u8_batch(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: int, left: int, top: int, fill: int = 114) -> torch.Tensor:
+    """n raw frames of one shape (n, h, w, 3) uint8 BGR on the device -> (n, 3, H, W) uint8 RGB, one launch (see letterbox_u8)."""
+    _C.require_cuda(src)
+    _C.require_cuda(dst)
+    if src.dtype != torch.uint8 or dst.dtype != torch.uint8 or src.dim() != 4 or src.shape[3] != 3 or src.stride(3) != 1 or src.stride(2) != 3:
+        raise _C.DroneYoloError("letterbox: src must be a uint8 (n, h, w, 3) batch with packed pixels")
+    if dst.dim() != 4 or dst.shape[1] != 3 or dst.shape[0] != src.shape[0] or not dst[0].is_contiguous():
+        raise _C.DroneYoloError("letterbox: dst must be a uint8 (n, 3, H, W) batch of contiguous images")
+    _C.check(_C.lib().dy_letterbox_u8_batch(src.data_ptr(), src.shape[0], src.stride(0), src.shape[1], src.shape[2], src.stride(1),
+                                            dst.data_ptr(), dst.stride(0), dst.shape[2], dst.shape[3], int(new_w), int(new_h),
+                                            int(left), int(top), int(fill), _C.stream_ptr(dst.device)), "dy_letterbox_u8_batch")
+    return dst
+
+
 def sppf_pool(buf: torch.Tensor, c: int) -> torch.Tensor:
     """buf: bf16 NHWC (B,>=4c,H,W); fills channels [c,4c) with mp5, mp5∘mp5, mp5∘mp5∘mp5 of channels [0,c)."""
     p, ld, B, H, W, Cc = nhwc_view(buf, "sppf buffer")

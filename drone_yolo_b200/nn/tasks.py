@@ -268,8 +268,8 @@ class DetectionModel(BaseModel):
 
 
 def attempt_load_state(model: BaseModel, path):
-    """Load a `.pt` that holds a plain state_dict (or {'model': state_dict}).  Pickled reference checkpoints need
-    the reference classes importable and are converted with tools/export_state_dict.py."""
+    """Load a `.pt` that holds a plain state_dict (or {'model': state_dict}).  Pickled reference checkpoints
+    ({'model': <DetectionModel>, ...}) are read by nn/ckpt.py load_reference_checkpoint, which YOLO('<file>.pt') uses."""
     obj = torch.load(path, map_location="cpu", weights_only=True)
     return model.load(obj)
 

@@ -129,6 +129,10 @@ int dy_dwconv3x3s2(const void* in, int in_ld, int B, int H, int W, int Cin, cons
  */
 int dy_letterbox_u8(const void* src, int h, int w, int src_pitch, void* dst, int H, int W, int new_w, int new_h,
                     int left, int top, int fill, void* stream);
+/* The same for n frames of ONE geometry in one launch: frame i is read at src + i*src_image_stride bytes and written at
+ * dst + i*dst_image_stride bytes (dst_image_stride a multiple of 4; 3*H*W for consecutive images of the input batch). */
+int dy_letterbox_u8_batch(const void* src, int n, size_t src_image_stride, int h, int w, int src_pitch, void* dst,
+                          size_t dst_image_stride, int H, int W, int new_w, int new_h, int left, int top, int fill, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * Detect decode: DFL softmax-expectation + dist2bbox(xywh) + stride scaling + class sigmoid.

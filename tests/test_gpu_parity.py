@@ -641,3 +641,38 @@ def test_inference_slicer_one_batch_matches_tile_list_predict(dev):
     assert float(got[:, 2].max()) <= 1100 and float(got[:, 3].max()) <= 700 and float(got[:, :4].min()) >= 0
     again = slicer(frame)                                          # cached engine, reused staging
     assert np.array_equal(np.asarray(again.boxes.data), got)
+
+
+def test_letterbox_batch_launch_equals_per_frame(K, dev):
+    from drone_yolo_b200.engine.predictor import letterbox_geometry
+
+    n, h, w = 9, 270, 480
+    src = torch.from_numpy(np.random.default_rng(5).integers(0, 256, (n, h, w, 3), dtype=np.uint8)).to(dev)
+    nw, nh, left, top, H, W = letterbox_geometry((h, w), (320, 320), auto=False)
+    one = torch.zeros((n, 3, H, W), dtype=torch.uint8, device=dev)
+    for i in range(n):
+        K.letterbox_u8(src[i], one[i], nw, nh, left, top)
+    got = K.letterbox_u8_batch(src, torch.zeros_like(one), nw, nh, left, top)
+    assert torch.equal(got, one)
+    wide = torch.zeros((n, 3, H, W + 64), dtype=torch.uint8, device=dev)[:, :, :, :W]       # images must be contiguous
+    from drone_yolo_b200._C import DroneYoloError
+    with pytest.raises(DroneYoloError):
+        K.letterbox_u8_batch(src, wide, nw, nh, left, top)
+
+
+def test_predict_nine_same_shape_frames_and_staging_reuse(dev):
+    """Nine frames of one shape, then the same frames reversed (staging buffers reused): same detections as the host cv2 path."""
+    from drone_yolo_b200 import YOLO
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    frames = [np.random.default_rng(i).integers(0, 256, (360, 640, 3), dtype=np.uint8) for i in range(9)]
+    a = model.predict(frames, imgsz=320, conf=0.001, iou=0.7, device=dev, gpu_preprocess=True)
+    a2 = model.predict(frames[::-1], imgsz=320, conf=0.001, iou=0.7, device=dev, gpu_preprocess=True)      # staging block reused
+    model.predictor = None
+    b = model.predict(frames, imgsz=320, conf=0.001, iou=0.7, device=dev, gpu_preprocess=False)
+    assert len(a) == len(b) == 9 and sum(len(r) for r in a) > 0
+    for ra, rb, rc in zip(a, b, a2[::-1]):
+        assert torch.equal(torch.as_tensor(ra.boxes.data), torch.as_tensor(rb.boxes.data))
+        assert torch.equal(torch.as_tensor(rc.boxes.data), torch.as_tensor(rb.boxes.data))
