@@ -22,13 +22,14 @@ def main():
     ap.add_argument("--scale", default="s")
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--hw", type=int, nargs=2, default=(2160, 3840))
+    ap.add_argument("--conf", type=float, default=0.25, help="0.001: every tile returns max_det rows, the merge sees 1800 rows")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     model = YOLO(f"yolov8{a.scale}-p2-repvgg.yaml", nc=10)
     recipe.apply_recipe(model.model)
     frames = [np.random.default_rng(i).integers(0, 256, (*a.hw, 3), dtype=np.uint8) for i in range(3)]
-    kw = dict(imgsz=640, conf=0.25, iou=0.7, device=dev)
+    kw = dict(imgsz=640, conf=a.conf, iou=0.7, device=dev)
     offsets = generate_offsets((a.hw[1], a.hw[0]), (2160, 2160), (0.2, 0.2))
 
     def per_tile(frame):
@@ -45,7 +46,7 @@ def main():
         return rows
 
     slicer = InferenceSlicer(model, slice_wh=(2160, 2160), overlap_ratio_wh=(0.2, 0.2), iou_threshold=0.7, **kw)
-    out = {"frame_hw": list(a.hw), "tiles": len(offsets), "scale": a.scale}
+    out = {"frame_hw": list(a.hw), "tiles": len(offsets), "scale": a.scale, "conf": a.conf}
     for name, fn in (("per_tile_calls", per_tile), ("one_batch", slicer)):
         model.predictor = None
         for i in range(3):
@@ -56,6 +57,8 @@ def main():
             fn(frames[i % 3])
         torch.cuda.synchronize()
         out[name + "_ms_per_frame"] = (time.perf_counter() - t0) * 1e3 / a.frames
+    last = slicer(frames[0])
+    out["merged_rows"] = len(last)
     out["speedup"] = out["per_tile_calls_ms_per_frame"] / out["one_batch_ms_per_frame"]
     print(json.dumps(out))
 
