@@ -72,6 +72,27 @@ class InferenceSlicer:
             m.predictor.args.__dict__.update(args)
         return m.predictor
 
+    MAX_MERGE_ROWS = 16384                     # dy_box_nms_f64: one CTA scans the `removed` set, 256 words of 64 rows
+
+    def _merge_keep(self, rows: np.ndarray, device) -> np.ndarray:
+        """Keep mask of the merge NMS over frame rows (n, 6) float64.  More rows than one launch takes (many small tiles at a
+        low confidence threshold) are merged category by category — categories never interact unless class_agnostic."""
+        n = len(rows)
+        if n <= self.MAX_MERGE_ROWS:
+            return K.box_nms_f64(torch.from_numpy(rows).to(device), self.iou_threshold, self.class_agnostic).cpu().numpy()
+        if self.class_agnostic:
+            raise _C.DroneYoloError(f"InferenceSlicer: {n} rows to merge class-agnostically, at most {self.MAX_MERGE_ROWS} per "
+                                    "launch: raise conf, lower max_det or use larger tiles")
+        keep = np.zeros(n, dtype=bool)
+        for c in np.unique(rows[:, 5]):
+            idx = np.nonzero(rows[:, 5] == c)[0]
+            if len(idx) > self.MAX_MERGE_ROWS:
+                raise _C.DroneYoloError(f"InferenceSlicer: {len(idx)} rows of class {int(c)} to merge, at most "
+                                        f"{self.MAX_MERGE_ROWS} per launch: raise conf, lower max_det or use larger tiles")
+            sub = np.ascontiguousarray(rows[idx])
+            keep[idx] = K.box_nms_f64(torch.from_numpy(sub).to(device), self.iou_threshold, False).cpu().numpy()
+        return keep
+
     def _upload(self, image: np.ndarray, device) -> torch.Tensor:
         key = image.shape
         if key not in self._frame:
@@ -116,8 +137,7 @@ class InferenceSlicer:
                     moved.append(rows)
             rows = np.concatenate(moved, 0) if moved else np.zeros((0, 6))
             if len(rows):
-                keep = K.box_nms_f64(torch.from_numpy(rows).to(p.device), self.iou_threshold, self.class_agnostic)
-                rows = rows[keep.cpu().numpy()]
+                rows = rows[self._merge_keep(rows, p.device)]
             t3 = time.perf_counter()
         res = Results(image, path="frame.jpg", names=self.model.model.names, boxes=torch.from_numpy(rows),
                       orig_shape=image.shape[:2])

@@ -676,3 +676,44 @@ def test_predict_nine_same_shape_frames_and_staging_reuse(dev):
     for ra, rb, rc in zip(a, b, a2[::-1]):
         assert torch.equal(torch.as_tensor(ra.boxes.data), torch.as_tensor(rb.boxes.data))
         assert torch.equal(torch.as_tensor(rc.boxes.data), torch.as_tensor(rb.boxes.data))
+
+
+def test_tile_merge_properties_at_max_rows(K, dev):
+    """16384 rows (the most one launch takes): idempotence (merging the survivors again removes nothing), every removed row has a
+    kept same-category row ranked above it with IoU > threshold, no two survivors of one category overlap above the threshold."""
+    from oracle import slicer_np
+
+    n, thr = 16384, 0.6
+    rows = _clustered_rows(n, seed=99, n_cls=4)
+    keep = K.box_nms_f64(torch.from_numpy(rows).to(dev), thr).cpu().numpy()
+    kept = np.ascontiguousarray(rows[keep])
+    assert 0 < len(kept) < n
+    assert K.box_nms_f64(torch.from_numpy(kept).to(dev), thr).cpu().numpy().all()
+    g = np.random.default_rng(1)
+    kept_idx = np.nonzero(keep)[0]
+    for i in g.choice(np.nonzero(~keep)[0], 200, replace=False):
+        iou = slicer_np.box_iou_batch(rows[i:i + 1, :4], kept[:, :4])[0]
+        above = (kept[:, 4] > rows[i, 4]) | ((kept[:, 4] == rows[i, 4]) & (kept_idx > i))
+        assert ((iou > thr) & (kept[:, 5] == rows[i, 5]) & above).any()
+    for c in range(4):
+        sub = kept[kept[:, 5] == c][:3000]
+        iou = slicer_np.box_iou_batch(sub[:, :4], sub[:, :4])
+        np.fill_diagonal(iou, 0.0)
+        assert not (iou > thr).any()
+
+
+def test_inference_slicer_merges_per_category_beyond_one_launch(dev):
+    from drone_yolo_b200.engine.slicer import InferenceSlicer
+    from oracle import slicer_np
+
+    rows = _clustered_rows(17000, seed=5, n_cls=4)
+    sl = InferenceSlicer(None, iou_threshold=0.5)
+    got = sl._merge_keep(rows, dev)
+    want = np.zeros(len(rows), dtype=bool)
+    for c in range(4):
+        idx = np.nonzero(rows[:, 5] == c)[0]
+        want[idx] = slicer_np.box_nms_keep(rows[idx], 0.5)
+    assert np.array_equal(got, want)
+    from drone_yolo_b200._C import DroneYoloError
+    with pytest.raises(DroneYoloError):
+        InferenceSlicer(None, iou_threshold=0.5, class_agnostic=True)._merge_keep(rows, dev)
