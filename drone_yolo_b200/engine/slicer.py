@@ -100,8 +100,11 @@ class InferenceSlicer:
             self._frame[key] = (torch.empty(key, dtype=torch.uint8).pin_memory(),
                                 torch.empty(key, dtype=torch.uint8, device=device))
         host, dev = self._frame[key]
-        host.copy_(torch.from_numpy(np.ascontiguousarray(image)))
-        dev.copy_(host, non_blocking=True)
+        src = torch.from_numpy(np.ascontiguousarray(image))
+        rows = max(1, (4 << 20) // max(1, image.shape[1] * 3))     # ~4 MB bands: band k crosses PCIe while band k+1 is staged
+        for r0 in range(0, image.shape[0], rows):
+            host[r0:r0 + rows].copy_(src[r0:r0 + rows])
+            dev[r0:r0 + rows].copy_(host[r0:r0 + rows], non_blocking=True)
         return dev
 
     def __call__(self, image: np.ndarray) -> Results:
