@@ -334,3 +334,23 @@ def test_file_sources_follow_the_reference_loader(tmp_path):
     p3 = DetectionPredictor(overrides=dict(batch=4, vid_stride=3))
     got = list(p3._batches(str(vid)))
     assert [len(b[1]) for b in got] == [2] and abs(int(got[0][1][1].mean()) - 150) <= 3      # frames 3 and 6 (1-based)
+
+
+def test_inference_slicer_argument_checks():
+    """Constructor mirrors supervision.InferenceSlicer (mix6.py:84-89); bad arguments fail before any CUDA work."""
+    from drone_yolo_b200 import InferenceSlicer
+    from drone_yolo_b200._C import DroneYoloError
+    from drone_yolo_b200.engine.slicer import generate_offsets
+
+    s = InferenceSlicer(None, slice_wh=(2160, 2160), overlap_ratio_wh=(0.2, 0.2), iou_threshold=0.7, thread_workers=1, conf=0.7, classes=[0])
+    assert s.slice_wh == (2160, 2160) and s.iou_threshold == 0.7 and s.predict_kwargs == {"conf": 0.7, "classes": [0]}
+    with pytest.raises(AssertionError):
+        InferenceSlicer(None, iou_threshold=1.5)
+    for bad in (np.zeros((8, 8), np.uint8), np.zeros((8, 8, 3), np.float32), "frame.jpg"):
+        with pytest.raises(DroneYoloError):
+            s(bad)
+    with pytest.raises(ValueError):
+        generate_offsets((100, 100), (0, 10), (0.2, 0.2))
+    with pytest.raises(ValueError):
+        generate_offsets((100, 100), (10, 10), (1.0, 0.2))
+    assert generate_offsets((100, 50), (200, 200), (0.2, 0.2)).tolist() == [[0, 0, 100, 50]]      # frame smaller than a tile
