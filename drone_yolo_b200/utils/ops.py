@@ -72,26 +72,28 @@ def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xyw
 def scale_boxes_batch(img1_shape, boxes, img0_shapes):
     """`scale_boxes` for a whole batch at once: boxes (B, k, 4) float32 xyxy (CPU tensor, modified in place), img0_shapes a list
     of B (h, w).  Element for element the arithmetic of the per-image call (reference ops.py:92-127: `-= pad`, `/= gain` with the
-    Python scalar taken as float32, clamp to the image), done in a handful of tensor ops instead of ~12 per image."""
-    if len(set(tuple(s[:2]) for s in img0_shapes)) == 1:
-        return scale_boxes(img1_shape, boxes, tuple(img0_shapes[0][:2]))
-    gain, padx, pady = [], [], []
-    for s in img0_shapes:
-        g = min(img1_shape[0] / s[0], img1_shape[1] / s[1])
-        gain.append(g)
-        padx.append(round((img1_shape[1] - s[1] * g) / 2 - 0.1))
-        pady.append(round((img1_shape[0] - s[0] * g) / 2 - 0.1))
-    col = lambda v: torch.tensor(v, dtype=torch.float64).to(torch.float32)[:, None]   # noqa: E731
-    px, py, g = col(padx), col(pady), col(gain)
-    w, h = col([s[1] for s in img0_shapes]), col([s[0] for s in img0_shapes])
-    zero = torch.zeros((), dtype=torch.float32)
-    boxes[..., 0] -= px
-    boxes[..., 1] -= py
-    boxes[..., 2] -= px
-    boxes[..., 3] -= py
-    boxes /= g[:, :, None]
-    for c, hi in ((0, w), (1, h), (2, w), (3, h)):
-        boxes[..., c] = torch.minimum(torch.maximum(boxes[..., c], zero), hi)
+    Python scalar taken as float32, clamp to the image), in three broadcast tensor ops instead of ~12 small ones per image."""
+    shapes = [tuple(s[:2]) for s in img0_shapes]
+    uniq = {}
+    for s in shapes:
+        if s not in uniq:
+            g = min(img1_shape[0] / s[0], img1_shape[1] / s[1])
+            px = round((img1_shape[1] - s[1] * g) / 2 - 0.1)
+            py = round((img1_shape[0] - s[0] * g) / 2 - 0.1)
+            uniq[s] = ([px, py, px, py], g, [s[1], s[0], s[1], s[0]])
+    if len(uniq) == 1:
+        pad, g, hi = next(iter(uniq.values()))
+        pad_t = torch.tensor(pad, dtype=torch.float32)
+        g_t = torch.tensor(g, dtype=torch.float64).to(torch.float32)
+        hi_t = torch.tensor(hi, dtype=torch.float32)
+    else:
+        pad_t = torch.tensor([uniq[s][0] for s in shapes], dtype=torch.float32)[:, None, :]
+        g_t = torch.tensor([uniq[s][1] for s in shapes], dtype=torch.float64).to(torch.float32)[:, None, None]
+        hi_t = torch.tensor([uniq[s][2] for s in shapes], dtype=torch.float32)[:, None, :]
+    boxes -= pad_t
+    boxes /= g_t
+    torch.minimum(boxes, hi_t, out=boxes)
+    torch.maximum(boxes, torch.zeros((), dtype=torch.float32), out=boxes)
     return boxes
 
 
