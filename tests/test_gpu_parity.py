@@ -717,3 +717,34 @@ def test_inference_slicer_merges_per_category_beyond_one_launch(dev):
     from drone_yolo_b200._C import DroneYoloError
     with pytest.raises(DroneYoloError):
         InferenceSlicer(None, iou_threshold=0.5, class_agnostic=True)._merge_keep(rows, dev)
+
+
+def test_predict_directory_and_video_sources(dev, tmp_path):
+    """Path sources (LoadImagesAndVideos): a directory of images in batches of `batch`, then a video frame by frame; the detections
+    equal those of the same decoded frames passed in memory."""
+    import cv2
+    from drone_yolo_b200 import YOLO
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    g = np.random.default_rng(11)
+    for name in ("a.png", "b.png", "c.png"):
+        assert cv2.imwrite(str(tmp_path / name), g.integers(0, 256, (96, 128, 3), dtype=np.uint8))
+    kw = dict(imgsz=128, conf=0.001, iou=0.7, max_det=30, device=dev)
+    res = model.predict(str(tmp_path), batch=2, **kw)
+    assert [r.path.rsplit("/", 1)[-1] for r in res] == ["a.png", "b.png", "c.png"] and all(r.orig_shape == (96, 128) for r in res)
+    mem = model.predict([cv2.imread(str(tmp_path / n)) for n in ("a.png", "b.png")], **kw)
+    for u, v in zip(res[:2], mem):
+        assert torch.equal(torch.as_tensor(u.boxes.data), torch.as_tensor(v.boxes.data))
+    last = model.predict(cv2.imread(str(tmp_path / "c.png")), **kw)[0]          # the ragged last batch (one image) ran on its own engine
+    assert torch.equal(torch.as_tensor(res[2].boxes.data), torch.as_tensor(last.boxes.data))
+    vid = tmp_path / "clip.avi"
+    wr = cv2.VideoWriter(str(vid), cv2.VideoWriter_fourcc(*"MJPG"), 10, (128, 96))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build cannot write MJPG/avi")
+    for i in range(5):
+        wr.write(g.integers(0, 256, (96, 128, 3), dtype=np.uint8))
+    wr.release()
+    out = list(model.predict(str(vid), batch=2, stream=True, **kw))
+    assert len(out) == 5 and all(r.path.endswith("clip.avi") and r.orig_shape == (96, 128) for r in out)
