@@ -13,3 +13,6 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
     -f -o gpurun_out/${tag}_conv_full python tools/profile_step.py --micro-batch 64 > gpurun_out/${tag}_ncu2.log 2>&1
 echo "full capture exit $?"
 timeout 600 python tools/bench_decode_nms.py > gpurun_out/${tag}_config4.jsonl 2>gpurun_out/${tag}_config4.err; echo "config 4 exit $?"
+timeout 300 python tools/bench_preprocess.py > gpurun_out/${tag}_preprocess.log 2>&1; echo "preprocess exit $?"; tail -2 gpurun_out/${tag}_preprocess.log
+timeout 300 python tools/bench_slicer.py > gpurun_out/${tag}_slicer.jsonl 2>gpurun_out/${tag}_slicer.err &&
+timeout 300 python tools/bench_slicer.py --conf 0.001 >> gpurun_out/${tag}_slicer.jsonl 2>>gpurun_out/${tag}_slicer.err; echo "slicer exit $?"; cat gpurun_out/${tag}_slicer.jsonl
