@@ -113,7 +113,8 @@ class DetectionPredictor:
         key = (B, H, W, dtype, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes else None, a.agnostic_nms, a.multi_label,
                a.micro_batch, a.cuda_graph)
         if key not in self.engines:
-            if len(self.engines) >= max(int(getattr(a, "engine_cache", 8)), 1):     # engines hold their arenas: bounded
+            held = sum(e.plan.arena_bytes for e in self.engines.values())            # engines hold their arenas: bounded by
+            if len(self.engines) >= max(int(getattr(a, "engine_cache", 8)), 1) or held > (48 << 30):   # count and by bytes
                 self.engines.clear()
             self.engines[key] = Engine(self.model, B, (H, W), self.device, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou,
                                        max_det=a.max_det, classes=a.classes, agnostic=a.agnostic_nms,
