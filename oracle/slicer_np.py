@@ -5,7 +5,8 @@
 (imported at mix6.py:2, unpinned): its published algorithm (InferenceSlicer._generate_offset, move_boxes,
 Detections.merge, Detections.with_nms -> box_non_max_suppression, box_iou_batch) is restated here from its
 documentation — PARITY UNPINNED for this step; the anchors are the call site's arguments (mix6.py:84-89: slice_wh
-(2160, 2160), overlap (0.2, 0.2), iou 0.7) and hand-computed known answers in tests/test_oracle_golden.py.
+(2160, 2160), overlap (0.2, 0.2), iou 0.7), hand-computed known answers, and — for the greedy rule itself — agreement with the
+installed torchvision.ops.nms on tie-free float64 rows (tests/test_oracle_golden.py).
 
 Precision: tile boxes are float32 (Results.boxes.xyxy); adding the integer tile origin promotes them to float64, so the
 merge NMS runs in float64.  Ranking: `np.flip(argsort(conf))` — with a stable ascending sort, equal scores rank the

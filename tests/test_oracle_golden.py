@@ -167,3 +167,29 @@ def test_slicer_merge_nms_known_answers():
     offs = slicer_np.generate_offsets((3840, 2160), (2160, 2160), (0.2, 0.2))
     out = slicer_np.merge_tiles([t0, t1], offs[:2], 0.7)
     assert out.dtype == np.float64 and out.tolist() == [[1800.5, 100, 1900, 200, np.float32(0.9), 0], [2228, 500, 2328, 600, np.float32(0.3), 2]]
+
+
+def test_slicer_merge_nms_agrees_with_torchvision_on_tie_free_rows():
+    """Independent check of the greedy rule: on tie-free scores, the kept set per category equals torchvision.ops.nms on the same
+    float64 boxes (same IoU formula, strict >); the two differ only in their tie order, which the known-answer test pins."""
+    import torchvision
+    from oracle import slicer_np
+
+    g = np.random.default_rng(21)
+    n = 600
+    c = g.uniform(0, 800, (n, 2))
+    wh = g.uniform(30, 120, (n, 2))
+    conf = g.permutation(n).astype(np.float64) / n + 0.001                   # all distinct
+    rows = np.concatenate([c - wh / 2, c + wh / 2, conf[:, None], g.integers(0, 3, (n, 1)).astype(np.float64)], 1)
+    for thr in (0.3, 0.5, 0.7):
+        keep = slicer_np.box_nms_keep(rows, thr)
+        want = np.zeros(n, dtype=bool)
+        for k in range(3):
+            idx = np.nonzero(rows[:, 5] == k)[0]
+            kept = torchvision.ops.nms(torch.from_numpy(rows[idx, :4]), torch.from_numpy(rows[idx, 4]), thr).numpy()
+            want[idx[kept]] = True
+        assert np.array_equal(keep, want) and 0 < keep.sum() < n
+        t = torchvision.ops.nms(torch.from_numpy(rows[:, :4]), torch.from_numpy(rows[:, 4]), thr).numpy()
+        agn = np.zeros(n, dtype=bool)
+        agn[t] = True
+        assert np.array_equal(slicer_np.box_nms_keep(rows, thr, class_agnostic=True), agn)
