@@ -91,6 +91,8 @@ SYMBOLS = {
     "dy_program_add_dwconv3x3s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "dy_program_add_decode": (C.c_int, [C.c_void_p, C.POINTER(DecodeDesc)]),
     "dy_program_add_nms": (C.c_int, [C.c_void_p, C.POINTER(NmsDesc)]),
+    "dy_program_set_lane": (C.c_int, [C.c_void_p, C.c_int]),
+    "dy_program_add_sync": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "dy_program_run": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "dy_program_num_launches": (C.c_int, [C.c_void_p]),
     "dy_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),

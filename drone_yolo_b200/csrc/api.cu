@@ -42,10 +42,13 @@ int num_sms() {
   return n;
 }
 
-enum OpKind { OP_CONV, OP_STEM, OP_POOL, OP_UPSAMPLE, OP_DWCONV, OP_DECODE, OP_NMS };
+enum OpKind { OP_CONV, OP_STEM, OP_POOL, OP_UPSAMPLE, OP_DWCONV, OP_DECODE, OP_NMS, OP_SYNC };
 
 struct Op {
   OpKind kind;
+  int lane = 0;                       // 0 = the caller's stream, k > 0 = the program's k-th side stream
+  int waiter = 0, signaller = 0;      // OP_SYNC: lane `waiter` waits for everything enqueued so far on lane `signaller`
+  cudaEvent_t event = nullptr;
   ConvParams conv; ConvLaunch conv_launch;
   // generic scalar arguments for the small ops
   const void* in; void* out; const float* w; const float* b;
@@ -60,6 +63,8 @@ struct Op {
 struct dy_program {
   std::vector<dy::Op*> ops;
   int launches = 0;
+  int lane = 0;                           // lane of the ops added from now on (dy_program_set_lane)
+  std::vector<cudaStream_t> side;         // side streams, lane k -> side[k - 1]; lower priority than any prioritised caller stream
 };
 
 extern "C" {
@@ -84,11 +89,16 @@ int dy_program_create(dy_program** out) {
 
 void dy_program_destroy(dy_program* p) {
   if (!p) return;
-  for (dy::Op* o : p->ops) delete o;
+  for (dy::Op* o : p->ops) {
+    if (o->event) cudaEventDestroy(o->event);
+    delete o;
+  }
+  for (cudaStream_t s : p->side) cudaStreamDestroy(s);
   delete p;
 }
 
 static int push(dy_program* p, dy::Op* o, int launches) {
+  o->lane = p->lane;
   p->ops.push_back(o);
   p->launches += launches;
   return DY_OK;
@@ -152,12 +162,48 @@ int dy_program_add_nms(dy_program* p, const dy_nms_desc* d) {
   return push(p, o, 2);
 }
 
+// Lanes: independent branches of the layer graph (the Detect branches of one pyramid level against the rest of the neck)
+// are enqueued on side streams, so that the CTAs of one branch fill the SMs another branch's kernel leaves idle during
+// its ramp-up, its last partial wave and its drain.  Side streams are created here (never during a stream capture) with
+// the lowest priority: a caller that captures / runs on a prioritised stream keeps the main chain ahead of the branches.
+int dy_program_set_lane(dy_program* p, int lane) {
+  DY_CHECK_ARG(p && lane >= 0 && lane <= 8, "program_set_lane: lane must be in [0, 8]");
+  while (static_cast<int>(p->side.size()) < lane) {
+    int least = 0, greatest = 0;
+    DY_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    cudaStream_t s = nullptr;
+    DY_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, least));
+    p->side.push_back(s);
+  }
+  p->lane = lane;
+  return DY_OK;
+}
+
+int dy_program_add_sync(dy_program* p, int waiter, int signaller) {
+  DY_CHECK_ARG(p && waiter != signaller && waiter >= 0 && signaller >= 0 && waiter <= static_cast<int>(p->side.size()) &&
+               signaller <= static_cast<int>(p->side.size()), "program_add_sync: unknown lane (declare it with dy_program_set_lane first)");
+  dy::Op* o = new dy::Op();
+  o->kind = dy::OP_SYNC; o->waiter = waiter; o->signaller = signaller;
+  cudaError_t e = cudaEventCreateWithFlags(&o->event, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete o; return dy::fail(DY_ERR_CUDA, "program_add_sync: %s", cudaGetErrorString(e)); }
+  p->ops.push_back(o);
+  return DY_OK;
+}
+
 int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream_) {
   DY_CHECK_ARG(p, "program_run: null program");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaStream_t main_stream = static_cast<cudaStream_t>(stream_);
   for (dy::Op* o : p->ops) {
     int rc = DY_OK;
+    cudaStream_t stream = o->lane == 0 ? main_stream : p->side[o->lane - 1];
     switch (o->kind) {
+      case dy::OP_SYNC: {
+        cudaStream_t sig = o->signaller == 0 ? main_stream : p->side[o->signaller - 1];
+        cudaStream_t wai = o->waiter == 0 ? main_stream : p->side[o->waiter - 1];
+        DY_CUDA(cudaEventRecord(o->event, sig));
+        DY_CUDA(cudaStreamWaitEvent(wai, o->event, 0));
+        break;
+      }
       case dy::OP_CONV: rc = dy::conv_launch(&o->conv, &o->conv_launch, stream); break;
       case dy::OP_STEM:
         rc = dy::stem_launch(static_cast<const char*>(o->in) + in_offset_bytes, o->Cin, o->B, o->H, o->W,

@@ -99,6 +99,11 @@ __device__ __forceinline__ float act1(uint32_t acc, float hb, bool silu) {
 //   0: 1x1 (one tap, flat pixel index), 1: 3x3 stride 1 (tap (r,c) shifts the box by (c-1, r-1)), 2: 3x3 stride 2 (parity views),
 //   3: 3x3 stride 1 halo, one 64-channel block, 128-byte rows;  4: 3x3 stride 1 halo, Cin <= 32, 64-byte rows;
 //   5: 3x3 stride 2, Cin <= 32, 64-byte rows (a filter row of three taps per pipeline stage).
+//   6: 3x3 stride 1 halo, Cin >= 128, Cout <= 128 ("paired halo"): the L2 -> SM path (~56 B/cycle/SM measured) bounds the
+//      generic mode 1, which fetches 16 KB of A and 16 KB of B per 4 MMAs (128 B/cycle at the tensor rate).  Here the A
+//      operand of a (tile, 64-channel block) is ONE halo tile read by all nine taps (23 KB instead of 144 KB), and every
+//      streamed weight tile (tap, block) feeds TWO pixel tiles with their own accumulators: ~41 B/cycle at the tensor rate.
+//      Two rings: A (halo tiles) and B (weight tiles), each with its own full / empty barriers.
 // CW = chunk width (channels) of the TMA-store epilogue: 64 or 32 bf16 (F32 = false), 32 fp32 (F32 = true).
 // CW = 0 selects the generic register->global epilogue (odd widths).
 // Shared memory: [resident weights][stages x (A blocks [+ B blocks])][2 groups x 2 staging tiles].
@@ -118,9 +123,12 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
   __shared__ __align__(8) uint64_t res_bar[2 * EG];     // [group][staging buffer]: residual tile landed
   __shared__ __align__(8) uint64_t d2_bar[2];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
+  __shared__ __align__(8) uint64_t afull_bar[kMaxStages];     // mode 6: the halo-tile ring (full_bar / empty_bar then serve the weight ring)
+  __shared__ __align__(8) uint64_t aempty_bar[kMaxStages];
   __shared__ uint32_t tmem_base_s;
   constexpr int NTAPS = MODE == 0 ? 1 : 9;
   constexpr bool HALO = (MODE == 3 || MODE == 4);
+  constexpr bool PAIRED = (MODE == 6);
   constexpr bool S2 = (MODE == 2 || MODE == 5);         // stride 2: four parity views
   constexpr int ROWB = (MODE == 4 || MODE == 5) ? 64 : 128;   // bytes per pixel / per weight row in the A / B shared-memory tiles
   constexpr int A_BLK = kBlockM * ROWB;                 // one A k-block: 64 channels (16 KB) or 32 channels (8 KB)
@@ -166,8 +174,9 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
     if (FUSE2) { prefetch_tmap(&p.tmW2); prefetch_tmap(&p.tmO2); }
   }
   if (warp == 1 && elect_one()) {
-    const uint32_t producers = bres ? 1u : 2u;             // A thread (+ B thread) arrive on every full barrier
+    const uint32_t producers = (bres || PAIRED) ? 1u : 2u; // A thread (+ B thread) arrive on every full barrier
     for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
+    if constexpr (PAIRED) { for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); } }
     for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int i = 0; i < 2 * EG; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1);
@@ -203,6 +212,30 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
       [[maybe_unused]] const int kit = opaque(kiters), kps_r = opaque(kps), kcmax = opaque(kblocks * kBlockK);
       [[maybe_unused]] const uint32_t e_minus_f = empty0 - full0;
       [[maybe_unused]] uint32_t fullb = full0, dst = stage0;
+      if constexpr (PAIRED) {
+        // one halo tile per (pixel tile, 64-channel block); the two tiles of a pair alternate
+        const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
+        const int na = opaque(p.a_stages);
+        const uint32_t abytes = opaque(static_cast<uint32_t>(p.a_stage_bytes));
+        int sa = 0; uint32_t pa = 0;
+        while (it.valid()) {
+          TileIter t0 = it; it.next(n_iter, tiles_w, tiles_h);
+          TileIter t1 = it; const bool two = it.valid();
+          if (two) it.next(n_iter, tiles_w, tiles_h);
+          for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (j == 1 && !two) break;
+              const TileIter& t = j ? t1 : t0;
+              mbar_wait_a(aempty0 + sa * 8, pa ^ 1u);
+              mbar_arrive_expect_tx_a(afull0 + sa * 8, halo_tx);
+              if (!(dbg & 4)) tma_load_4d_a(smem_base + static_cast<uint32_t>(sa) * abytes, &p.tmA[0], afull0 + sa * 8, kb * kBlockK,
+                                            t.tw_i * TW - 1, t.th_i * TH - 1, t.tb_i * TB);
+              if (++sa == na) { sa = 0; pa ^= 1u; }
+            }
+          }
+        }
+      } else
       for (; it.valid(); it.next(n_iter, tiles_w, tiles_h)) {
         const int w0 = it.tw_i * TW, h0 = it.th_i * TH, b0 = it.tb_i * TB;
         if constexpr (HALO) {
@@ -250,6 +283,22 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
     if (elect_one()) {
       constexpr uint32_t lead = 1u;
       const int kblocks = opaque(p.kblocks);
+      if constexpr (PAIRED) {
+        // weight tiles (tap, block) in the order the MMA issuer consumes them, once per tile PAIR
+        TileIter cnt(p, blockIdx.x, gridDim.x);
+        const int items = (cnt.remaining + 1) >> 1;
+        const uint32_t b_ring0 = smem_base + static_cast<uint32_t>(p.a_stages) * static_cast<uint32_t>(p.a_stage_bytes);
+        const uint32_t b_tx = (dbg & 8) ? 0u : b_bytes;
+        int sb = 0; uint32_t pb = 0;
+        for (int i = 0; i < items; ++i)
+          for (int kb = 0; kb < kblocks; ++kb)
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait_a(empty0 + sb * 8, pb ^ 1u);
+              mbar_arrive_expect_tx_a(full0 + sb * 8, b_tx);
+              if (!(dbg & 8)) tma_load_3d_a(b_ring0 + static_cast<uint32_t>(sb) * b_bytes, &p.tmB, full0 + sb * 8, kb * kBlockK, 0, t);
+              if (++sb == nstages) { sb = 0; pb ^= 1u; }
+            }
+      } else
       if (bres) {
         const int n0 = (p.n_split > 1 ? static_cast<int>(blockIdx.x) % p.n_split : 0) * p.BN;
         mbar_arrive_expect_tx_p(lead, bres_b, (dbg & 8) ? 0u : bres_bytes);
@@ -306,13 +355,68 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
       const uint32_t bbytes = opaque(b_bytes);
       // descriptor = constant high word | (address >> 4): only the low word changes
       const uint64_t b_hi = umma_desc_kmajor(0, 8 * ROWB, LAYOUT) & 0xffffffff00000000ull;
-      const uint64_t a_hi = HALO ? (umma_desc_kmajor(0, static_cast<uint32_t>(p.halo_pitch) * ROWB, LAYOUT) & 0xffffffff00000000ull) : b_hi;
+      const uint64_t a_hi = (HALO || PAIRED) ? (umma_desc_kmajor(0, static_cast<uint32_t>(p.halo_pitch) * ROWB, LAYOUT) & 0xffffffff00000000ull) : b_hi;
       const uint32_t lo_const = static_cast<uint32_t>(umma_desc_kmajor(0, 1024, LAYOUT) & 0xffffffffull);   // LBO field
       const uint32_t BNu = opaque(static_cast<uint32_t>(p.BN));
       [[maybe_unused]] int trk = 0, trt = 0;
       TileIter count_it(p, blockIdx.x, gridDim.x);
       const int my_total = count_it.remaining;
       if (bres) mbar_wait_a(bres_b, 0);
+      if constexpr (PAIRED) {
+        // per pair: for every 64-channel block, nine weight tiles, each multiplied into both tiles' accumulators
+        const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
+        const int na = opaque(p.a_stages), kblocks = opaque(p.kblocks);
+        const uint32_t abytes = opaque(static_cast<uint32_t>(p.a_stage_bytes));
+        const uint32_t b_ring0 = smem_base + static_cast<uint32_t>(na) * abytes;
+        const uint32_t halo_rowstep = static_cast<uint32_t>(p.halo_pitch * ROWB) >> 4;
+        const uint32_t BNv = opaque(static_cast<uint32_t>(p.BN));
+        int sa = 0; uint32_t pa = 0;
+        int sb = 0; uint32_t pb = 0;
+        bool okf = mbar_try_wait_a(full0, 0u);
+        for (int t = 0; t < my_total; t += 2) {
+          const bool two = t + 1 < my_total;
+          // accumulator slots t & 3 and (t + 1) & 3 (nacc == 4), phase (t >> 2) & 1
+          const uint32_t slot0 = static_cast<uint32_t>(t) & 3u, accp = (static_cast<uint32_t>(t) >> 2) & 1u;
+          mbar_wait_a(tempty0 + slot0 * 8, accp ^ 1u);
+          if (two) mbar_wait_a(tempty0 + (slot0 + 1) * 8, accp ^ 1u);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + slot0 * BNv, d1 = d0 + BNv;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            const int sa0 = sa; int sa1 = sa + 1; uint32_t pa1 = pa;
+            if (sa1 == na) { sa1 = 0; pa1 ^= 1u; }
+            mbar_wait_a(afull0 + sa0 * 8, pa);
+            if (two) mbar_wait_a(afull0 + sa1 * 8, pa1);
+            tc_fence_after();
+            const uint32_t a0_lo = lo_const | (((smem_base + static_cast<uint32_t>(sa0) * abytes) & 0x3ffffu) >> 4);
+            const uint32_t a1_lo = lo_const | (((smem_base + static_cast<uint32_t>(sa1) * abytes) & 0x3ffffu) >> 4);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait_unless(full0 + sb * 8, pb, okf);
+              tc_fence_after();
+              const uint32_t b_lo = lo_const | (((b_ring0 + static_cast<uint32_t>(sb) * bbytes) & 0x3ffffu) >> 4);
+              const uint32_t fb = empty0 + sb * 8;
+              if (++sb == nstages) { sb = 0; pb ^= 1u; }
+              const uint32_t r = static_cast<uint32_t>(tap) / 3u, c = static_cast<uint32_t>(tap) - 3u * r;
+              const uint32_t shift = r * halo_rowstep + c * (ROWB >> 4);
+              const uint32_t accum = (kb | tap) ? 1u : 0u;
+              if (!(dbg & 2)) {
+                okf = umma_bf16_ss_x4_waitahead(d0, a_hi | (a0_lo + shift), b_hi | b_lo, idesc, accum, full0 + sb * 8, pb);
+                if (two) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_bf16_ss(d1, a_hi | (a1_lo + shift + 2 * k), b_hi | (b_lo + 2 * k), idesc, (accum | k) ? 1u : 0u);
+                }
+              } else okf = mbar_try_wait_a(full0 + sb * 8, pb);
+              umma_commit_a(fb);                                // the weight slot is free once these MMAs retire
+            }
+            umma_commit_a(aempty0 + sa0 * 8);
+            if (two) umma_commit_a(aempty0 + sa1 * 8);
+            if (two) { sa = sa1 + 1; pa = pa1; } else { sa = sa0 + 1; }
+            if (sa == na) { sa = 0; pa ^= 1u; }
+          }
+          umma_commit_a(tfull0 + slot0 * 8);
+          if (two) umma_commit_a(tfull0 + (slot0 + 1) * 8);
+        }
+      } else
       if constexpr (HALO) {
         const int m = warp - 1;                                            // this issuer's tile parity
         [[maybe_unused]] const int trole = m == 0 ? 1 : 2;
@@ -447,7 +551,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
 #define DY_TRE(ev) do { } while (0)
 #endif
     const int rows_valid = p.TW * p.TH * p.TB;
-    const uint32_t stg = smem_base + bres_bytes + static_cast<uint32_t>(p.stages) * sbytes + static_cast<uint32_t>(g * p.nbuf) * STG_BYTES;
+    const uint32_t stg = smem_base + static_cast<uint32_t>(p.stg_off) + static_cast<uint32_t>(g * p.nbuf) * STG_BYTES;
     const uint32_t resb0 = smem_u32(&res_bar[g * 2]);
     const bool has_res = CW > 0 && !F32 && p.has_res_tma != 0;
     const uint32_t res_tx = static_cast<uint32_t>(rows_valid) * CW * 2u;
@@ -975,6 +1079,12 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       else if (cin_pad == kBlockK) mode = 3;
     }
   }
+  if (mode == 1 && !fuse2 && !f32 && d->up_out == nullptr && cin_pad >= 2 * kBlockK && cout_pad <= 128 && cout_pad % 32 == 0 &&
+      d->Cout % 8 == 0 && !env_int("DY_NO_PAIRED", 0)) {
+    // paired halo (mode 6): needs whole 8x16 tiles to pay (a ragged map wastes MMA rows the generic mode does not)
+    const double eff = double(Wo) * Ho / (double(ceil_div(Wo, kHaloTW)) * kHaloTW * ceil_div(Ho, kHaloTH) * kHaloTH);
+    if (eff >= 0.8) { mode = 6; p->BN = cout_pad; p->n_tiles = 1; }
+  }
   if (mode == 3 || mode == 4) {
     // halo: resident weights of ONE n tile per CTA (9 x BN rows); several n tiles -> static split of the grid
     const int m_tiles = ceil_div(Wo, kHaloTW) * ceil_div(Ho, kHaloTH) * d->B;
@@ -988,11 +1098,12 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   }
   if (fuse2 && mode != 3 && !(mode == 5 && d->tail_decode == 3))
     return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs the 64-channel halo mode (or the 32-channel stride-2 mode with a SiLU bf16 tail)");
-  const bool halo = (mode == 3 || mode == 4);
+  const bool paired = (mode == 6);
+  const bool halo = (mode == 3 || mode == 4 || paired);     // tile geometry / activation box of the halo family
   const int rowb = (mode == 4 || mode == 5) ? 64 : 128;
   const int a_blk = kBlockM * rowb;
   p->mode = mode;
-  p->kblocks = (halo || mode == 5) ? 1 : cin_pad / kBlockK;
+  p->kblocks = ((halo && !paired) || mode == 5) ? 1 : cin_pad / kBlockK;
   const int kiters = p->ntaps * p->kblocks;
   const bool flat = (k == 1 && d->up_out == nullptr);         // 1x1: flat GEMM over all pixels unless a spatial tile is needed
   if (d->up_out) {
@@ -1073,7 +1184,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       else if (p->n_tiles == 1) cw = p->BN > 32 ? 64 : 32;
       // K-heavy tiles: the epilogue has time to spare, shared memory does not -> narrow staging tiles.  The 64-channel halo
       // mode needs the room for a fourth activation stage (HBM latency x bandwidth ~ 64 KB in flight per SM).
-      if (cw == 64 && (mode == 3 || (!halo && (kiters >= 8 || p->BN >= 128))) && p->BN % 32 == 0) cw = 32;
+      if (cw == 64 && (mode == 3 || paired || (!halo && (kiters >= 8 || p->BN >= 128))) && p->BN % 32 == 0) cw = 32;
       if (env_int("DY_CONV_CW", 0) == 32 && cw == 64 && p->BN % 32 == 0) cw = 32;
     }
     if (d->residual && f32) cw = 0;                            // fp32 + residual: generic path (not used by the model)
@@ -1151,19 +1262,32 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int cw = p->use_tma_store;
   // K-heavy generic tiles: one staging tile per group (the epilogue has slack), the room goes to fatter pipeline stages
   p->nbuf = (!fuse2 && ((!halo && kiters >= 8 && !env_int("DY_CONV_NBUF2", 0)) || (mode == 3 && p->BN > 64))) ? 1 : 2;   // the fused tail stages two tiles
+  if (paired) p->nbuf = env_int("DY_PAIRED_NBUF", 2);
   const int b_tile = p->BN * rowb;
   const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
   const int bias_bytes = (fuse2 ? 576 : round_up(p->n_tiles * p->BN + 64, 4)) * 4;
   p->eg = ((mode == 4 || (mode == 3 && !fuse2 && env_int("DY_CONV_EG3_M3", 1))) && cw == 32 && !f32 && p->BN <= 64 && !env_int("DY_CONV_EG2", 0)) ? 3 : 2;   // epilogue groups
   int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
-  if (p->nbuf == 1 && halo && !env_int("DY_CONV_NBUF1", 0)) {
+  if (p->nbuf == 1 && halo && !paired && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
     // previous chunk's store (~1700 cycles per 32-column chunk); take the second one whenever two halo stages still fit
     const int halo_stage = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
     if (kMaxDynSmem - 1024 - 2 * staging - bias_bytes - b_all >= 2 * halo_stage) { p->nbuf = 2; staging *= 2; }
   }
   const int budget = kMaxDynSmem - 1024 - staging - bias_bytes;
-  if (halo) {
+  if (paired) {
+    // two rings: halo tiles (one per pixel tile and 64-channel block; a pair holds two while the next two load) and weight
+    // tiles (one per tap and block, 8 MMAs each when paired): the weight ring takes what the halo ring leaves
+    p->b_resident = 0;
+    p->a_stage_bytes = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
+    p->a_stages = env_int("DY_PAIRED_ASTAGES", 4);
+    p->stage_bytes = b_tile;
+    int stages = (budget - p->a_stages * p->a_stage_bytes) / p->stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    DY_CHECK_ARG(p->a_stages >= 2 && p->a_stages <= kMaxStages && stages >= 2, "conv: paired halo mode does not fit shared memory (BN %d)", p->BN);
+    p->stages = stages;
+    p->kps = 1;
+  } else if (halo) {
     p->b_resident = 1;
     p->stage_bytes = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
     int stages = (budget - b_all) / p->stage_bytes;
@@ -1199,11 +1323,13 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (nacc > kMaxAcc) nacc = kMaxAcc;
     if (fuse2 && nacc > (kTmemCols - 128) / p->BN) nacc = (kTmemCols - 128) / p->BN;   // the last 128 columns hold the two tail accumulators
     if (halo) nacc &= ~1;
+    if (paired) nacc = nacc >= 4 ? 4 : 0;                                   // the issuer addresses accumulator slots as tile & 3
     if (p->eg == 3) nacc = nacc >= 6 ? 6 : 0;                               // even (two MMA issuers) and a multiple of the three groups
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;
   }
-  p->bias_off = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + staging;
+  p->stg_off = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + (paired ? p->a_stages * p->a_stage_bytes : 0);
+  p->bias_off = p->stg_off + staging;
   l->smem_bytes = p->bias_off + bias_bytes + 1024;
   const int total = p->m_tiles * p->n_tiles;
   if (p->n_split > 1) {
@@ -1260,6 +1386,7 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream)
                             : (p->eg == 3 ? conv_launch_t<3, 32, false, false, 3>(p, l, stream) : conv_launch_m<3>(p, l, stream));
     case 4: return p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream);
+    case 6: return conv_launch_t<6, 32, false>(p, l, stream);
     default: return p->fuse2 ? conv_launch_t<5, 32, false, true>(p, l, stream) : conv_launch_m<5>(p, l, stream);
   }
 }

@@ -22,6 +22,8 @@ struct ConvParams {
   int B, Ho, Wo, Cout;
   int stages, stage_bytes, kps;        // pipeline stages, bytes per stage, 64-channel k-blocks per stage
   int nacc, b_resident, mode;
+  int a_stages, a_stage_bytes;         // mode 6: the halo-tile ring in front of the weight ring (`stages` x `stage_bytes`)
+  int stg_off;                         // byte offset of the epilogue staging tiles (behind resident weights and pipeline stages)
   int halo_pitch;                      // pixels per halo-tile row in shared memory (TW + 2)
   int use_tma_store;                   // chunk width CW of the TMA-store epilogue (0 = generic register->global path)
   int has_res_tma;

@@ -33,7 +33,8 @@ class Engine:
     def __init__(self, model, batch: int, imgsz, device, micro_batch: int = 0, conf: float = 0.25, iou: float = 0.7,
                  max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
                  max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True,
-                 input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True, input_slots: int = 1):
+                 input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True, input_slots: int = 1,
+                 head_lanes: Optional[int] = None):
         device = torch.device(device)
         if device.type != "cuda":
             raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
@@ -54,7 +55,8 @@ class Engine:
             self.image_slots = [self._all_images[k * batch:(k + 1) * batch] for k in range(self.input_slots)]
             self.images = self.image_slots[0]
             self.y = torch.empty((batch, 4 + self.nc, self.A), device=device, dtype=torch.float32)
-            self.plan = LayerPlan(model, self.mb, H, W, device, self._all_images, self.y, fuse_decode=fuse_decode)
+            self.plan = LayerPlan(model, self.mb, H, W, device, self._all_images, self.y, fuse_decode=fuse_decode,
+                                  head_lanes=head_lanes)
             ml = bool(multi_label) and self.nc > 1
             self.nms_bufs = K.NmsBuffers(batch, self.nc, self.A, max_det, ml, device)
             self.nms_cfg = dict(conf=conf, iou=iou, max_det=max_det, classes=classes, agnostic=agnostic, multi_label=ml,
@@ -71,9 +73,12 @@ class Engine:
             self.enqueue()                       # eager warm-up (sets kernel attributes, pages in code)
             torch.cuda.synchronize(device)
             if cuda_graph:
+                # captured on a prioritised stream: the plan's side lanes (Detect branches, lowest priority) then yield the
+                # SMs to the main chain whenever both have CTAs waiting
+                cap = torch.cuda.Stream(device=device, priority=-1)
                 for k in range(self.input_slots):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=cap):
                         self.enqueue(slot=k)
                     self.graphs.append(g)
                 self.graph = self.graphs[0]

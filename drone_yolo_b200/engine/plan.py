@@ -39,7 +39,8 @@ class _Buf:
 class LayerPlan:
     """Symbolic pass -> arena assignment -> dy_program."""
 
-    def __init__(self, model, mb: int, H: int, W: int, device, images: torch.Tensor, y: torch.Tensor, fuse_decode: bool = False):
+    def __init__(self, model, mb: int, H: int, W: int, device, images: torch.Tensor, y: torch.Tensor, fuse_decode: bool = False,
+                 head_lanes: Optional[int] = None):
         if H % 32 or W % 32:
             raise _C.DroneYoloError(f"input {H}x{W} must be a multiple of the maximum stride 32")
         self.model, self.mb, self.H, self.W, self.device = model, mb, H, W, device
@@ -51,6 +52,11 @@ class LayerPlan:
         # decode inside the Detect tails: the raw maps of those levels are never materialised (Engine.raw_maps() is then
         # unavailable); needs the whole batch in one replay because the prediction tensor's address is baked into tensor maps
         self.fuse_cv1 = not os.environ.get("DY_NO_FUSE_CV1")
+        # side lanes for the Detect branches (dy_program_set_lane): 0 = everything on the caller's stream in layer order,
+        # 1 = the branches of every level on one side stream, 2 = box branch and class branch on two side streams.  A level's
+        # branches are emitted as soon as its source layer is done, so they overlap the rest of the neck.
+        self.head_lanes = int(os.environ.get("DY_HEAD_LANES", "2")) if head_lanes is None else int(head_lanes)
+        self.lane = 0
         self.fuse_decode = (bool(fuse_decode) and self.fuse_tail and not os.environ.get("DY_NO_FUSE_DECODE")
                             and y is not None and mb == y.shape[0])
         self._build_symbolic()
@@ -81,7 +87,11 @@ class LayerPlan:
         self._touch(kw.get("inp"), kw.get("out"), kw.get("res"), kw["tail"][3] if kw.get("tail") else None)
         for r in kw.get("levels", ()):
             self._touch(r)
+        kw["lane"] = self.lane
         self.ops.append(kw)
+
+    def _sync(self, waiter, signaller):
+        self.ops.append({"kind": "sync", "waiter": waiter, "signaller": signaller, "lane": 0})
 
     def _build_symbolic(self):
         layers = list(self.model.model)
@@ -110,6 +120,9 @@ class LayerPlan:
         self.layer_ref: list[Optional[Ref]] = [None] * n
         cat_buf: dict[int, int] = {}
         res = {"H": self.H, "W": self.W}
+        det = layers[-1] if isinstance(layers[-1], Detect) else None
+        det_src = [(j if j >= 0 else n - 1 + j) for j in det.f] if det is not None else []
+        self._det_state = None
 
         def dest(i, c, H, W):
             """Where layer i writes its output."""
@@ -169,12 +182,17 @@ class LayerPlan:
                 b = self.bufs[cat_buf[i]]
                 out = Ref(cat_buf[i], 0, b.C, b.H, b.W)
             elif isinstance(m, Detect):
-                srcs = [self.layer_ref[j] for j in f]
-                self._emit_detect(m, srcs)
+                for li, j in enumerate(det_src):             # levels not emitted yet (side lanes off)
+                    if self._det_state is None or li not in self._det_state["done"]:
+                        self._emit_detect_level(m, li, self.layer_ref[j])
+                self._finish_detect(m)
                 out = None
             else:
                 raise _C.DroneYoloError(f"layer {i}: {type(m).__name__} has no plan lowering")
             self.layer_ref[i] = out
+            if self.head_lanes > 0 and det is not None and i in det_src and out is not None:
+                # this pyramid level is complete: its Detect branches only depend on it (head.py:64-74) -> side lane(s), now
+                self._emit_detect_level(det, det_src.index(i), out)
         del res
 
     @staticmethod
@@ -225,49 +243,90 @@ class LayerPlan:
             self._op(kind="conv", mod=b.cv2, inp=tmp, out=Ref(cat, (2 + i) * c, c, H, W), res=xin if b.add else None)
         self._op(kind="conv", mod=m.cv2, inp=Ref(cat, 0, (2 + n) * c, H, W), out=out)
 
-    def _emit_detect(self, m: Detect, srcs):
-        packed = m.packed()
-        levels, level_off, level_stride, all_levels = [], [], [], []
-        a_off = 0
-        for i, src in enumerate(srcs):
-            H, W = src.H, src.W
-            c2, c3 = m.cv2[i][0].conv.out_channels, m.cv3[i][0].conv.out_channels
-            (wf, bf), (wbx, bbx), (wcl, bcl) = packed[i]
-            t1 = self._new_buf(c2 + c3, H, W)
-            ncp = m.raw_ld - 4 * m.reg_max          # class logits padded to 16 channels (zero weights) -> TMA-store path
-            self._op(kind="conv", w=(wf, bf), cout=c2 + c3, k=3, s=1, act=True, inp=src, out=Ref(t1, 0, c2 + c3, H, W))
-            # Each branch ends Conv(c,c,3) -> nn.Conv2d(c,n,1) (head.py:41-47).  Where the 64-channel halo kernel applies, the
-            # 1x1 runs inside the 3x3's epilogue (dy_conv_desc.weight2) and the intermediate tensor is never written; with
-            # fuse_decode the same epilogue also decodes the logits (dy_conv_desc.tail_decode) and the raw map is skipped too.
-            # ragged 8x16 tiles waste MMA rows, but a level this small is launch-bound: three launches less win
-            halo_ok = self.fuse_tail and (H * W / (-(-W // 8) * 8 * -(-H // 16) * 16) >= 0.8 or self.mb * H * W <= 65536)
-            branches = ((m.cv2[i][1], 0, c2, (wbx, bbx), 4 * m.reg_max, 0), (m.cv3[i][1], c2, c3, (wcl, bcl), ncp, 4 * m.reg_max))
-            fusable = [halo_ok and cw == 64 and cout1 <= 64 for (_, _, cw, _, cout1, _) in branches]
-            dec = self.fuse_decode and all(fusable) and m.nc <= 32 and W % 4 == 0 and a_off % 4 == 0
-            raw = None if dec else self._new_buf(m.raw_ld, H, W, esz=4)
-            t2 = None
-            for bi, (mod3, cin0, cw, (w1, b1), cout1, c0out) in enumerate(branches):
-                if fusable[bi]:
-                    tail = ((w1, b1, cout1, None, (bi + 1, a_off, float(m.stride[i]))) if dec
-                            else (w1, b1, cout1, Ref(raw, c0out, cout1, H, W)))
-                    self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=None, tail=tail)
-                else:
-                    if t2 is None:
-                        t2 = self._new_buf(c2 + c3, H, W)
-                    self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=Ref(t2, cin0, cw, H, W))
-                    self._op(kind="conv", w=(w1, b1), cout=cout1, k=1, s=1, act=False, inp=Ref(t2, cin0, cw, H, W),
-                             out=Ref(raw, c0out, cout1, H, W))
-            if not dec:
-                levels.append(Ref(raw, 0, m.no, H, W)); level_off.append(a_off); level_stride.append(float(m.stride[i]))
-            all_levels.append(None if dec else Ref(raw, 0, m.no, H, W))
-            a_off += H * W
-        if levels:
-            self._op(kind="decode", levels=levels, det=m, strides=level_stride,
-                     anchor_off=level_off if len(levels) < len(srcs) else None)
-        self.raw_refs = all_levels
+    def _emit_detect_level(self, m: Detect, i: int, src: Ref):
+        """The three convs of pyramid level `i` (head.py:41-47, 64-74): merged first 3x3 (N = c2 + c3), then per branch
+        Conv(c,c,3) -> nn.Conv2d(c,n,1), fused (+ decode) where the 64-channel halo kernel applies."""
+        if self._det_state is None:
+            strides = [int(v) for v in m.stride.tolist()]
+            hw = [(self.H // st) * (self.W // st) for st in strides]
+            self._det_state = {"packed": m.packed(), "done": set(), "levels": {}, "all": {}, "forks": {},
+                               "a_off": [sum(hw[:k]) for k in range(len(hw))]}
+        st = self._det_state
+        packed, a_off = st["packed"], st["a_off"][i]
+        lanes = self.head_lanes
+        if lanes > 0:
+            st["forks"][i] = len(self.ops)
+            self._sync(1, 0)                        # lane 1 continues from here: the level's source is complete
+            self.lane = 1
+        H, W = src.H, src.W
+        if H * W != (self.H // int(m.stride[i])) * (self.W // int(m.stride[i])):
+            raise _C.DroneYoloError(f"Detect level {i}: source resolution {H}x{W} does not match stride {int(m.stride[i])}")
+        c2, c3 = m.cv2[i][0].conv.out_channels, m.cv3[i][0].conv.out_channels
+        (wf, bf), (wbx, bbx), (wcl, bcl) = packed[i]
+        t1 = self._new_buf(c2 + c3, H, W)
+        ncp = m.raw_ld - 4 * m.reg_max          # class logits padded to 16 channels (zero weights) -> TMA-store path
+        self._op(kind="conv", w=(wf, bf), cout=c2 + c3, k=3, s=1, act=True, inp=src, out=Ref(t1, 0, c2 + c3, H, W))
+        # Each branch ends Conv(c,c,3) -> nn.Conv2d(c,n,1) (head.py:41-47).  Where the 64-channel halo kernel applies, the
+        # 1x1 runs inside the 3x3's epilogue (dy_conv_desc.weight2) and the intermediate tensor is never written; with
+        # fuse_decode the same epilogue also decodes the logits (dy_conv_desc.tail_decode) and the raw map is skipped too.
+        # ragged 8x16 tiles waste MMA rows, but a level this small is launch-bound: three launches less win
+        halo_ok = self.fuse_tail and (H * W / (-(-W // 8) * 8 * -(-H // 16) * 16) >= 0.8 or self.mb * H * W <= 65536)
+        branches = ((m.cv2[i][1], 0, c2, (wbx, bbx), 4 * m.reg_max, 0), (m.cv3[i][1], c2, c3, (wcl, bcl), ncp, 4 * m.reg_max))
+        fusable = [halo_ok and cw == 64 and cout1 <= 64 for (_, _, cw, _, cout1, _) in branches]
+        dec = self.fuse_decode and all(fusable) and m.nc <= 32 and W % 4 == 0 and a_off % 4 == 0
+        raw = None if dec else self._new_buf(m.raw_ld, H, W, esz=4)
+        t2 = None
+        for bi, (mod3, cin0, cw, (w1, b1), cout1, c0out) in enumerate(branches):
+            if lanes >= 2 and bi == 1:
+                self._sync(2, 1)                    # the class branch runs beside the box branch, behind the merged first conv
+                self.lane = 2
+            if fusable[bi]:
+                tail = ((w1, b1, cout1, None, (bi + 1, a_off, float(m.stride[i]))) if dec
+                        else (w1, b1, cout1, Ref(raw, c0out, cout1, H, W)))
+                self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=None, tail=tail)
+            else:
+                if t2 is None:
+                    t2 = self._new_buf(c2 + c3, H, W)
+                self._op(kind="conv", mod=mod3, inp=Ref(t1, cin0, cw, H, W), out=Ref(t2, cin0, cw, H, W))
+                self._op(kind="conv", w=(w1, b1), cout=cout1, k=1, s=1, act=False, inp=Ref(t2, cin0, cw, H, W),
+                         out=Ref(raw, c0out, cout1, H, W))
+        self.lane = 0
+        if not dec:
+            st["levels"][i] = (Ref(raw, 0, m.no, H, W), a_off, float(m.stride[i]))
+        st["all"][i] = None if dec else Ref(raw, 0, m.no, H, W)
+        st["done"].add(i)
+
+    def _finish_detect(self, m: Detect):
+        st = self._det_state
+        for lane in range(1, min(self.head_lanes, 2) + 1):
+            self._sync(0, lane)                     # join: the decode of the remaining levels and the NMS read every branch's output
+        if self.head_lanes > 0:
+            # Side-lane ops run concurrently with the main chain: whatever they touch is live from the fork to the end of the
+            # program (the arena otherwise recycles a buffer after its last reader IN PROGRAM ORDER)
+            end = len(self.ops)
+            fork_of = {}
+            cur = None
+            for idx, op in enumerate(self.ops):
+                if op["kind"] == "sync" and op["waiter"] == 1 and op["signaller"] == 0:
+                    cur = idx
+                if op.get("lane", 0) > 0 and op["kind"] != "sync":
+                    fork_of[idx] = cur
+            for idx, fork in fork_of.items():
+                op = self.ops[idx]
+                refs = [op.get("inp"), op.get("out"), op.get("res"), op["tail"][3] if op.get("tail") else None]
+                for r in refs:
+                    if r is not None:
+                        b = self.bufs[r.buf]
+                        b.first = min(b.first, fork)
+                        b.last = max(b.last, end)
+        order = sorted(st["levels"])
+        if order:
+            self._op(kind="decode", levels=[st["levels"][i][0] for i in order], det=m, strides=[st["levels"][i][2] for i in order],
+                     anchor_off=[st["levels"][i][1] for i in order] if len(order) < len(st["all"]) else None)
+        self.raw_refs = [st["all"][i] for i in sorted(st["all"])]
 
     # ---------------------------------------------------------------------------------------------
-    def _assign_arena(self):
+    def _assign_arena(self, allocate: bool = True):
         """First-fit offsets with lifetime reuse (buffers are free after their last reader)."""
         live: list[tuple[int, int, int]] = []      # (offset, nbytes, last)
         total = 0
@@ -286,7 +345,8 @@ class LayerPlan:
             live.append((off, b.nbytes, b.last))
             total = max(total, off + b.nbytes)
         self.arena_bytes = total
-        self.arena = torch.empty((max(total, 1024),), device=self.device, dtype=torch.uint8)
+        if allocate:
+            self.arena = torch.empty((max(total, 1024),), device=self.device, dtype=torch.uint8)
 
     def tensor(self, r: Ref) -> torch.Tensor:
         """(mb, c, H, W) channels-last view of a Ref inside the arena."""
@@ -302,8 +362,19 @@ class LayerPlan:
         _C.check(lib.dy_program_create(C.byref(h)), "dy_program_create")
         self.handle = h
         mb = self.mb
+        lane = 0
         for op in self.ops:
             kind = op["kind"]
+            if kind == "sync":
+                for ln in (op["waiter"], op["signaller"]):          # a side lane exists once it has been selected
+                    if ln > 0:
+                        _C.check(lib.dy_program_set_lane(h, ln), "set_lane")
+                _C.check(lib.dy_program_set_lane(h, lane), "set_lane")
+                _C.check(lib.dy_program_add_sync(h, op["waiter"], op["signaller"]), "add_sync")
+                continue
+            if op.get("lane", 0) != lane:
+                lane = op.get("lane", 0)
+                _C.check(lib.dy_program_set_lane(h, lane), "set_lane")
             if kind == "stem":
                 w, b = op["mod"].packed()
                 self.keep.append((w, b))

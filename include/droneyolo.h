@@ -214,6 +214,14 @@ int dy_program_add_dwconv3x3s2(dy_program* p, const void* in, int in_ld, int B, 
                                const float* weight, const float* bias, int Cout, void* out, int out_ld);
 int dy_program_add_decode(dy_program* p, const dy_decode_desc* d);
 int dy_program_add_nms(dy_program* p, const dy_nms_desc* d);
+/* Lanes: ops added after dy_program_set_lane(p, k) are enqueued on the program's k-th side stream (k = 0: the stream
+ * given to dy_program_run; 1 <= k <= 8: created by this call, lowest priority).  dy_program_add_sync(p, waiter, signaller)
+ * makes lane `waiter` wait (event record + stream wait, capturable) for everything added so far on lane `signaller`.
+ * The caller forks every side lane from lane 0 before its first op and joins it back into lane 0 after its last one.
+ * Replaces: nothing in the reference (its layer loop nn/tasks.py:134-161 is strictly sequential on the default stream);
+ * the branches are the per-level Detect convs of nn/modules/head.py:64-74, which only depend on their own level. */
+int dy_program_set_lane(dy_program* p, int lane);
+int dy_program_add_sync(dy_program* p, int waiter, int signaller);
 /* in_offset_bytes / out_offset_bytes are added to the stem input pointer and to the decode output
  * pointer: the same program serves successive micro-batches of one large resident batch. */
 int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream);

@@ -84,6 +84,11 @@ CONV_CASES = [
     (4, 32, 64, 320, 320, 3, 2, True, False, False, 0, 0, 0),       # stride 2 with 64-byte rows (model.1 of the s scale)
     (2, 16, 32, 64, 96, 3, 2, True, False, False, 16, 32, 0),       # ... n scale, inside slices
     (1, 24, 48, 31, 45, 3, 2, True, False, False, 0, 0, 0),         # ... odd map
+    (4, 128, 128, 40, 40, 3, 1, True, True, False, 0, 0, 0),        # paired halo mode (Cin >= 128, Cout <= 128): ragged tile row + residual
+    (3, 256, 128, 40, 40, 3, 1, True, False, False, 0, 0, 0),       # ... four 64-channel blocks (Detect's merged first conv at P4)
+    (16, 128, 64, 48, 32, 3, 1, True, False, False, 64, 64, 0),     # ... pairs and single tiles per CTA, N = 64, inside concat slices
+    (1, 192, 96, 16, 32, 3, 1, False, False, False, 0, 0, 0),       # ... one tile per CTA, three blocks, N = 96, no activation
+    (24, 128, 128, 80, 80, 3, 1, True, False, False, 0, 0, 0),      # ... eight tiles per CTA: every ring wraps several times
 ]
 
 
