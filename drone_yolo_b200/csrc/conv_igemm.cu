@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
   __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t res_bar[2 * EG];     // [group][staging buffer]: residual tile landed
-  __shared__ __align__(8) uint64_t d2_bar[2];           // [group]: fused 1x1 tail finished
+  __shared__ __align__(8) uint64_t d2_bar[3];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ __align__(8) uint64_t afull_bar[kMaxStages];     // mode 6: the halo-tile ring (full_bar / empty_bar then serve the weight ring)
   __shared__ __align__(8) uint64_t aempty_bar[kMaxStages];
@@ -175,11 +175,11 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
   }
   if (warp == 1 && elect_one()) {
     const uint32_t producers = (bres || PAIRED) ? 1u : 2u; // A thread (+ B thread) arrive on every full barrier
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], PAIRED ? 2 : 1); }
     if constexpr (PAIRED) { for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); } }
     for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int i = 0; i < 2 * EG; ++i) mbar_init(&res_bar[i], 1);
-    mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1);
+    mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1); mbar_init(&d2_bar[2], 1);
     mbar_init(&bres_bar, 1);
     fence_mbar_init();
   }
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
         }
       }
     }
-  } else if (warp == 1 || (HALO && warp == 2)) {
+  } else if (warp == 1 || ((HALO || PAIRED) && warp == 2)) {
     // ===================== MMA issuers =====================
     // Halo modes: TWO issuing threads (warps 1 and 2) take alternate tiles, so one thread's barrier waits / commits overlap
     // the other's MMA issue (the tensor pipe executes both streams; the accumulators and smem stages are disjoint).
@@ -363,58 +363,57 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
       const int my_total = count_it.remaining;
       if (bres) mbar_wait_a(bres_b, 0);
       if constexpr (PAIRED) {
-        // per pair: for every 64-channel block, nine weight tiles, each multiplied into both tiles' accumulators
+        // TWO issuing threads (warps 1 and 2): issuer j multiplies every weight tile into the j-th pixel tile of the pair, so
+        // each thread issues 4 MMAs per weight stage and the two instruction streams overlap (one thread issuing all 8 next
+        // to its barrier traffic ran the tensor pipe at ~97 cycles per MMA instead of 64).  Halo slots: a pair takes two
+        // consecutive slots per 64-channel block (issuer j the j-th; the ring is even, so the parity never changes); a final
+        // single tile belongs to issuer 0, while issuer 1 just hands the weight stages back.
+        const int j = warp - 1;
         const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
         const int na = opaque(p.a_stages), kblocks = opaque(p.kblocks);
         const uint32_t abytes = opaque(static_cast<uint32_t>(p.a_stage_bytes));
         const uint32_t b_ring0 = smem_base + static_cast<uint32_t>(na) * abytes;
         const uint32_t halo_rowstep = static_cast<uint32_t>(p.halo_pitch * ROWB) >> 4;
         const uint32_t BNv = opaque(static_cast<uint32_t>(p.BN));
-        int sa = 0; uint32_t pa = 0;
+        const uint32_t bstep = opaque(bbytes >> 4);
+        const uint32_t b_lo0 = opaque(lo_const | ((b_ring0 & 0x3ffffu) >> 4));
+        const uint32_t a_lo_base = opaque(lo_const | ((smem_base & 0x3ffffu) >> 4));
+        const uint32_t astep = opaque(abytes >> 4);
+        int sa = j; uint32_t pa = 0;
         int sb = 0; uint32_t pb = 0;
+        uint32_t b_lo = b_lo0, fullb = full0;
+        const uint32_t e_minus_f = empty0 - full0;
         bool okf = mbar_try_wait_a(full0, 0u);
         for (int t = 0; t < my_total; t += 2) {
           const bool two = t + 1 < my_total;
-          // accumulator slots t & 3 and (t + 1) & 3 (nacc == 4), phase (t >> 2) & 1
-          const uint32_t slot0 = static_cast<uint32_t>(t) & 3u, accp = (static_cast<uint32_t>(t) >> 2) & 1u;
-          mbar_wait_a(tempty0 + slot0 * 8, accp ^ 1u);
-          if (two) mbar_wait_a(tempty0 + (slot0 + 1) * 8, accp ^ 1u);
-          tc_fence_after();
-          const uint32_t d0 = tmem_base + slot0 * BNv, d1 = d0 + BNv;
+          const bool mine = (j == 0) || two;                                 // issuer 1 has no tile in a final single item
+          const uint32_t slot = (static_cast<uint32_t>(t) & 3u) + static_cast<uint32_t>(j), accp = (static_cast<uint32_t>(t) >> 2) & 1u;
+          if (mine) { mbar_wait_a(tempty0 + slot * 8, accp ^ 1u); tc_fence_after(); }
+          const uint32_t d = tmem_base + slot * BNv;
           for (int kb = 0; kb < kblocks; ++kb) {
-            const int sa0 = sa; int sa1 = sa + 1; uint32_t pa1 = pa;
-            if (sa1 == na) { sa1 = 0; pa1 ^= 1u; }
-            mbar_wait_a(afull0 + sa0 * 8, pa);
-            if (two) mbar_wait_a(afull0 + sa1 * 8, pa1);
-            tc_fence_after();
-            const uint32_t a0_lo = lo_const | (((smem_base + static_cast<uint32_t>(sa0) * abytes) & 0x3ffffu) >> 4);
-            const uint32_t a1_lo = lo_const | (((smem_base + static_cast<uint32_t>(sa1) * abytes) & 0x3ffffu) >> 4);
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait_unless(full0 + sb * 8, pb, okf);
-              tc_fence_after();
-              const uint32_t b_lo = lo_const | (((b_ring0 + static_cast<uint32_t>(sb) * bbytes) & 0x3ffffu) >> 4);
-              const uint32_t fb = empty0 + sb * 8;
-              if (++sb == nstages) { sb = 0; pb ^= 1u; }
-              const uint32_t r = static_cast<uint32_t>(tap) / 3u, c = static_cast<uint32_t>(tap) - 3u * r;
-              const uint32_t shift = r * halo_rowstep + c * (ROWB >> 4);
-              const uint32_t accum = (kb | tap) ? 1u : 0u;
-              if (!(dbg & 2)) {
-                okf = umma_bf16_ss_x4_waitahead(d0, a_hi | (a0_lo + shift), b_hi | b_lo, idesc, accum, full0 + sb * 8, pb);
-                if (two) {
+            if (mine) { mbar_wait_a(afull0 + sa * 8, pa); tc_fence_after(); }
+            const uint32_t a_lo = a_lo_base + static_cast<uint32_t>(sa) * astep;
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_bf16_ss(d1, a_hi | (a1_lo + shift + 2 * k), b_hi | (b_lo + 2 * k), idesc, (accum | k) ? 1u : 0u);
-                }
-              } else okf = mbar_try_wait_a(full0 + sb * 8, pb);
-              umma_commit_a(fb);                                // the weight slot is free once these MMAs retire
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait_unless(fullb, pb, okf);
+              tc_fence_after();
+              uint32_t nfullb = fullb + 8, nb_lo = b_lo + bstep, npb = pb;
+              if (++sb == nstages) { sb = 0; nfullb = full0; nb_lo = b_lo0; npb ^= 1u; }
+              const uint32_t shift = static_cast<uint32_t>(tap / 3) * halo_rowstep + static_cast<uint32_t>(tap % 3) * (ROWB >> 4);
+              if (mine && !(dbg & 2)) {
+                okf = umma_bf16_ss_x4_waitahead(d, a_hi | (a_lo + shift), b_hi | b_lo, idesc, (kb | tap) ? 1u : 0u, nfullb, npb);
+                umma_commit_a(fullb + e_minus_f);                          // one of the two arrivals that free the weight stage
+              } else {
+                okf = mbar_try_wait_a(nfullb, npb);
+                mbar_arrive_a(fullb + e_minus_f);
+              }
+              fullb = nfullb; b_lo = nb_lo; pb = npb;
             }
-            umma_commit_a(aempty0 + sa0 * 8);
-            if (two) umma_commit_a(aempty0 + sa1 * 8);
-            if (two) { sa = sa1 + 1; pa = pa1; } else { sa = sa0 + 1; }
-            if (sa == na) { sa = 0; pa ^= 1u; }
+            if (mine) umma_commit_a(aempty0 + sa * 8);
+            sa += two ? 2 : 1;
+            if (sa >= na) { sa -= na; pa ^= 1u; }
           }
-          umma_commit_a(tfull0 + slot0 * 8);
-          if (two) umma_commit_a(tfull0 + (slot0 + 1) * 8);
+          if (mine) umma_commit_a(tfull0 + slot * 8);
         }
       } else
       if constexpr (HALO) {
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
         // ---------------- fused Detect tail: SiLU tile (2 x 32 channels, bf16, 64B swizzle) -> second GEMM -> fp32 out ----------------
         static_assert(!FUSE2 || ((MODE == 3 || MODE == 5) && CW == 32 && !F32), "fused tail: 64 output channels, 32-wide chunks");
         const uint32_t d2b = smem_u32(&d2_bar[g]);
-        const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(kTmemCols - 128 + 64 * g);       // this group's private columns
+        const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(kTmemCols - 64 * EG + 64 * g);   // this group's private columns
         if (leader) bulk_wait_group_read<0>();       // the previous tile's output stores have read the staging memory
         named_bar_sync(barid, 128);
 #pragma unroll
@@ -1267,6 +1266,8 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   const int b_all = p->ntaps * p->kblocks * b_tile + (fuse2 ? p->N2 * 128 : 0);
   const int bias_bytes = (fuse2 ? 576 : round_up(p->n_tiles * p->BN + 64, 4)) * 4;
   p->eg = ((mode == 4 || (mode == 3 && !fuse2 && env_int("DY_CONV_EG3_M3", 1))) && cw == 32 && !f32 && p->BN <= 64 && !env_int("DY_CONV_EG2", 0)) ? 3 : 2;   // epilogue groups
+  // fused Detect tails: ~6000 cycles of serial epilogue chain per tile and group against a ~1750-cycle mainloop -> a third group
+  if (fuse2 && mode == 3 && env_int("DY_TAIL_EG3", 1)) p->eg = 3;
   int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
   if (p->nbuf == 1 && halo && !paired && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
@@ -1280,7 +1281,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     // tiles (one per tap and block, 8 MMAs each when paired): the weight ring takes what the halo ring leaves
     p->b_resident = 0;
     p->a_stage_bytes = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
-    p->a_stages = env_int("DY_PAIRED_ASTAGES", 4);
+    p->a_stages = env_int("DY_PAIRED_ASTAGES", 4) & ~1;                      // even: each of the two MMA issuers keeps its own slot parity
     p->stage_bytes = b_tile;
     int stages = (budget - p->a_stages * p->a_stage_bytes) / p->stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -1321,10 +1322,10 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     const int overrun = cw ? (ceil_div(p->BN, cw) * cw - p->BN) : (ceil_div(p->BN, 32) * 32 - p->BN);
     int nacc = (kTmemCols - overrun) / p->BN;
     if (nacc > kMaxAcc) nacc = kMaxAcc;
-    if (fuse2 && nacc > (kTmemCols - 128) / p->BN) nacc = (kTmemCols - 128) / p->BN;   // the last 128 columns hold the two tail accumulators
+    if (fuse2 && nacc > (kTmemCols - 64 * p->eg) / p->BN) nacc = (kTmemCols - 64 * p->eg) / p->BN;   // the last 64 columns per group hold the tail accumulators
     if (halo) nacc &= ~1;
     if (paired) nacc = nacc >= 4 ? 4 : 0;                                   // the issuer addresses accumulator slots as tile & 3
-    if (p->eg == 3) nacc = nacc >= 6 ? 6 : 0;                               // even (two MMA issuers) and a multiple of the three groups
+    if (p->eg == 3 && !fuse2) nacc = nacc >= 6 ? 6 : 0;                     // even (two MMA issuers) and a multiple of the three groups
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;
   }
@@ -1383,7 +1384,7 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 0: return conv_launch_m<0>(p, l, stream);
     case 1: return conv_launch_m<1>(p, l, stream);
     case 2: return conv_launch_m<2>(p, l, stream);
-    case 3: return p->fuse2 ? conv_launch_t<3, 32, false, true>(p, l, stream)
+    case 3: return p->fuse2 ? (p->eg == 3 ? conv_launch_t<3, 32, false, true, 3>(p, l, stream) : conv_launch_t<3, 32, false, true>(p, l, stream))
                             : (p->eg == 3 ? conv_launch_t<3, 32, false, false, 3>(p, l, stream) : conv_launch_m<3>(p, l, stream));
     case 4: return p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream);
     case 6: return conv_launch_t<6, 32, false>(p, l, stream);

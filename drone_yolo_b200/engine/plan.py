@@ -54,8 +54,10 @@ class LayerPlan:
         self.fuse_cv1 = not os.environ.get("DY_NO_FUSE_CV1")
         # side lanes for the Detect branches (dy_program_set_lane): 0 = everything on the caller's stream in layer order,
         # 1 = the branches of every level on one side stream, 2 = box branch and class branch on two side streams.  A level's
-        # branches are emitted as soon as its source layer is done, so they overlap the rest of the neck.
-        self.head_lanes = int(os.environ.get("DY_HEAD_LANES", "2")) if head_lanes is None else int(head_lanes)
+        # branches are emitted as soon as its source layer is done, so they overlap the rest of the neck.  Measured on the
+        # power-capped s@640 B=64 step (profiles/r02_summary.md): 17.55 k images/s with 0, 1 or 2 lanes alike (the persistent
+        # kernels hold one CTA per SM, so a second lane only fills partial waves) -> off by default.
+        self.head_lanes = int(os.environ.get("DY_HEAD_LANES", "0")) if head_lanes is None else int(head_lanes)
         self.lane = 0
         self.fuse_decode = (bool(fuse_decode) and self.fuse_tail and not os.environ.get("DY_NO_FUSE_DECODE")
                             and y is not None and mb == y.shape[0])

@@ -12,10 +12,29 @@ NMS_CASES = {
     "agnostic": dict(conf_thres=0.001, iou_thres=0.5, max_det=100, agnostic=True),
     "classes": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, classes=[1, 3, 7]),
     "maxnms": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=200),
-    "predict": dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+    "predict": dict(conf_thres=None, iou_thres=0.45, max_det=300),       # conf: the fixture's `predict_conf` (a few dozen rows survive)
 }
 REGIMES = ("sparse", "vallike", "dense")
 CONV_FIXTURES = ("n_repvgg_128", "n_repvgg_sf_64", "n_p2_64", "s_repvgg_64")
+
+
+def nms_case(g, case):
+    kw = dict(NMS_CASES[case])
+    if kw["conf_thres"] is None:
+        kw["conf_thres"] = float(g["predict_conf"])
+    return kw
+
+
+def frames_of(g):
+    """The raw uint8 BGR frames of a predict fixture, regenerated from its seeds (tools/make_golden.py predict_fixture)."""
+    frames = []
+    for i, (h, w) in enumerate(g["shapes"].tolist()):
+        f = np.random.RandomState(int(g["frame_seed0"]) + i).randint(0, 256, (h, w, 3), dtype=np.uint8)
+        yy, xx = np.mgrid[0:h, 0:w]
+        ramp = ((np.sin(xx / 17.0 + i) + np.cos(yy / 23.0)) * 50 + 128).clip(0, 255).astype(np.uint8)
+        f[...] = (f.astype(np.uint16) // 4 + ramp[..., None].astype(np.uint16) * 3 // 4).astype(np.uint8)
+        frames.append(f)
+    return frames
 
 
 def build_model(g):
@@ -42,12 +61,69 @@ def test_decode_oracle_matches_reference(golden_dir, regime):
 @pytest.mark.parametrize("case", sorted(NMS_CASES))
 def test_nms_oracle_bit_exact_vs_reference(golden_dir, regime, case):
     g = np.load(golden_dir / f"decode_nms_{regime}.npz")
-    out, kept = nms_np.non_max_suppression(g["y"], return_kept=True, **NMS_CASES[case])
+    out, kept = nms_np.non_max_suppression(g["y"], return_kept=True, **nms_case(g, case))
     for b in range(int(g["B"])):
         ref_rows, ref_kept = g[f"{case}_out{b}"], g[f"{case}_kept{b}"]
         assert out[b].shape == ref_rows.shape, (regime, case, b)
         assert np.array_equal(out[b].view(np.uint32), ref_rows.view(np.uint32)), (regime, case, b)   # bit-exact rows
         assert np.array_equal(kept[b], ref_kept), (regime, case, b)                                   # and kept indices
+    if case == "predict":
+        assert min(g[f"predict_out{b}"].shape[0] for b in range(int(g["B"]))) >= 20, "the predict case must not be vacuous"
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+@pytest.mark.parametrize("case", ["default", "multilabel", "predict"])
+def test_nms_oracle_bit_exact_vs_reference_34k(golden_dir, regime, case):
+    """BASELINE config 4 at its real size (34 000 anchors, one image), rows and kept indices written by the real reference.
+    Dense: 33 5xx candidates > max_nms, so the reference's truncation ran (tools/make_golden.py asserted that its unstable
+    argsort gave the stable order's result on this vector)."""
+    g = np.load(golden_dir / f"decode_nms_{regime}_34k.npz")
+    assert g["y"].shape == (1, 14, 34000)
+    out, kept = nms_np.non_max_suppression(g["y"], return_kept=True, **nms_case(g, case))
+    assert np.array_equal(out[0].view(np.uint32), g[f"{case}_out0"].view(np.uint32)), (regime, case)
+    assert np.array_equal(kept[0], g[f"{case}_kept0"]), (regime, case)
+    if regime == "dense" and case == "default":
+        assert int((g["y"][0, 4:].max(0) > 0.001).sum()) > 30000
+
+
+@pytest.mark.parametrize("tag", ["ragged", "rect"])
+def test_predict_pre_and_post_processing_vs_reference(golden_dir, tag):
+    """The reference's YOLO.predict on raw frames, with the conv stack factored out: (1) the letterbox restatement reproduces
+    the tensor its preprocess handed to the model, (2) the NMS oracle on the tensor its model handed to NMS followed by THIS
+    package's scale_boxes / clip_boxes (the host post-step the predictor runs) reproduces its `boxes.data`, bit for bit."""
+    from oracle import letterbox_np
+    from drone_yolo_b200.utils import ops
+
+    g = np.load(golden_dir / f"predict_{tag}.npz")
+    frames = frames_of(g)
+    same = len({f.shape for f in frames}) == 1
+    imgsz = int(g["imgsz"])
+    canv = np.stack([letterbox_np.letterbox_chw_rgb(f, (imgsz, imgsz), auto=same) for f in frames])
+    assert canv.shape == g["im_u8"].shape and np.array_equal(canv, g["im_u8"])
+    out = nms_np.non_max_suppression(g["y"], float(g["conf"]), float(g["iou"]), max_det=int(g["max_det"]))
+    for b, rows in enumerate(out):
+        t = torch.from_numpy(rows.copy())
+        t[:, :4] = ops.scale_boxes(canv.shape[2:], t[:, :4], tuple(int(v) for v in g[f"orig_shape{b}"]))
+        want = g[f"boxes{b}"]
+        assert t.shape == want.shape and want.shape[0] >= 10
+        assert np.array_equal(t.numpy().view(np.uint32), want.view(np.uint32)), (tag, b)
+        padded = torch.zeros((1, int(g["max_det"]), 6))                      # the predictor's batched form of the same arithmetic
+        padded[0, : rows.shape[0]] = torch.from_numpy(rows)
+        ops.scale_boxes_batch(canv.shape[2:], padded[..., :4], [tuple(int(v) for v in g[f"orig_shape{b}"])])
+        assert np.array_equal(padded[0, : rows.shape[0]].numpy().view(np.uint32), want.view(np.uint32)), (tag, b)
+
+
+def test_convstack_oracle_matches_reference_at_640(golden_dir):
+    """BASELINE config 2's model (Drone-YOLO-s) at 640x640, one image: raw maps stored as fp16."""
+    g = np.load(golden_dir / "convstack_s_repvgg_640_big.npz")
+    m = build_model(g)
+    x = recipe.images(1, 640, 640, int(g["image_seed"]))
+    y, raw = torch_ref.forward(m, x)
+    assert y.shape == (1, 14, 34000)
+    for i, r in enumerate(raw):
+        np.testing.assert_allclose(r.numpy(), g[f"raw{i}"].astype(np.float32), rtol=2e-3, atol=2e-3)      # fp16 storage
+    np.testing.assert_allclose(y[:, :4], g["y"][:, :4], rtol=0, atol=1e-2)
+    np.testing.assert_allclose(y[:, 4:], g["y"][:, 4:], rtol=1e-3, atol=1e-6)
 
 
 LABELS = [[[3.0, 40.0, 52.0, 30.0, 22.0], [7.0, 90.5, 30.25, 12.0, 44.0], [3.0, 41.0, 51.0, 28.0, 24.0]], []]   # tools/make_golden.py
