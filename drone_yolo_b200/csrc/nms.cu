@@ -11,13 +11,15 @@
 //            so ascending key order == descending score, ties broken by the lower candidate index: the order
 //            torchvision's stable descending sort produces.
 //  kernel 2  nms_select_kernel   one CTA per image
-//            repeatedly (a) radix-selects the next 512 smallest keys (MSD histogram passes in shared memory),
+//            repeatedly (a) selects the next <= 4096 smallest keys: one histogram pass over score bins spread over
+//            (conf, 1] when the bin holding the wanted rank is small enough to take whole, else exact MSD radix passes,
 //            (b) bitonic-sorts them, (c) builds class-offset boxes `xyxy + cls*max_wh` (:305-311) exactly as fp32
 //            torch ops do (no FMA contraction), (d) suppresses them against the boxes kept so far, (e) builds the
 //            512x512 upper-triangular IoU>thr bitmask in shared memory and (f) lets one warp do the greedy scan.
 //            Stops at max_det kept boxes (:313) or after max_nms candidates (:301-302); writes rows
 //            (x1,y1,x2,y2,conf,cls), the per-image count and (optionally) the reference's kept indices.
 #include "dy_common.cuh"
+#include <cstring>
 
 namespace dy {
 
@@ -28,7 +30,8 @@ static constexpr int kK = 512;                 // candidates per greedy round (=
 static constexpr int kWords = kK / 32;
 static constexpr int kBins = 2048;
 static constexpr int kBig = 4096;               // keys selected + sorted per super-round
-static constexpr int kFirst = 2048;             // ... of the first super-round (half the select + sort cost)
+static constexpr int kFirst = 1024;             // ... of the first super-round: the bitonic sort costs n log^2 n (2048 keys: 31 k clocks, 1024:
+                                                // 13 k) and most images reach max_det within their first few hundred ranks
 static constexpr int kMaxPasses = 8;
 static constexpr int kMaxClassWords = 32;      // class filter bitmask: nc <= 1024
 
@@ -43,6 +46,7 @@ struct NmsParams {
   unsigned long long cap;                      // candidate capacity per image
   unsigned long long* keys;                    // [B][cap]
   int* img_count;                              // [B]
+  unsigned int bin_base; int bin_shift;        // score bins of the one-pass selection: bin = (~score_bits - bin_base) >> bin_shift
   int* chunk_base;                             // [B][nchunks]
   int* chunk_cnt;                              // [B][nchunks]
   float* out; int* counts; long long* kept;
@@ -246,8 +250,8 @@ __device__ __forceinline__ bool iou_decide(const float4& a, float area_a, const 
 // debug builds only: per-image clock totals of the select kernel's phases (tools/trace_nms.py)
 __device__ unsigned long long g_nms_trace[1024 * 16];
 #define NMS_T0() long long t_ph = clock64()
-#define NMS_TP(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_now = clock64(); g_nms_trace[(blockIdx.x & 1023) * 16 + (k)] += t_now - t_ph; t_ph = t_now; } } while (0)
-#define NMS_TC(k, v) do { if (threadIdx.x == 0) g_nms_trace[(blockIdx.x & 1023) * 16 + (k)] += (v); } while (0)
+#define NMS_TP(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_now = clock64(); g_nms_trace[(b & 1023) * 16 + (k)] += t_now - t_ph; t_ph = t_now; } } while (0)
+#define NMS_TC(k, v) do { if (threadIdx.x == 0) g_nms_trace[(b & 1023) * 16 + (k)] += (v); } while (0)
 #else
 #define NMS_T0()
 #define NMS_TP(k)
@@ -263,6 +267,7 @@ struct SelShared {
   unsigned int remv[kWords];
   unsigned int undw[kWords], keptw[kWords];   // greedy fixed point: undecided / kept candidates, one word per warp
   int scan_tmp[kSelThreads / 32];
+  int max_tmp[kSelThreads / 32];
   unsigned short kidx[kK];
   int sel_count;
   int kept;
@@ -289,9 +294,17 @@ __device__ __forceinline__ void load_offset_box(const NmsParams& p, const float*
   *area = __fmul_rn(__fsub_rn(box->z, box->x), __fsub_rn(box->w, box->y));
 }
 
+__device__ __forceinline__ unsigned int score_bin(const NmsParams& p, unsigned long long key) {
+  const unsigned int u = static_cast<unsigned int>(key >> 32);
+  if (u <= p.bin_base) return 0u;
+  const unsigned int v = (u - p.bin_base) >> p.bin_shift;
+  return v < static_cast<unsigned>(kBins - 1) ? v : static_cast<unsigned>(kBins - 1);
+}
+
 __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_constant__ NmsParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SelShared& s = *reinterpret_cast<SelShared*>(smem_raw);
+  const int b = blockIdx.x;
   // kept-box state lives behind SelShared: boxes, screening areas, areas, ranks, keys (mdp entries each; the entries past
   // the kept count hold a zero box and sarea = +inf, which the screen always rules out: the loop below reads 4 at a time)
   const int mdp = kept_pad(p.max_det);
@@ -302,7 +315,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   unsigned long long* kkey = reinterpret_cast<unsigned long long*>(krank + mdp);
   unsigned long long* big = reinterpret_cast<unsigned long long*>(smem_raw + kSelSharedBytes + kept_bytes(p.max_det));
 
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.img_count[b];
   const float* img = (p.in_place ? p.pred_rw : p.pred) + static_cast<size_t>(b) * (4 + p.nc) * static_cast<size_t>(p.A);
   const unsigned long long* keys = p.keys + static_cast<size_t>(b) * p.cap;
@@ -311,6 +324,16 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   for (int i = tid; i < mdp; i += kSelThreads) { kbox[i] = make_float4(0.f, 0.f, 0.f, 0.f); ksarea[i] = __int_as_float(0x7f800000); }
   __syncthreads();
 
+  // Are the scores spread over the bins of the one-pass selection?  A sample of 512 keys: if any warp finds 8 of its 32
+  // keys in one bin, the image has near-identical scores by the thousand (e.g. an untrained head) and takes the exact radix
+  // passes with warp-aggregated histograms, first super-round of 2048 - the path tuned for clustered, heavily suppressed boxes.
+  bool spread;
+  {
+    unsigned int bin = 0xffffffffu - static_cast<unsigned>(lane);         // distinct dummies for lanes without a key
+    if (tid < n) bin = score_bin(p, keys[tid]);
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    spread = !__syncthreads_or(__popc(peers) >= 8);
+  }
   NMS_T0();
   NMS_TC(11, n);
   int processed = 0;
@@ -319,11 +342,88 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
   bool done = false;
   while (processed < limit && !done) {
     // =============== super-round: the next SK (<= 4096) smallest keys, selected once and sorted in shared memory ===============
-    const int SK = min(first ? kFirst : kBig, limit - processed);   // most images reach max_det inside the first ~2000 ranks
+    // first super-round: everything when the image has at most 2048 candidates (one sort, rounds of 512: the clustered,
+    // heavily suppressed images need all of them anyway), else the top ~1024
+    const int cap = first ? ((!spread || n <= kBig / 2) ? kBig / 2 : kFirst) : kBig;
+    int SK = min(cap, limit - processed);
     unsigned long long prefix_val = 0ull, prefix_mask = 0ull;
     unsigned int k_rem = static_cast<unsigned>(SK);
     const bool take_all = (n - processed) <= SK;          // everything left fits: no selection needed
-    if (!take_all) {
+    if (take_all) SK = n - processed;
+    bool fast = false, bins_ok = false;
+    if (spread && (!take_all || SK <= kBig / 2)) {
+      // ---- one-pass selection: histogram of kBins score bins spread over (conf, 1]; the bin that holds rank SK is taken
+      //      WHOLE when everything up to it fits the sort buffer (a super-round may be any size; only the max_nms limit is
+      //      exact).  Identical scores by the thousand (one crowded bin) fall through to the exact radix passes below.
+      for (int i = tid; i < kBins; i += kSelThreads) s.hist[i] = 0u;
+      __syncthreads();
+      for (int i0 = 0; i0 < n; i0 += kSelThreads * 4) {
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kSelThreads + tid;
+          key[u] = (i < n) ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kSelThreads + tid;
+          // plain shared-memory atomics: only taken for well spread scores (see `spread` above), where the keys of a warp
+          // rarely share a bin and a match.any aggregation costs more than the conflicts it saves
+          if (i < n && (first || key[u] > prev_T)) atomicAdd(&s.hist[score_bin(p, key[u])], 1u);
+        }
+      }
+      __syncthreads();
+      const unsigned h0 = s.hist[tid * 4], h1 = s.hist[tid * 4 + 1], h2 = s.hist[tid * 4 + 2], h3 = s.hist[tid * 4 + 3];
+      const int mine = static_cast<int>(h0 + h1 + h2 + h3);
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+      unsigned int hmax = max(max(h0, h1), max(h2, h3));                 // most crowded bin (the counting sort below is
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, d));   // quadratic inside a bin)
+      if (lane == 31) { s.scan_tmp[warp] = incl; s.max_tmp[warp] = static_cast<int>(hmax); }
+      __syncthreads();
+      int wbase = 0;
+      for (int w = 0; w < warp; ++w) wbase += s.scan_tmp[w];
+      int crowd = 0;
+      for (int w = 0; w < kSelThreads / 32; ++w) crowd = max(crowd, s.max_tmp[w]);
+      bins_ok = crowd <= 192;
+      const unsigned int excl = static_cast<unsigned>(wbase + incl - mine);
+      if (!take_all && k_rem > excl && k_rem <= excl + static_cast<unsigned>(mine)) {
+        unsigned int below = excl; int bin = tid * 4; unsigned int cnt = h0;
+        if (k_rem > below + h0) { below += h0; bin++; cnt = h1;
+          if (k_rem > below + h1) { below += h1; bin++; cnt = h2;
+            if (k_rem > below + h2) { below += h2; bin++; cnt = h3; } } }
+        s.found_bin = bin; s.found_below = below; s.found_count = cnt;
+      }
+      __syncthreads();
+      // the rank-SK key sits in bin `found_bin`: take the bins BELOW it (slightly fewer than SK keys, so the sort size
+      // stays at the power of two SK was chosen for) unless they hold less than half of what was asked for (a crowded bin:
+      // then the bin itself too if everything fits, else the exact passes)
+      const unsigned int below = s.found_below, upto = s.found_below + s.found_count;
+      const unsigned int room = static_cast<unsigned>(min(cap, limit - processed));
+      int last_bin = -1;
+      if (take_all) last_bin = kBins - 1;                                  // every live key, T = ~0: the bins only serve the sort
+      else if (2u * below >= static_cast<unsigned>(SK)) { last_bin = s.found_bin - 1; SK = static_cast<int>(below); }
+      else if (upto <= room) { last_bin = s.found_bin; SK = static_cast<int>(upto); }
+      if (last_bin >= 0) {
+        fast = true;
+        // counting sort by bin (below): start offset of every bin, and a cursor per bin that the gather advances
+        unsigned int* start = s.mask;                                      // kBins + 1 words of the (idle) pair matrix
+        const unsigned int st[4] = {excl, excl + h0, excl + h0 + h1, excl + h0 + h1 + h2};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { start[tid * 4 + k] = st[k]; s.hist[tid * 4 + k] = st[k]; }
+        if (tid == kSelThreads - 1) start[kBins] = excl + static_cast<unsigned>(mine);
+        if (last_bin >= kBins - 1) prefix_val = ~0ull;
+        else {
+          const unsigned long long umax = static_cast<unsigned long long>(p.bin_base) +
+                                          ((static_cast<unsigned long long>(last_bin) + 1ull) << p.bin_shift) - 1ull;
+          prefix_val = umax >= 0xffffffffull ? ~0ull : ((umax << 32) | 0xffffffffull);
+        }
+      }
+      __syncthreads();                                                     // found_* are rewritten by the radix passes
+    }
+    if (!take_all && !fast) {
       for (int ps = 0; ps < p.npasses; ++ps) {
         const int shift = p.pass_shift[ps];
         const unsigned int dmask = (1u << p.pass_bits[ps]) - 1u;
@@ -385,7 +485,49 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
     const unsigned long long T = take_all ? ~0ull : prefix_val;
     NMS_TP(0); NMS_TC(9, 1);
 
-    // ---- gather keys in (prev_T, T] into big[] and bitonic-sort them ascending ----
+    // ---- gather keys in (prev_T, T] into big[] in ascending order ----
+    const bool csort = fast && bins_ok && SK <= kBig / 2;
+    if (csort) {
+      // Counting sort on the score bins of the one-pass selection: every taken key goes to the next free slot of its bin's
+      // segment (upper half of big[] as scratch), then finds its place inside the segment by counting the smaller keys of
+      // that segment (a bin holds a key or two; a crowded one costs its length per key, never correctness).  Three barrier
+      // intervals instead of the ~30 of a 1024-key bitonic network (21 k clocks per image).
+      unsigned long long* tmp = big + kBig / 2;
+      const unsigned int* start = s.mask;
+      for (int i0 = 0; i0 < n; i0 += kSelThreads * 4) {
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kSelThreads + tid;
+          key[u] = (i < n) ? keys[i] : ~0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kSelThreads + tid;
+          if (i < n && (first || key[u] > prev_T) && key[u] <= T) {
+            const unsigned int pos = atomicAdd(&s.hist[score_bin(p, key[u])], 1u);
+            tmp[pos] = key[u];
+            if (pos < static_cast<unsigned>(kK)) {               // a candidate of the first round: its four box values are ~1.5 us
+              const unsigned a = static_cast<unsigned>(key[u] & 0xffffffffull) / static_cast<unsigned>(p.nc);   // of HBM latency away
+#pragma unroll
+              for (int c = 0; c < 4; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(img + static_cast<size_t>(c) * p.A + a));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      NMS_TP(1);
+      for (int q = tid; q < SK; q += kSelThreads) {
+        const unsigned long long key = tmp[q];
+        const unsigned int bin = score_bin(p, key);
+        const unsigned int lo = start[bin], hi = start[bin + 1];
+        unsigned int r = lo;
+        for (unsigned int j = lo; j < hi; ++j) r += tmp[j] < key ? 1u : 0u;
+        big[r] = key;
+      }
+      __syncthreads();
+      NMS_TP(2);
+    } else {
     int npow = kK;                                   // sort size: next power of two >= SK (>= 512)
     while (npow < SK) npow <<= 1;
     if (tid == 0) s.sel_count = 0;
@@ -402,9 +544,15 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * kSelThreads + tid;
         const bool live = first ? true : (key[u] > prev_T);
-        if (i < n && live && key[u] <= T) {
-          const int slot = atomicAdd(&s.sel_count, 1);
-          if (slot < kBig) big[slot] = key[u];
+        const bool take = i < n && live && key[u] <= T;
+        const unsigned int takers = __ballot_sync(0xffffffffu, take);      // one shared-memory atomic per warp and trip
+        if (takers) {
+          const int leader = __ffs(takers) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&s.sel_count, __popc(takers));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          const int slot = base + __popc(takers & ((1u << lane) - 1u));
+          if (take && slot < kBig) big[slot] = key[u];
         }
       }
     }
@@ -443,9 +591,13 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       }
     }
     NMS_TP(2);
+    }
     // =============== greedy rounds of 512 candidates in sorted order ===============
-    for (int off = 0; off < SK; off += kK) {
-      const int K = min(kK, SK - off);
+    for (int off = 0, K = 0; off < SK; off += K) {
+      // Spread scores: the first round takes what the image can use if nothing were suppressed (max_det plus a quarter; the
+      // pair tests grow with K^2), every other round a full block (a round that falls short costs more than it saved).
+      K = min(kK, SK - off);
+      if (spread && processed + off == 0) K = min(K, (p.max_det + (p.max_det >> 2) + 32 + 31) & ~31);
       NMS_TC(10, 1);
       // ---- (c) class-offset boxes ----
       const bool have = tid < K;
@@ -701,17 +853,37 @@ int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
   while (hi > 0) { const int nb = hi >= 11 ? 11 : hi; p.pass_shift[np] = hi - nb; p.pass_bits[np++] = nb; hi -= nb; }
   p.npasses = np;
 
+  // score bins of the one-pass selection: candidates have conf < score (<= 1 for probabilities), i.e. the high key word
+  // u = ~score_bits lies in [~bits(1.0), ~bits(conf)); kBins bins of 2^shift float steps cover that range (scores above 1
+  // fall into bin 0, anything beyond the last bin into the last one: the order of bins is the order of keys)
+  {
+    const float cf = d->conf_thres > 0.f ? d->conf_thres : 0.f;
+    unsigned int cbits; memcpy(&cbits, &cf, 4);
+    const unsigned int one = 0x3f800000u;
+    const unsigned int range = cbits < one ? one - cbits : 0u;
+    int sh = 0;
+    while ((range >> sh) >= static_cast<unsigned>(kBins)) ++sh;
+    p.bin_base = ~one; p.bin_shift = sh;
+  }
+
   DY_CUDA(cudaMemsetAsync(p.img_count, 0, static_cast<size_t>(d->B) * 4, stream));
+  const size_t smem = kSelSharedBytes + kept_bytes(d->max_det) + static_cast<size_t>(kBig) * 8;
+  {
+    // the opt-in is per device: remember the largest request made on each one
+    static size_t smem_set[64] = {0};
+    int dev = 0;
+    DY_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
+      DY_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+    }
+  }
   dim3 fgrid(w.nchunks, d->B);
   nms_filter_kernel<<<fgrid, kFilterThreads, 0, stream>>>(p);
   int rc = launch_status("nms_filter_kernel");
   if (rc) return rc;
-  const size_t smem = kSelSharedBytes + kept_bytes(d->max_det) + static_cast<size_t>(kBig) * 8;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    DY_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
-  }
+  // A plain launch: as a programmatic dependent of the filter kernel the select CTAs were placed while filter CTAs still held
+  // most SMs - two per SM on the few that were free - and the issue-bound pair tests of a B = 64 batch ran twice as long.
   nms_select_kernel<<<d->B, kSelThreads, smem, stream>>>(p);
   return launch_status("nms_select_kernel");
 }

@@ -72,3 +72,16 @@ def synthetic_raw_maps(B: int, imgsz: int, nc: int, mu: float, seed: int = 1234)
 
 def ties_free(scores: np.ndarray) -> bool:
     return np.unique(scores).size == scores.size
+
+
+def predict_frames(shapes, seed0: int = 100):
+    """Raw uint8 BGR frames of the predict-level fixtures (tools/make_golden.py predict_fixture): seeded noise over a
+    low-frequency pattern, so that the letterbox resize has something to interpolate."""
+    frames = []
+    for i, (h, w) in enumerate(shapes):
+        f = np.random.RandomState(seed0 + i).randint(0, 256, (h, w, 3), dtype=np.uint8)
+        yy, xx = np.mgrid[0:h, 0:w]
+        ramp = ((np.sin(xx / 17.0 + i) + np.cos(yy / 23.0)) * 50 + 128).clip(0, 255).astype(np.uint8)
+        f[...] = (f.astype(np.uint16) // 4 + ramp[..., None].astype(np.uint16) * 3 // 4).astype(np.uint8)
+        frames.append(f)
+    return frames

@@ -21,9 +21,16 @@ NMS_CASES = {
     "agnostic": dict(conf_thres=0.001, iou_thres=0.5, max_det=100, agnostic=True),
     "classes": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, classes=[1, 3, 7]),
     "maxnms": dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=200),
-    "predict": dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+    "predict": dict(conf_thres=None, iou_thres=0.45, max_det=300),       # conf: the fixture's `predict_conf` (a few dozen rows survive)
 }
 STRIDES = [4.0, 8.0, 16.0, 32.0]
+
+
+def nms_case(g, case):
+    kw = dict(NMS_CASES[case])
+    if kw["conf_thres"] is None:
+        kw["conf_thres"] = float(g["predict_conf"])
+    return kw
 
 
 @pytest.fixture(scope="module")
@@ -306,9 +313,23 @@ def assert_nms_equal(out, counts, kept, ref_out, ref_kept):
 @pytest.mark.parametrize("case", sorted(NMS_CASES))
 def test_nms_bit_exact_vs_reference_golden(K, dev, golden_dir, regime, case):
     g = np.load(golden_dir / f"decode_nms_{regime}.npz")
-    out, counts, kept = run_nms(K, dev, g["y"], NMS_CASES[case])
+    out, counts, kept = run_nms(K, dev, g["y"], nms_case(g, case))
     B = int(g["B"])
     assert_nms_equal(out, counts, kept, [g[f"{case}_out{b}"] for b in range(B)], [g[f"{case}_kept{b}"] for b in range(B)])
+
+
+@pytest.mark.parametrize("regime", ["sparse", "vallike", "dense"])
+@pytest.mark.parametrize("case", ["default", "multilabel", "predict"])
+def test_nms_bit_exact_vs_reference_golden_34k(K, dev, golden_dir, regime, case):
+    """BASELINE config 4 at its real size: 34 000 anchors, rows and kept indices written by the REAL reference (dense: the
+    max_nms truncation ran on 33 5xx candidates)."""
+    g = np.load(golden_dir / f"decode_nms_{regime}_34k.npz")
+    out, counts, kept = run_nms(K, dev, g["y"], nms_case(g, case))
+    assert_nms_equal(out, counts, kept, [g[f"{case}_out0"]], [g[f"{case}_kept0"]])
+    # the same image inside a larger batch (other images differ): per-image independence at B = 8
+    y = np.concatenate([g["y"]] + [np.roll(g["y"], 17 * (i + 1), axis=2) for i in range(7)])
+    out, counts, kept = run_nms(K, dev, y, nms_case(g, case))
+    assert_nms_equal(out[:1], counts[:1], kept[:1], [g[f"{case}_out0"]], [g[f"{case}_kept0"]])
 
 
 @pytest.mark.parametrize("mu", [-11.0, -10.0, -7.5])
@@ -444,6 +465,58 @@ def test_model_vs_reference_golden(dev, golden_dir, tag, path):
         close(r, torch.from_numpy(g[f"raw{i}"].astype(np.float32)), 2e-2, 2e-2)      # north_star: rtol 2e-2
     assert float((y[:, :4].cpu() - torch.from_numpy(g["y"][:, :4])).abs().max()) < 0.5   # north_star: 0.5 px
     close(y[:, 4:], torch.from_numpy(g["y"][:, 4:]), 2e-2, 1e-4)
+
+
+def test_model_vs_reference_golden_s640(dev, golden_dir):
+    """BASELINE config 2's model at its real resolution (one image) against the real reference's fp32 outputs: raw maps
+    rtol 2e-2 (stored fp16), decoded boxes 0.5 px; the engine with the decode fused into the conv tails gives the same y."""
+    from drone_yolo_b200.engine.engine import Engine
+
+    g = np.load(golden_dir / "convstack_s_repvgg_640_big.npz")
+    m = build(g, dev).to(dev).fuse(verbose=False)
+    x = recipe.images(1, 640, 640, int(g["image_seed"])).to(dev)
+    eng = Engine(m, 1, 640, dev, conf=0.001, iou=0.7, fuse_decode=False)
+    eng(x)
+    for i, r in enumerate(eng.raw_maps()):
+        close(r, torch.from_numpy(g[f"raw{i}"].astype(np.float32)), 2e-2, 3e-2)
+    for e in (eng, Engine(m, 1, 640, dev, conf=0.001, iou=0.7)):
+        if e is not eng:
+            e(x)
+        assert float((e.y[:, :4].cpu() - torch.from_numpy(g["y"][:, :4])).abs().max()) < 0.5
+        close(e.y[:, 4:], torch.from_numpy(g["y"][:, 4:]), 2e-2, 1e-4)
+
+
+@pytest.mark.parametrize("tag", ["ragged", "rect"])
+def test_predict_pre_and_post_processing_vs_reference(K, dev, golden_dir, tag):
+    """The reference's YOLO.predict on raw frames with the conv stack factored out: the GPU letterbox reproduces the tensor
+    its preprocess handed to the model; the GPU NMS on the tensor its model handed to NMS, followed by the predictor's
+    postprocess (batched scale_boxes + clamp, Results), reproduces its `boxes.data` bit for bit."""
+    from drone_yolo_b200.engine.predictor import DetectionPredictor, letterbox_geometry
+
+    g = np.load(golden_dir / f"predict_{tag}.npz")
+    frames = recipe.predict_frames([tuple(v) for v in g["shapes"].tolist()], int(g["frame_seed0"]))
+    same = len({f.shape for f in frames}) == 1
+    imgsz = int(g["imgsz"])
+    H, W = g["im_u8"].shape[2:]
+    canv = torch.zeros((len(frames), 3, H, W), dtype=torch.uint8, device=dev)
+    for i, f in enumerate(frames):
+        geo = letterbox_geometry(f.shape[:2], (imgsz, imgsz), auto=same)
+        assert (geo[4], geo[5]) == (H, W)
+        K.letterbox_u8(torch.from_numpy(f).to(dev), canv[i], geo[0], geo[1], geo[2], geo[3])
+    assert np.array_equal(canv.cpu().numpy(), g["im_u8"]), "letterbox differs from the reference's preprocess"
+    out, counts, _ = K.nms(torch.from_numpy(g["y"]).to(dev), float(g["conf"]), float(g["iou"]), max_det=int(g["max_det"]))
+    pred = DetectionPredictor(overrides=dict(conf=float(g["conf"]), iou=float(g["iou"]), max_det=int(g["max_det"])))
+
+    class _Names:
+        names = {i: str(i) for i in range(10)}
+
+    pred.model = _Names()
+    res = pred.postprocess((out, counts), canv, frames, [f"image{i}.jpg" for i in range(len(frames))])
+    for b, r in enumerate(res):
+        want = g[f"boxes{b}"]
+        got = r.boxes.data.cpu().numpy()
+        assert got.shape == want.shape and r.orig_shape == tuple(int(v) for v in g[f"orig_shape{b}"])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (tag, b)
 
 
 @pytest.mark.parametrize("scale,imgsz,B,mb", [("s", 640, 4, 2), ("n", 320, 3, 1), ("x", 320, 2, 2), ("m", 256, 2, 1),

@@ -26,24 +26,8 @@ def nms_case(g, case):
 
 
 def frames_of(g):
-    """The raw uint8 BGR frames of a predict fixture, regenerated from its seeds (tools/make_golden.py predict_fixture)."""
-    frames = []
-    for i, (h, w) in enumerate(g["shapes"].tolist()):
-        f = np.random.RandomState(int(g["frame_seed0"]) + i).randint(0, 256, (h, w, 3), dtype=np.uint8)
-        yy, xx = np.mgrid[0:h, 0:w]
-        ramp = ((np.sin(xx / 17.0 + i) + np.cos(yy / 23.0)) * 50 + 128).clip(0, 255).astype(np.uint8)
-        f[...] = (f.astype(np.uint16) // 4 + ramp[..., None].astype(np.uint16) * 3 // 4).astype(np.uint8)
-        frames.append(f)
-    return frames
-
-
-def build_model(g):
-    from drone_yolo_b200.nn.tasks import DetectionModel
-
-    torch.manual_seed(int(g["model_seed"]))
-    m = DetectionModel(str(g["yaml"]), nc=int(g["nc"]), verbose=False)
-    recipe.apply_recipe(m, int(g["bn_seed"]), float(g["cls_delta"]))
-    return m.eval()
+    """The raw uint8 BGR frames of a predict fixture, regenerated from its seeds."""
+    return recipe.predict_frames([tuple(v) for v in g["shapes"].tolist()], int(g["frame_seed0"]))
 
 
 @pytest.mark.parametrize("regime", REGIMES)

@@ -139,12 +139,7 @@ def predict_fixture(tasks, tag, shapes, imgsz=128, conf=0.001, iou=0.7, max_det=
     torch.manual_seed(0)
     yolo = YOLO(str(tmp / "yolov8n-p2-repvgg.yaml"))
     recipe.apply_recipe(yolo.model)
-    frames = [np.random.RandomState(100 + i).randint(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(shapes)]
-    # low-frequency content on top of the noise so that the resize has something to interpolate
-    for i, f in enumerate(frames):
-        yy, xx = np.mgrid[0:f.shape[0], 0:f.shape[1]]
-        ramp = ((np.sin(xx / 17.0 + i) + np.cos(yy / 23.0)) * 50 + 128).clip(0, 255).astype(np.uint8)
-        f[...] = (f.astype(np.uint16) // 4 + ramp[..., None].astype(np.uint16) * 3 // 4).astype(np.uint8)
+    frames = recipe.predict_frames(shapes, 100)
     seen = {}
     real_nms = ops.non_max_suppression
 
