@@ -62,6 +62,7 @@ class NmsDesc(C.Structure):
         ("xyxy_in_place", C.c_int32),
         ("out", C.c_void_p), ("counts", C.c_void_p), ("kept", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("rescale", C.c_void_p),
     ]
 
 

@@ -33,12 +33,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached) return cached;
+  static int cached[64] = {0};
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-    return 148;
-  cached = n;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 

@@ -172,11 +172,9 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(__nv_bfloat16* 
 
 template <int NV>
 static int sppf_pool_launch_nv(void* buf, int B, int H, int W, int C, int ld, size_t smem, cudaStream_t stream) {
-  static size_t smem_set = 48 * 1024;
-  if (smem > smem_set) {
-    DY_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
-  }
+  static unsigned long long seen = 0;                       // per device: the opt-in up to the 227 KB limit, once
+  if (smem > 48 * 1024 && first_use_on_device(&seen))
+    DY_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   sppf_pool_kernel<NV><<<B * (C / (8 * NV)), kPoolThreads, smem, stream>>>(static_cast<__nv_bfloat16*>(buf), H, W, C, ld);
   return launch_status("sppf_pool_kernel");
 }

@@ -1350,11 +1350,10 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
 
 template <int MODE, int CW, bool F32, bool FUSE2 = false, int EG = 2>
 static int conv_launch_t(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
-  static int max_smem_set = 0;
-  if (max_smem_set < l->smem_bytes) {
+  static unsigned long long seen = 0;                        // one bit per device: the opt-in is a per-device attribute
+  if (first_use_on_device(&seen)) {
     // 227 KB opt-in limit covers static + dynamic shared memory; the kernel's static part (barriers) is < 1 KB
     DY_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<MODE, CW, F32, FUSE2, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    max_smem_set = kMaxDynSmem;
   }
   static const bool use_pdl = (getenv("DY_NO_PDL") == nullptr);
   cudaLaunchConfig_t cfg{};

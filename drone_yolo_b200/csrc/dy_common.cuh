@@ -32,7 +32,18 @@ inline int launch_status(const char* what) {
   return DY_OK;
 }
 
-int num_sms();   // SM count of the current device (cached)
+int num_sms();   // SM count of the current device (cached per device)
+
+// The dynamic shared-memory opt-in (cudaFuncAttributeMaxDynamicSharedMemorySize) is a per-DEVICE attribute of a kernel:
+// `seen` holds one bit per device ordinal; returns true the first time the calling thread's current device asks.
+inline bool first_use_on_device(unsigned long long* seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (*seen & bit) return false;
+  *seen |= bit;
+  return true;
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -50,6 +50,7 @@ struct NmsParams {
   int* chunk_base;                             // [B][nchunks]
   int* chunk_cnt;                              // [B][nchunks]
   float* out; int* counts; long long* kept;
+  const float* rescale;                        // optional [B][8]: pad_x, pad_y, gain, w0, h0 (scale_boxes + clip_boxes in the output phase)
   int npasses; int pass_shift[kMaxPasses]; int pass_bits[kMaxPasses];
 };
 
@@ -762,6 +763,14 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       const float cx = img[a], cy = img[A + a], hw = __fmul_rn(img[2 * A + a], 0.5f), hh = __fmul_rn(img[3 * A + a], 0.5f);
       x1 = __fsub_rn(cx, hw); y1 = __fsub_rn(cy, hh); x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
     }
+    if (p.rescale) {
+      // ops.scale_boxes (ops.py:92-127): boxes[..., 0/2] -= pad_x, [..., 1/3] -= pad_y, boxes[..., :4] /= gain (fp32, the
+      // Python scalar as float32), then ops.clip_boxes (:335-354): clamp to the original image
+      const float* rs = p.rescale + static_cast<size_t>(b) * 8;
+      const float px = rs[0], py = rs[1], g = rs[2], w0 = rs[3], h0 = rs[4];
+      x1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x1, px), g), 0.f), w0); y1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y1, py), g), 0.f), h0);
+      x2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x2, px), g), 0.f), w0); y2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y2, py), g), 0.f), h0);
+    }
     float* o = p.out + (static_cast<size_t>(b) * p.max_det + t) * 6;
     o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
     o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
@@ -841,6 +850,7 @@ int nms_launch(const dy_nms_desc* d, cudaStream_t stream) {
   p.chunk_base = reinterpret_cast<int*>(ws + w.chunk_base);
   p.chunk_cnt = reinterpret_cast<int*>(ws + w.chunk_cnt);
   p.out = d->out; p.counts = d->counts; p.kept = reinterpret_cast<long long*>(d->kept);
+  p.rescale = d->rescale;
 
   // MSD digit plan over the 64-bit key: 32 score bits, then the significant bits of anchor*nc+cls
   int np = 0;

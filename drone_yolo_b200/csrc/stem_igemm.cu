@@ -348,11 +348,10 @@ int stem_tc_launch(const void* in, int in_dtype, int B, int H, int W, const floa
   p.np = u8 ? 16 : 12;                                       // even: the two patch producers own alternate slots
   const int smem = 1024 + 8192 + kStemNA * kStemABytes + 2 * kStemEG * 8192 + p.np * ((p.patch_bytes + 1023) & ~1023);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[u8]) {
+  static unsigned long long seen[2] = {0, 0};                // the opt-in is per device
+  if (first_use_on_device(&seen[u8 ? 1 : 0])) {
     if (u8) DY_CUDA(cudaFuncSetAttribute(stem_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     else DY_CUDA(cudaFuncSetAttribute(stem_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set[u8] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStemThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;

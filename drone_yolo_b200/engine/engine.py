@@ -34,7 +34,7 @@ class Engine:
                  max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
                  max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True,
                  input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True, input_slots: int = 1,
-                 head_lanes: Optional[int] = None):
+                 head_lanes: Optional[int] = None, rescale: bool = False):
         device = torch.device(device)
         if device.type != "cuda":
             raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
@@ -59,15 +59,28 @@ class Engine:
                                   head_lanes=head_lanes)
             ml = bool(multi_label) and self.nc > 1
             self.nms_bufs = K.NmsBuffers(batch, self.nc, self.A, max_det, ml, device)
+            classes = K.normalize_classes(classes)
             self.nms_cfg = dict(conf=conf, iou=iou, max_det=max_det, classes=classes, agnostic=agnostic, multi_label=ml,
                                 max_nms=max_nms, max_wh=max_wh)
-            d = K.nms_desc(self.y, self.nms_bufs, conf, iou, max_det, max_nms, max_wh, agnostic, ml, classes,
-                           in_place=False, want_kept=True)
-            h = C.c_void_p()
-            _C.check(_C.lib().dy_program_create(C.byref(h)), "dy_program_create")
-            self._nms_prog = h
-            _C.check(_C.lib().dy_program_add_nms(h, C.byref(d)), "dy_program_add_nms")
-            self.launches_per_step = self.plan.launches * (batch // self.mb) + _C.lib().dy_program_num_launches(h)
+            # `rescale`: the NMS output phase also maps the rows to each original image (scale_boxes + clip_boxes, ops.py:92-127,
+            # 335-354); `self.rescale` holds (pad_x, pad_y, gain, w0, h0) per image, identity until the predictor fills it
+            # (one parameter block per input slot: the upload of batch i+1's block must not race the NMS of batch i)
+            self.rescale_slots = None
+            if rescale:
+                self.rescale_slots = torch.zeros((self.input_slots, batch, 8), device=device, dtype=torch.float32)
+                self.rescale_slots[..., 2] = 1.0
+                self.rescale_slots[..., 3] = float(W)
+                self.rescale_slots[..., 4] = float(H)
+            self._nms_progs = []
+            for k in range(self.input_slots if rescale else 1):
+                d = K.nms_desc(self.y, self.nms_bufs, conf, iou, max_det, max_nms, max_wh, agnostic, ml, classes,
+                               in_place=False, want_kept=True, rescale=self.rescale_slots[k] if rescale else None)
+                h = C.c_void_p()
+                _C.check(_C.lib().dy_program_create(C.byref(h)), "dy_program_create")
+                self._nms_progs.append(h)
+                _C.check(_C.lib().dy_program_add_nms(h, C.byref(d)), "dy_program_add_nms")
+            self._nms_prog = self._nms_progs[0]
+            self.launches_per_step = self.plan.launches * (batch // self.mb) + _C.lib().dy_program_num_launches(self._nms_prog)
             self.graph: Optional[torch.cuda.CUDAGraph] = None
             self.graphs: list = []
             self.enqueue()                       # eager warm-up (sets kernel attributes, pages in code)
@@ -85,19 +98,24 @@ class Engine:
 
     def enqueue(self, stream: Optional[int] = None, nms: bool = True, slot: int = 0):
         """Enqueue the whole step on `stream` (default: torch's current stream), reading input slot `slot`."""
-        s = _C.stream_ptr(self.device) if stream is None else stream
-        in_bytes = self.mb * 3 * self.H * self.W * self.images.element_size()
-        out_bytes = self.mb * (4 + self.nc) * self.A * 4
-        slot_bytes = self.batch * 3 * self.H * self.W * self.images.element_size()
-        for m in range(self.batch // self.mb):
-            self.plan.run(slot * slot_bytes + m * in_bytes, m * out_bytes, s)
-        if nms:
-            _C.check(_C.lib().dy_program_run(self._nms_prog, 0, 0, s), "dy_program_run(nms)")
+        with torch.cuda.device(self.device):       # the library launches on the calling thread's current device
+            s = _C.stream_ptr(self.device) if stream is None else stream
+            in_bytes = self.mb * 3 * self.H * self.W * self.images.element_size()
+            out_bytes = self.mb * (4 + self.nc) * self.A * 4
+            slot_bytes = self.batch * 3 * self.H * self.W * self.images.element_size()
+            for m in range(self.batch // self.mb):
+                self.plan.run(slot * slot_bytes + m * in_bytes, m * out_bytes, s)
+            if nms:
+                _C.check(_C.lib().dy_program_run(self._nms_progs[slot % len(self._nms_progs)], 0, 0, s), "dy_program_run(nms)")
 
     def step(self, slot: int = 0):
         """Run conv stack + decode + NMS on the resident batch of input slot `slot`; results in y / nms_bufs (no host sync)."""
         if self.graphs:
-            self.graphs[slot].replay()
+            if self.device.index != torch.cuda.current_device():
+                with torch.cuda.device(self.device):
+                    self.graphs[slot].replay()
+            else:
+                self.graphs[slot].replay()
         else:
             self.enqueue(slot=slot)
         return self.nms_bufs.out, self.nms_bufs.counts
@@ -114,7 +132,7 @@ class Engine:
 
     def __del__(self):
         try:
-            if getattr(self, "_nms_prog", None):
-                _C.lib().dy_program_destroy(self._nms_prog)
+            for h in getattr(self, "_nms_progs", []):
+                _C.lib().dy_program_destroy(h)
         except Exception:  # noqa: BLE001
             pass

@@ -93,7 +93,7 @@ class Model(nn.Module):
             self.predictor.setup_model(model=self.model)
         else:  # only update args (engine/model.py:555-557); engines are keyed by the settings they depend on
             dev_changed = "device" in kwargs and str(kwargs["device"]) != str(getattr(self.predictor.args, "device", None))
-            self.predictor.args.__dict__.update(args)
+            self.predictor.update_args(args)
             if dev_changed:
                 self.predictor.setup_model(model=self.model)
         return self.predictor(source=source, stream=stream)

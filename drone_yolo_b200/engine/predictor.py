@@ -3,13 +3,20 @@
 Mirror of the reference's BasePredictor / DetectionPredictor (ultralytics/engine/predictor.py:66-410,
 models/yolo/detect/predict.py:23-73) for the inference hot path: same constructor (`overrides`, `_callbacks`),
 `setup_model`, `__call__(source, stream)`, `preprocess`, `inference`, `postprocess`, the five `on_predict_*`
-callback events and `Results.speed`.  Differences: one batched D2H of the padded detections instead of per-image
-boolean-mask syncs; `orig_img` of tensor sources is produced lazily; boxes are rescaled on the host (<= max_det rows).
+callback events and `Results.speed`.  Differences:
+  * the batch loop (predictor.py:251-288) is a two-slot pipeline: batch i+1 is staged and uploaded (copy stream) while
+    batch i computes and batch i-1 is turned into Results on the host; no device-wide synchronisation, `Results.speed`
+    comes from CUDA events;
+  * one D2H of the padded detections per batch instead of per-image boolean-mask syncs; scale_boxes + clip_boxes run in
+    the NMS output phase (dy_nms_desc.rescale); `orig_img` of tensor sources is produced lazily;
+  * under torch.distributed (one process per GPU) every batch is sharded over the ranks and gathered to rank 0, which
+    builds the Results (the reference's `select_device("0,1")`, utils/torch_utils.py:202-219, silently uses cuda:0).
 """
 from __future__ import annotations
 
 import threading
 import time
+from collections import OrderedDict, deque
 from pathlib import Path
 from types import SimpleNamespace
 
@@ -18,13 +25,15 @@ import torch
 
 from .. import _C
 from .. import kernels as K
+from ..parallel import DetectionGather, shard_bounds, shard_of
 from ..utils import ops
 from .engine import Engine
 from .results import Results
 
 DEFAULTS = dict(task="detect", mode="predict", imgsz=640, batch=1, device=None, conf=0.25, iou=0.7, max_det=300,
                 half=False, classes=None, agnostic_nms=False, augment=False, stream=False, verbose=False,
-                micro_batch=0, cuda_graph=True, multi_label=False, gpu_preprocess=True, engine_cache=8, vid_stride=1)
+                micro_batch=0, cuda_graph=True, multi_label=False, gpu_preprocess=True, engine_cache=8, vid_stride=1,
+                dtype="bf16", distributed=True)
 IMG_FORMATS = {"bmp", "dng", "jpeg", "jpg", "mpo", "png", "tif", "tiff", "webp", "pfm"}                       # data/utils.py:38 (heic needs pillow-heif: not read)
 VID_FORMATS = {"asf", "avi", "gif", "m4v", "mkv", "mov", "mp4", "mpeg", "mpg", "ts", "wmv", "webm"}           # data/utils.py:39
 EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end", "on_predict_end")
@@ -71,12 +80,11 @@ class DetectionPredictor:
         args.update(overrides or {})
         if args.get("conf") is None:
             args["conf"] = 0.25
-        if args.get("augment"):
-            raise _C.DroneYoloError("augment=True (TTA) is outside the inference hot path")
         self.args = SimpleNamespace(**args)
+        self._check_args()
         self.model = None
         self.device = None
-        self.engines: dict = {}
+        self.engines: "OrderedDict" = OrderedDict()              # LRU: key -> Engine
         self.callbacks = {e: [] for e in EVENTS}
         for k, v in (_callbacks or {}).items():
             self.callbacks.setdefault(k, []).extend(v if isinstance(v, (list, tuple)) else [v])
@@ -85,7 +93,34 @@ class DetectionPredictor:
         self.save_dir = None
         self.seen = 0
         self._lock = threading.Lock()
-        self._pinned: dict = {}
+        self._pinned: "OrderedDict" = OrderedDict()              # LRU staging buffers (bounded, see _staging)
+        self._copy_stream = None
+        self._gather = None
+
+    def _check_args(self):
+        """Precision and TTA switches of the reference that this path cannot honour raise instead of being ignored.
+        `half` (cfg/default.yaml:54, autobackend.py:132,157): the reference's only precision switch, fp32 vs fp16.  Here the
+        conv stack ALWAYS runs bf16 with fp32 accumulation (raw maps within rtol 2e-2 of the fp32 reference) and decode + NMS
+        ALWAYS run fp32, so `half=True` and `half=False` are both accepted and select the same arithmetic; an explicit request
+        for another precision (`dtype="fp32"` / "fp16") raises."""
+        a = self.args
+        if getattr(a, "augment", False):
+            raise _C.DroneYoloError("augment=True (TTA) is outside the inference hot path")
+        if str(getattr(a, "dtype", "bf16")).lower() not in ("bf16", "bfloat16"):
+            raise _C.DroneYoloError(f"dtype={a.dtype!r}: the sm_100a conv stack is bf16 (fp32 accumulate; decode and NMS fp32) - there is "
+                                    "no fp32 / fp16 conv path; use the reference for those")
+        a.classes = K.normalize_classes(getattr(a, "classes", None))   # int / tensor / ndarray / list -> list of ints (mix6.py:80: classes=0)
+
+    def update_args(self, args: dict):
+        """Later predict() calls only update the arguments (engine/model.py:555-557); a rejected value is not kept."""
+        old = dict(self.args.__dict__)
+        self.args.__dict__.update(args)
+        try:
+            self._check_args()
+        except Exception:
+            self.args.__dict__.clear()
+            self.args.__dict__.update(old)
+            raise
 
     # ---- setup ---------------------------------------------------------------------------------
     def setup_model(self, model, verbose=False):
@@ -95,11 +130,19 @@ class DetectionPredictor:
             dev = "cuda:0"
         if isinstance(dev, int) or (isinstance(dev, str) and dev.isdigit()):
             dev = f"cuda:{dev}"
+        if isinstance(dev, str) and "," in dev:
+            # the reference accepts "0,1,.." and then runs on the first device only (torch_utils.py:202-219); multi-GPU here is
+            # one process per GPU under torchrun (each rank passes its own device), see _dist()
+            raise _C.DroneYoloError(f"device '{dev}': one process drives one GPU - launch with torchrun (one rank per GPU) to shard batches")
         self.device = torch.device(dev)
         if self.device.type != "cuda":
             raise _C.DroneYoloError(f"device '{dev}': drone_yolo_b200 has no CPU path (use the reference for CPU inference)")
         self.model = model.to(self.device).eval().fuse(verbose=False)
+        self._flush()
         self.engines.clear()
+        self._pinned.clear()
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._gather = None
 
     def add_callback(self, event, func):
         self.callbacks[event].append(func)
@@ -108,18 +151,53 @@ class DetectionPredictor:
         for cb in self.callbacks.get(event, []):
             cb(self)
 
+    def _dist(self):
+        """(world, rank) when batches are sharded over the ranks of an initialised process group, else (1, 0)."""
+        import torch.distributed as dist
+
+        if getattr(self.args, "distributed", True) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_world_size(), dist.get_rank()
+        return 1, 0
+
     def engine_for(self, B, H, W, dtype=torch.float32) -> Engine:
         a = self.args
-        key = (B, H, W, dtype, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes else None, a.agnostic_nms, a.multi_label,
-               a.micro_batch, a.cuda_graph)
-        if key not in self.engines:
-            held = sum(e.plan.arena_bytes for e in self.engines.values())            # engines hold their arenas: bounded by
-            if len(self.engines) >= max(int(getattr(a, "engine_cache", 8)), 1) or held > (48 << 30):   # count and by bytes
-                self.engines.clear()
-            self.engines[key] = Engine(self.model, B, (H, W), self.device, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou,
-                                       max_det=a.max_det, classes=a.classes, agnostic=a.agnostic_nms,
-                                       multi_label=a.multi_label, cuda_graph=a.cuda_graph, input_dtype=dtype)
-        return self.engines[key]
+        key = (B, H, W, dtype, a.conf, a.iou, a.max_det, tuple(a.classes) if a.classes is not None else None, a.agnostic_nms,
+               a.multi_label, a.micro_batch, a.cuda_graph)
+        eng = self.engines.get(key)
+        if eng is not None:
+            self.engines.move_to_end(key)
+            return eng
+        # engines hold their arenas: bounded by count and by bytes; the least recently used one goes first (never one with a
+        # batch in flight: `_inflight` is drained before anything is dropped)
+        limit = max(int(getattr(a, "engine_cache", 8)), 1)
+        while self.engines and (len(self.engines) >= limit or sum(e.plan.arena_bytes for e in self.engines.values()) > (48 << 30)):
+            self._flush()
+            self.engines.popitem(last=False)
+        eng = Engine(self.model, B, (H, W), self.device, micro_batch=a.micro_batch, conf=a.conf, iou=a.iou,
+                     max_det=a.max_det, classes=a.classes, agnostic=a.agnostic_nms, multi_label=a.multi_label,
+                     cuda_graph=a.cuda_graph, input_dtype=dtype, input_slots=2, rescale=True)
+        eng._next_slot = 0
+        eng._host = [None, None]                                # pinned (out, counts) per slot, allocated on first use
+        eng._slot_done = [None, None]                           # event: the step that last read the slot has finished
+        self.engines[key] = eng
+        return eng
+
+    def _staging(self, key, shape, device_too=True):
+        """Pinned host (+ device) staging pair for raw frames, one per (pipeline slot, position in the batch), grown to the
+        largest frame seen and bounded in number (LRU): a folder of mixed-size images no longer leaks a pair per shape."""
+        need = int(np.prod(shape))
+        ent = self._pinned.get(key)
+        if ent is None or ent[0].numel() < need:
+            host = torch.empty((need,), dtype=torch.uint8).pin_memory()
+            dev = torch.empty((need,), dtype=torch.uint8, device=self.device) if device_too else None
+            ent = (host, dev)
+            self._pinned[key] = ent
+            while len(self._pinned) > 4 * 256:                  # 2 slots x up to 512 positions
+                self._pinned.popitem(last=False)
+        else:
+            self._pinned.move_to_end(key)
+        host, dev = ent
+        return host[:need].view(shape), (dev[:need].view(shape) if dev is not None else None)
 
     # ---- source handling (reference data/build.py:186-219, data/loaders.py) ---------------------
     def _batches(self, source):
@@ -223,95 +301,198 @@ class DetectionPredictor:
         if imgs:
             yield paths, imgs, None
 
+    # ---- preprocess (predictor.py:118-163) -----------------------------------------------------------
     def preprocess(self, im0s):
-        """uint8 HWC BGR list -> pinned uint8 (B,3,H,W) RGB (predictor.py:118-131, 147-163).  Like the reference, the
-        batch crosses PCIe as uint8; its `.float()` and `/ 255` (predictor.py:133-135) happen on the device, here inside the
-        stem kernel."""
+        """uint8 HWC BGR list -> uint8 (B,3,H,W) RGB batch on the host (predictor.py:118-131, 147-163): the reference's own
+        host path (cv2 LetterBox + stack + BGR->RGB + HWC->CHW); its `.float()` and `/ 255` (:133-135) happen in the stem
+        kernel.  Used when `gpu_preprocess=False` or for frames the GPU letterbox does not take."""
         a = self.args
         shape = (a.imgsz, a.imgsz) if isinstance(a.imgsz, int) else tuple(a.imgsz)
         same = len({x.shape for x in im0s}) == 1
-        if getattr(a, "gpu_preprocess", True) and all(x.ndim == 3 and x.shape[2] == 3 and x.dtype == np.uint8 for x in im0s):
-            return self.preprocess_gpu(im0s, shape, same)
         lb = [letterbox(x, shape, auto=same) for x in im0s]
-        arr = np.ascontiguousarray(np.stack(lb)[..., ::-1].transpose(0, 3, 1, 2))
-        key = arr.shape
-        if key not in self._pinned:
-            self._pinned[key] = torch.empty(key, dtype=torch.uint8).pin_memory()
-        buf = self._pinned[key]
-        buf.copy_(torch.from_numpy(arr))
-        return buf
+        return torch.from_numpy(np.ascontiguousarray(np.stack(lb)[..., ::-1].transpose(0, 3, 1, 2)))
 
-    def preprocess_gpu(self, im0s, shape, same):
-        """The raw frames cross PCIe as they are (pinned staging, one buffer per frame size) and ONE kernel per frame does
-        resize + border + BGR->RGB + HWC->CHW straight into the engine's uint8 input batch (dy_letterbox_u8): the host's
-        cv2.resize / copyMakeBorder / stack / transpose (about 1 ms per 1080p frame on one core) disappear."""
+    def _canvas(self, im0s):
+        """(H, W, per-frame geometry or None) of the letterboxed batch; geometry None -> host path."""
+        a = self.args
+        shape = (a.imgsz, a.imgsz) if isinstance(a.imgsz, int) else tuple(a.imgsz)
+        same = len({x.shape for x in im0s}) == 1
         geo = [letterbox_geometry(x.shape[:2], shape, auto=same) for x in im0s]
         H, W = geo[0][4], geo[0][5]
-        if any((g[4], g[5]) != (H, W) for g in geo) or W % 4:
-            lb = [letterbox(x, shape, auto=same) for x in im0s]          # ragged canvases: the host path decides
-            return torch.from_numpy(np.ascontiguousarray(np.stack(lb)[..., ::-1].transpose(0, 3, 1, 2)))
-        eng = self.engine_for(len(im0s), H, W, torch.uint8)
-        for i, (x, g) in enumerate(zip(im0s, geo)):
-            x = np.ascontiguousarray(x)
-            key = ("raw", i, x.shape)
-            if key not in self._pinned:
-                self._pinned[key] = (torch.empty(x.shape, dtype=torch.uint8).pin_memory(),
-                                     torch.empty(x.shape, dtype=torch.uint8, device=self.device))
-            host, dev = self._pinned[key]
-            host.copy_(torch.from_numpy(x))
-            dev.copy_(host, non_blocking=True)
-            K.letterbox_u8(dev, eng.images[i], g[0], g[1], g[2], g[3])
-        return eng.images
+        ok = (getattr(a, "gpu_preprocess", True) and W % 4 == 0 and all((g[4], g[5]) == (H, W) for g in geo)
+              and all(x.ndim == 3 and x.shape[2] == 3 and x.dtype == np.uint8 for x in im0s))
+        return H, W, (geo if ok else None)
 
-    # ---- the loop --------------------------------------------------------------------------------
+    # ---- the loop (predictor.py:221-306) ------------------------------------------------------------------
     def __call__(self, source=None, model=None, stream=False):
         gen = self.stream_inference(source, model)
         return gen if stream else list(gen)
 
+    def _launch(self, paths, im0s, tensor):
+        """Stage + upload one batch into a free input slot (copy stream), enqueue its engine step and the D2H of its padded
+        detections (compute stream).  Nothing here waits for the device."""
+        world, rank = self._dist()
+        n_items = tensor.shape[0] if tensor is not None else len(im0s)
+        lo, hi = (0, n_items) if world == 1 else shard_bounds(n_items, world, rank)
+        b_local = n_items if world == 1 else -(-n_items // world)            # equal shards (the last ones padded): one collective
+        t0 = time.perf_counter()
+        compute = torch.cuda.current_stream(self.device)
+        cs = self._copy_stream
+        if tensor is not None:
+            im = tensor if tensor.dtype == torch.uint8 else tensor.float()
+            H, W = im.shape[2:]
+            eng = self.engine_for(b_local, H, W, im.dtype)
+            slot = eng._next_slot
+            if eng._slot_done[slot] is not None:
+                cs.wait_event(eng._slot_done[slot])
+            if im.is_cuda:
+                cs.wait_stream(torch.cuda.current_stream(im.device))       # the caller's tensor may still be being written
+            with torch.cuda.stream(cs):
+                if hi > lo:
+                    eng.image_slots[slot][: hi - lo].copy_(im[lo:hi], non_blocking=True)
+            oshapes = [(H, W)] * n_items
+            in_shape = (H, W)
+        else:
+            H, W, geo = self._canvas(im0s)
+            eng = self.engine_for(b_local, H, W, torch.uint8)
+            slot = eng._next_slot
+            if eng._slot_done[slot] is not None:
+                cs.wait_event(eng._slot_done[slot])
+            if geo is None:                                                # host letterbox (the reference's own path)
+                arr = self.preprocess(im0s[lo:hi]) if hi > lo else None
+                if arr is not None and tuple(arr.shape[2:]) != (H, W):
+                    raise _C.DroneYoloError("host letterbox produced another canvas than the planned one")
+                with torch.cuda.stream(cs):
+                    if arr is not None:
+                        host, _ = self._staging(("canvas", slot), tuple(arr.shape), device_too=False)
+                        host.copy_(arr)
+                        eng.image_slots[slot][: hi - lo].copy_(host, non_blocking=True)
+            else:
+                # raw frames cross PCIe as they are; ONE kernel per frame does resize + border + BGR->RGB + HWC->CHW straight
+                # into the engine's input slot (dy_letterbox_u8)
+                with torch.cuda.stream(cs):
+                    for j in range(lo, hi):
+                        x = np.ascontiguousarray(im0s[j])
+                        host, dev = self._staging(("raw", slot, j - lo), x.shape)
+                        host.copy_(torch.from_numpy(x))
+                        dev.copy_(host, non_blocking=True)
+                        g = geo[j]
+                        K.letterbox_u8(dev, eng.image_slots[slot][j - lo], g[0], g[1], g[2], g[3])
+            oshapes = [tuple(o.shape[:2]) for o in im0s]
+            in_shape = (H, W)
+        # per-image scale_boxes / clip_boxes parameters for the NMS output phase (this rank's shard)
+        rs = ops.rescale_params(in_shape, oshapes[lo:hi] + [in_shape] * (b_local - (hi - lo)))
+        rs_host, _ = self._staging(("rescale", slot, b_local), (b_local * 8 * 4,), device_too=False)
+        rs_host.view(torch.float32).view(b_local, 8).copy_(rs)
+        with torch.cuda.stream(cs):
+            eng.rescale_slots[slot].copy_(rs_host.view(torch.float32).view(b_local, 8), non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(cs)
+        eng._next_slot = slot ^ 1
+        t1 = time.perf_counter()
+        compute.wait_event(uploaded)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(compute)
+        out, counts = eng.step(slot)
+        e1.record(compute)
+        if world > 1:
+            if self._gather is None or self._gather.key != (b_local, self.args.max_det):
+                self._gather = DetectionGather(b_local, self.args.max_det, self.device)
+            out, counts = self._gather.gather(out, counts)
+        host_pair = eng._host[slot]
+        if host_pair is None or host_pair[0].shape != out.shape:
+            host_pair = eng._host[slot] = (torch.empty(out.shape, dtype=torch.float32).pin_memory(),
+                                           torch.empty(counts.shape, dtype=torch.int32).pin_memory())
+        if rank == 0:
+            host_pair[0].copy_(out, non_blocking=True)
+            host_pair[1].copy_(counts, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        eng._slot_done[slot] = done                                        # the upload after next into this slot waits for it
+        return dict(paths=paths, im0s=im0s, tensor=tensor, eng=eng, slot=slot, host=host_pair, done=done, e0=e0, e1=e1,
+                    pre_ms=(t1 - t0) * 1e3, n=n_items, in_shape=in_shape, oshapes=oshapes, world=world, rank=rank, b_local=b_local)
+
+    def _finish(self, rec):
+        """Wait for ONE batch (its own event, not the device), build Results on the host, run the callbacks."""
+        rec["done"].synchronize()
+        t2 = time.perf_counter()
+        self.batch = (rec["paths"], rec["im0s"], None)
+        if rec["rank"] != 0:
+            self.results = []                                              # rank 0 holds every detection of the batch
+        else:
+            self.results = self.construct_results(rec)
+        t3 = time.perf_counter()
+        self.run_callbacks("on_predict_postprocess_end")
+        n = max(rec["n"], 1)
+        speed = {"preprocess": rec["pre_ms"] / n, "inference": rec["e0"].elapsed_time(rec["e1"]) / n, "postprocess": (t3 - t2) * 1e3 / n}
+        for r in self.results:
+            r.speed = speed
+        self.seen += rec["n"]
+        if self.args.verbose:
+            for p, r in zip(rec["paths"], self.results):
+                print(f"{p}: {rec['in_shape'][0]}x{rec['in_shape'][1]} {r.verbose()}{speed['inference']:.2f}ms")
+        self.run_callbacks("on_predict_batch_end")
+        return self.results
+
+    def _flush(self):
+        """Drop the batches in flight (an engine is about to be evicted or the model replaced)."""
+        q = getattr(self, "_inflight", None)
+        if q:
+            for rec in q:
+                rec["done"].synchronize()
+            q.clear()
+
     def stream_inference(self, source=None, model=None):
         if self.model is None:
             self.setup_model(model)
-        with self._lock, torch.inference_mode():
+        self._check_args()
+        with self._lock, torch.inference_mode(), torch.cuda.device(self.device):
             self.run_callbacks("on_predict_start")
+            self._inflight = deque()
             for paths, im0s, tensor in self._batches(source):
                 self.run_callbacks("on_predict_batch_start")
                 self.batch = (paths, im0s, None)
-                t0 = time.perf_counter()
-                im = tensor if tensor is not None else self.preprocess(im0s)
-                B, _, H, W = im.shape
-                if im.dtype != torch.uint8:
-                    im = im.float()
-                eng = self.engine_for(B, H, W, im.dtype)
-                if im.data_ptr() != eng.images.data_ptr():         # the GPU preprocess writes the static input in place
-                    eng.images.copy_(im, non_blocking=True)        # H2D (or D2D) into the static input
-                torch.cuda.synchronize(self.device)
-                t1 = time.perf_counter()
-                out, counts = self.inference(eng)
-                torch.cuda.synchronize(self.device)
-                t2 = time.perf_counter()
-                self.results = self.postprocess((out, counts), im, im0s if im0s is not None else tensor, paths)
-                t3 = time.perf_counter()
-                self.run_callbacks("on_predict_postprocess_end")
-                n = len(self.results)
-                speed = {"preprocess": (t1 - t0) * 1e3 / n, "inference": (t2 - t1) * 1e3 / n, "postprocess": (t3 - t2) * 1e3 / n}
-                for r in self.results:
-                    r.speed = speed
-                self.seen += n
-                if self.args.verbose:
-                    for p, r in zip(paths, self.results):
-                        print(f"{p}: {H}x{W} {r.verbose()}{speed['inference']:.2f}ms")
-                self.run_callbacks("on_predict_batch_end")
-                yield from self.results
+                self._inflight.append(self._launch(paths, im0s, tensor))
+                if len(self._inflight) == 2:                               # batch i+1 is queued: turn batch i into Results meanwhile
+                    yield from self._finish(self._inflight.popleft())
+            while self._inflight:
+                yield from self._finish(self._inflight.popleft())
             self.run_callbacks("on_predict_end")
 
-    def inference(self, eng: Engine):
+    def inference(self, eng: Engine, slot: int = 0):
         """conv stack + decode + NMS, one CUDA-graph replay (predictor.py:138-145 + detect/predict.py:25-35)."""
-        return eng.step()
+        return eng.step(slot)
+
+    def construct_results(self, rec):
+        """Padded detections (already in original-image coordinates: the NMS output phase applied scale_boxes + clip_boxes)
+        -> Results (detect/predict.py:37-73); each Results holds a view of its first counts[i] rows."""
+        host, cnt = rec["host"]
+        world, b_local, n_items = rec["world"], rec["b_local"], rec["n"]
+        counts = cnt.tolist()
+        rows = host.clone()                                                # the pinned pair is reused two batches later
+        names = self.model.names
+        orig_imgs, tensor, paths, oshapes = rec["im0s"], rec["tensor"], rec["paths"], rec["oshapes"]
+        results = []
+        for i in range(n_items):
+            if world == 1:
+                k = i
+            else:                                                          # image i lives in rank r's shard
+                r, pos = shard_of(i, n_items, world)
+                k = r * b_local + pos
+            if tensor is not None:
+                def orig(j=i, t=tensor):
+                    if t.dtype == torch.uint8:
+                        return t[j].permute(1, 2, 0).contiguous().cpu().numpy()
+                    return ops.convert_torch2numpy_batch(t[j:j + 1].float())[0]
+            else:
+                orig = orig_imgs[i]
+            results.append(Results(orig, path=paths[i], names=names, boxes=rows[k, :counts[k]], orig_shape=oshapes[i]))
+        return results
 
     def postprocess(self, preds, img, orig_imgs, paths):
-        """Padded detections -> Results; boxes rescaled to the original image (detect/predict.py:37-73).  One D2H of
-        (B, max_det, 6), one batched rescale + clamp (the reference's per-image scale_boxes arithmetic, element for element);
-        each Results holds a view of its first counts[i] rows."""
+        """The reference's hook (detect/predict.py:23-73) for padded detections in INPUT-pixel coordinates (an engine built
+        without the fused post-step, or `ops.nms_padded`): one D2H of (B, max_det, 6), one batched scale_boxes + clip_boxes
+        (the per-image arithmetic, element for element), Results."""
         out, counts = preds
         B = out.shape[0]
         host = out.cpu() if out.is_cuda else out.clone()

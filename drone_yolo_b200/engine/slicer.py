@@ -28,6 +28,7 @@ import torch
 
 from .. import _C
 from .. import kernels as K
+from ..utils import ops
 from .predictor import DetectionPredictor, letterbox_geometry
 from .results import Results
 
@@ -69,7 +70,7 @@ class InferenceSlicer:
             m.predictor = DetectionPredictor(overrides=args)
             m.predictor.setup_model(model=m.model)
         else:
-            m.predictor.args.__dict__.update(args)
+            m.predictor.update_args(args)
         return m.predictor
 
     MAX_MERGE_ROWS = 16384                     # dy_box_nms_f64: one CTA scans the `removed` set, 256 words of 64 rows
@@ -122,17 +123,20 @@ class InferenceSlicer:
         H, W = geo[0][4], geo[0][5]
         with p._lock, torch.inference_mode():
             frame = self._upload(image, p.device)
+            p._flush()                                 # nothing of a stream_inference loop is in flight on this engine's slots
             eng = p.engine_for(T, H, W, torch.uint8)
             for i, ((x0, y0, x1, y1), g) in enumerate(zip(offsets.tolist(), geo)):
-                K.letterbox_u8(frame[y0:y1, x0:x1], eng.images[i], g[0], g[1], g[2], g[3])
+                K.letterbox_u8(frame[y0:y1, x0:x1], eng.image_slots[0][i], g[0], g[1], g[2], g[3])
+            # tile-coordinate rows straight from the NMS output phase (scale_boxes + clip_boxes per tile, dy_nms_desc.rescale)
+            eng.rescale_slots[0].copy_(ops.rescale_params((H, W), tile_shapes))
             t1 = time.perf_counter()
-            preds = p.inference(eng)
-            tiles = [image[y0:y1, x0:x1] for x0, y0, x1, y1 in offsets.tolist()]
-            per_tile = p.postprocess(preds, eng.images, tiles, [f"tile{i}.jpg" for i in range(T)])
+            out, counts = p.inference(eng, 0)
+            host, n = out.cpu(), counts.cpu().tolist()
+            per_tile = [host[i, :n[i]] for i in range(T)]
             t2 = time.perf_counter()
             moved = []
             for r, (x0, y0, _, _) in zip(per_tile, offsets.tolist()):
-                rows = np.asarray(r.boxes.data, dtype=np.float64)
+                rows = np.asarray(r, dtype=np.float64)
                 if len(rows):
                     rows = rows.copy()
                     rows[:, [0, 2]] += float(x0)

@@ -15,6 +15,29 @@ from . import _C
 BLOCK_K = 64
 
 
+def _on_tensor_device(fn):
+    """The library launches on the CALLING THREAD's current device, with a stream and pointers that belong to the tensors'
+    device: make that device current for the duration of the call (predict(device='cuda:1') from a process whose current
+    device is 0 otherwise fails with invalid-resource-handle errors)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, (list, tuple)) and a and isinstance(a[0], torch.Tensor):
+                a = a[0]
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
 def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -137,6 +160,7 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
     return d
 
 
+@_on_tensor_device
 def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, residual=None, out=None,
            out_dtype=torch.bfloat16, up_out=None, tail=None) -> torch.Tensor:
     """act(conv(x) + bias) [+ residual] on tcgen05 tensor cores (dy_conv2d).  With `tail` (see conv_desc) the fused
@@ -152,6 +176,7 @@ def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, resid
     return out
 
 
+@_on_tensor_device
 def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: NCHW contiguous [B,3,H,W], fp32 in [0,1] or uint8 0..255 (scaled by 1/255 in the kernel); w27 fp32 [Cout,27];
     returns bf16 NHWC [B,Cout,H/2,W/2] view."""
@@ -169,6 +194,7 @@ def stem_conv(x: torch.Tensor, w27: torch.Tensor, bias: torch.Tensor, out: Optio
     return out
 
 
+@_on_tensor_device
 def letterbox_u8(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: int, left: int, top: int, fill: int = 114) -> torch.Tensor:
     """One raw frame (h, w, 3) uint8 BGR on the device -> one (3, H, W) uint8 RGB image of the engine's input batch:
     LetterBox (data/augment.py:1544-1610) + BGR->RGB + HWC->CHW in one kernel."""
@@ -184,6 +210,7 @@ def letterbox_u8(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: int, l
     return dst
 
 
+@_on_tensor_device
 def letterbox_u8_batch(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: int, left: int, top: int, fill: int = 114) -> torch.Tensor:
     """n raw frames of one shape (n, h, w, 3) uint8 BGR on the device -> (n, 3, H, W) uint8 RGB, one launch (see letterbox_u8)."""
     _C.require_cuda(src)
@@ -198,6 +225,7 @@ def letterbox_u8_batch(src: torch.Tensor, dst: torch.Tensor, new_w: int, new_h: 
     return dst
 
 
+@_on_tensor_device
 def sppf_pool(buf: torch.Tensor, c: int) -> torch.Tensor:
     """buf: bf16 NHWC (B,>=4c,H,W); fills channels [c,4c) with mp5, mp5∘mp5, mp5∘mp5∘mp5 of channels [0,c)."""
     p, ld, B, H, W, Cc = nhwc_view(buf, "sppf buffer")
@@ -207,6 +235,7 @@ def sppf_pool(buf: torch.Tensor, c: int) -> torch.Tensor:
     return buf
 
 
+@_on_tensor_device
 def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     xp, xld, B, H, W, Cc = nhwc_view(x, "upsample input")
     if out is None:
@@ -218,6 +247,7 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
+@_on_tensor_device
 def dwconv3x3s2(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x bf16 NHWC (B,2c,H,W); w fp32 [c,2,3,3] (BN folded); returns SiLU(conv+bias) (B,c,H/2,W/2)."""
     xp, xld, B, H, W, Cin = nhwc_view(x, "dwconv input")
@@ -271,6 +301,7 @@ def decode_desc(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: in
     return d
 
 
+@_on_tensor_device
 def detect_decode(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: int,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Detect._inference on the GPU: returns y (B, 4+nc, A) fp32."""
@@ -283,6 +314,20 @@ def detect_decode(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: 
     d = decode_desc(levels, strides, nc, out)
     _C.check(_C.lib().dy_detect_decode(C.byref(d), _C.stream_ptr(out.device)), "dy_detect_decode")
     return out
+
+
+def normalize_classes(classes):
+    """The reference's `classes` argument (cfg default None; ops.py:237-238 turns a list, an int or a tensor into a tensor):
+    None -> None (no filter), anything else -> list of ints (an empty list filters every detection out)."""
+    if classes is None:
+        return None
+    if isinstance(classes, torch.Tensor):
+        classes = classes.detach().cpu().reshape(-1).tolist()
+    elif hasattr(classes, "tolist") and not isinstance(classes, (list, tuple)):      # numpy arrays and scalars
+        classes = classes.tolist()
+    if isinstance(classes, (int, float)):
+        classes = [classes]
+    return [int(c) for c in classes]
 
 
 class NmsBuffers:
@@ -299,7 +344,8 @@ class NmsBuffers:
 
 
 def nms_desc(pred: torch.Tensor, bufs: NmsBuffers, conf_thres: float, iou_thres: float, max_det: int, max_nms: int,
-             max_wh: float, agnostic: bool, multi_label: bool, classes, in_place: bool, want_kept: bool = True) -> _C.NmsDesc:
+             max_wh: float, agnostic: bool, multi_label: bool, classes, in_place: bool, want_kept: bool = True,
+             rescale: Optional[torch.Tensor] = None) -> _C.NmsDesc:
     _C.require_cuda(pred)
     if pred.dim() != 3 or pred.dtype != torch.float32 or not pred.is_contiguous():
         raise _C.DroneYoloError("nms: prediction must be a contiguous fp32 (B, 4+nc, A) tensor")
@@ -310,7 +356,10 @@ def nms_desc(pred: torch.Tensor, bufs: NmsBuffers, conf_thres: float, iou_thres:
     d.conf_thres, d.iou_thres = float(conf_thres), float(iou_thres)
     d.max_det, d.max_nms, d.max_wh = int(max_det), int(max_nms), float(max_wh)
     d.agnostic, d.multi_label = int(bool(agnostic)), int(bool(multi_label))
+    classes = normalize_classes(classes)
     if classes is not None:
+        if len(classes) == 0:
+            classes = [nc]                  # no class passes (ops.py:294-295 with an empty tensor): an id outside [0, nc) sets no bit
         arr = (C.c_int32 * len(classes))(*[int(c) for c in classes])
         bufs._classes = arr  # keep alive
         d.classes_host, d.n_classes = C.cast(arr, C.POINTER(C.c_int32)), len(classes)
@@ -320,23 +369,31 @@ def nms_desc(pred: torch.Tensor, bufs: NmsBuffers, conf_thres: float, iou_thres:
     d.out, d.counts = bufs.out.data_ptr(), bufs.counts.data_ptr()
     d.kept = bufs.kept.data_ptr() if want_kept else None
     d.workspace, d.workspace_bytes = bufs.workspace.data_ptr(), bufs.workspace.numel()
+    if rescale is not None:
+        if rescale.dtype != torch.float32 or tuple(rescale.shape) != (B, 8) or not rescale.is_contiguous() or rescale.device != pred.device:
+            raise _C.DroneYoloError("nms: rescale must be a contiguous fp32 (B, 8) tensor on the prediction's device")
+        d.rescale = rescale.data_ptr()
+    else:
+        d.rescale = None
     return d
 
 
+@_on_tensor_device
 def nms(pred: torch.Tensor, conf_thres: float, iou_thres: float, max_det: int = 300, max_nms: int = 30000,
         max_wh: float = 7680, agnostic: bool = False, multi_label: bool = False, classes=None, in_place: bool = False,
-        bufs: Optional[NmsBuffers] = None):
+        bufs: Optional[NmsBuffers] = None, rescale: Optional[torch.Tensor] = None):
     """Batched NMS on the GPU. Returns (out (B,max_det,6), counts (B,), kept (B,max_det)) device tensors."""
     B, ch, A = pred.shape
     nc = ch - 4
     ml = bool(multi_label) and nc > 1
     if bufs is None or bufs.key != (B, nc, A, max_det, ml, str(pred.device)):
         bufs = NmsBuffers(B, nc, A, max_det, ml, pred.device)
-    d = nms_desc(pred, bufs, conf_thres, iou_thres, max_det, max_nms, max_wh, agnostic, ml, classes, in_place)
+    d = nms_desc(pred, bufs, conf_thres, iou_thres, max_det, max_nms, max_wh, agnostic, ml, classes, in_place, rescale=rescale)
     _C.check(_C.lib().dy_nms(C.byref(d), _C.stream_ptr(pred.device)), "dy_nms")
     return bufs.out, bufs.counts, bufs.kept
 
 
+@_on_tensor_device
 def box_nms_f64(rows: torch.Tensor, iou_thres: float, class_agnostic: bool = False) -> torch.Tensor:
     """Merge NMS of the tiled-frame dispatch (the overlap filter of supervision.InferenceSlicer, mix6.py:84-89):
     rows (n, 6) float64 [x1, y1, x2, y2, conf, cls] on the device -> keep mask (n,) bool in the original row order."""

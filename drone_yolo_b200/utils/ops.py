@@ -97,6 +97,20 @@ def scale_boxes_batch(img1_shape, boxes, img0_shapes):
     return boxes
 
 
+def rescale_params(img1_shape, img0_shapes) -> torch.Tensor:
+    """(B, 8) float32 rows (pad_x, pad_y, gain, w0, h0, 0, 0, 0): what `scale_boxes` + `clip_boxes` (reference ops.py:92-127,
+    335-354) need per image, for the fused post-step of dy_nms (`dy_nms_desc.rescale`)."""
+    out = torch.zeros((len(img0_shapes), 8), dtype=torch.float32)
+    for i, s in enumerate(img0_shapes):
+        g = min(img1_shape[0] / s[0], img1_shape[1] / s[1])
+        out[i, 0] = round((img1_shape[1] - s[1] * g) / 2 - 0.1)
+        out[i, 1] = round((img1_shape[0] - s[0] * g) / 2 - 0.1)
+        out[i, 2] = g
+        out[i, 3] = s[1]
+        out[i, 4] = s[0]
+    return out
+
+
 def convert_torch2numpy_batch(batch: torch.Tensor) -> np.ndarray:
     """(B,C,H,W) float 0..1 -> (B,H,W,C) uint8 (reference ops.py:841-851)."""
     return (batch.permute(0, 2, 3, 1).contiguous() * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()

@@ -177,6 +177,11 @@ typedef struct dy_nms_desc {
   int32_t xyxy_in_place;     /* 1: also overwrite pred rows 0..3 with x1,y1,x2,y2 (ops.py:259-260) */
   float* out; int32_t* counts; int64_t* kept;
   void* workspace; size_t workspace_bytes;
+  /* Optional fused Results post-step (ops.scale_boxes + ops.clip_boxes, utils/ops.py:92-127, 335-354, as
+   * DetectionPredictor.construct_result calls them, models/yolo/detect/predict.py:66-73): DEVICE fp32 [B][8] rows
+   * (pad_x, pad_y, gain, w0, h0, -, -, -) read when the output rows are written: x = clamp((x - pad_x) / gain, 0, w0),
+   * y = clamp((y - pad_y) / gain, 0, h0) in the reference's fp32 operation order.  NULL: rows stay in input pixels. */
+  const float* rescale;
 } dy_nms_desc;
 
 size_t dy_nms_workspace_bytes(int B, int nc, int A, int multi_label);

@@ -517,6 +517,15 @@ def test_predict_pre_and_post_processing_vs_reference(K, dev, golden_dir, tag):
         got = r.boxes.data.cpu().numpy()
         assert got.shape == want.shape and r.orig_shape == tuple(int(v) for v in g[f"orig_shape{b}"])
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (tag, b)
+    # the same post-step fused into the NMS output phase (dy_nms_desc.rescale): what the predictor's engines run
+    from drone_yolo_b200.utils import ops
+
+    rs = ops.rescale_params((H, W), [f.shape[:2] for f in frames]).to(dev)
+    out2, counts2, _ = K.nms(torch.from_numpy(g["y"]).to(dev), float(g["conf"]), float(g["iou"]), max_det=int(g["max_det"]), rescale=rs)
+    for b in range(len(frames)):
+        want = g[f"boxes{b}"]
+        assert int(counts2[b]) == want.shape[0]
+        assert np.array_equal(out2[b, : want.shape[0]].cpu().numpy().view(np.uint32), want.view(np.uint32)), (tag, b, "fused rescale")
 
 
 @pytest.mark.parametrize("scale,imgsz,B,mb", [("s", 640, 4, 2), ("n", 320, 3, 1), ("x", 320, 2, 2), ("m", 256, 2, 1),
@@ -644,6 +653,106 @@ def test_predict_api_matches_engine(dev):
         model.predict(torch.rand(1, 3, 100, 100, device=dev), device="cuda:0")
     with pytest.raises(DroneYoloError):
         model.predict(x, device="cuda:0", augment=True)
+
+
+def test_predict_classes_argument_forms(dev):
+    """`classes` as the reference accepts it (ops.py:237-238, 294-295): an int (mix6.py:80 passes classes=0), a list, a tensor,
+    an ndarray; an empty list lets nothing through."""
+    from drone_yolo_b200 import YOLO
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    x = recipe.images(2, 128, 128).to(dev)
+    kw = dict(conf=0.001, iou=0.7, max_det=300, device="cuda:0")
+    everything = model.predict(x, **kw)
+    want = [r.boxes.data[r.boxes.cls == 0] for r in everything]
+    assert sum(len(w) for w in want) > 0
+    for form in (0, [0], torch.tensor([0]), np.array([0]), np.int64(0)):
+        res = model.predict(x, classes=form, **kw)
+        assert all(bool((r.boxes.cls == 0).all()) for r in res)
+        assert sum(len(r) for r in res) >= sum(len(w) for w in want)      # the filter runs BEFORE NMS and max_det (ops.py:294-313)
+    assert all(len(r) == 0 for r in model.predict(x, classes=[], **kw))
+    res = model.predict(x, classes=[1, 3], **kw)
+    assert all(bool(((r.boxes.cls == 1) | (r.boxes.cls == 3)).all()) for r in res)
+
+
+def test_predict_pipeline_equals_batch_by_batch(dev, tmp_path):
+    """The two-slot loop (upload of batch i+1 under the compute of batch i, Results of batch i-1 on the host) returns what
+    one call per batch returns, in order, for full and ragged last batches and for both preprocess paths."""
+    import cv2
+    from drone_yolo_b200 import YOLO
+
+    torch.manual_seed(0)
+    model = YOLO("yolov8n-p2-repvgg.yaml", nc=10)
+    recipe.apply_recipe(model.model)
+    frames = recipe.predict_frames([(120, 160)] * 7, seed0=300)
+    for i, f in enumerate(frames):
+        cv2.imwrite(str(tmp_path / f"f{i:02d}.png"), f)
+    kw = dict(conf=0.001, iou=0.7, max_det=100, device="cuda:0", imgsz=128)
+    for gpu_pre in (True, False):
+        events = []
+        piped = list(model.predict(str(tmp_path), batch=3, stream=True, gpu_preprocess=gpu_pre, **kw))
+        assert len(piped) == 7 and [r.path.endswith(f"f{i:02d}.png") for i, r in enumerate(piped)] == [True] * 7
+        one = [model.predict([frames[i]], gpu_preprocess=gpu_pre, **kw)[0] for i in range(7)]
+        for a, b in zip(piped, one):
+            assert torch.equal(a.boxes.data, b.boxes.data) and a.orig_shape == b.orig_shape == (120, 160)
+        assert all(set(r.speed) == {"preprocess", "inference", "postprocess"} and r.speed["inference"] > 0 for r in piped)
+        model.predictor.add_callback("on_predict_batch_end", lambda p: events.append(len(p.results)))
+        list(model.predict(str(tmp_path), batch=3, stream=True, gpu_preprocess=gpu_pre, **kw))
+        assert events == [3, 3, 1]
+        model.predictor.callbacks["on_predict_batch_end"].clear()
+    with pytest.raises(Exception):
+        model.predict(frames[:1], dtype="fp32", **kw)                      # no fp32 conv path: an explicit request raises
+    assert len(model.predict(frames[:1], half=True, **kw)) == 1            # `half` selects the same bf16 arithmetic either way
+
+
+TWO_RANK_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{os.environ['PORT']}", rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+from drone_yolo_b200 import YOLO
+from oracle import recipe
+torch.manual_seed(0)
+model = YOLO("yolov8n-p2-repvgg.yaml", nc=10); recipe.apply_recipe(model.model)
+frames = recipe.predict_frames([(120, 160)] * 5 + [(90, 130)] * 2, seed0=300)
+kw = dict(conf=0.001, iou=0.7, max_det=100, device=f"cuda:{rank}", imgsz=128)
+res = model.predict(frames[:5], **kw)                       # 5 frames over 2 ranks: shards of 3 and 2, gathered to rank 0
+res2 = model.predict(frames, **kw)                          # ragged canvases (host letterbox path)
+if rank == 0:
+    solo = [model.predict(frames[:5], distributed=False, **kw), model.predict(frames, distributed=False, **kw)]
+    for got, want in zip((res, res2), solo):
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert torch.equal(a.boxes.data, b.boxes.data) and a.orig_shape == b.orig_shape
+    print("rank 0: sharded predict == single-GPU predict", [len(r) for r in res])
+else:
+    assert res == [] and res2 == []
+dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+"""
+
+
+def test_two_rank_sharded_predict_equals_single_gpu(dev, tmp_path):
+    """Predictor-level multi-GPU dispatch: under torch.distributed (NCCL, one process per GPU) YOLO.predict shards every batch,
+    gathers the padded detections to rank 0 with one collective and returns bit-identical Results there."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(TWO_RANK_WORKER)
+    root = str(Path(__file__).resolve().parents[1])
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(os.environ, RANK=str(r), PORT=str(port), REPO=root),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out
 
 
 # ---------------------------------------------------------------------------------------------- tiled frames (mix6.py:84-89)

@@ -30,6 +30,15 @@ def frames_of(g):
     return recipe.predict_frames([tuple(v) for v in g["shapes"].tolist()], int(g["frame_seed0"]))
 
 
+def build_model(g):
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(int(g["model_seed"]))
+    m = DetectionModel(str(g["yaml"]), nc=int(g["nc"]), verbose=False)
+    recipe.apply_recipe(m, int(g["bn_seed"]), float(g["cls_delta"]))
+    return m.eval()
+
+
 @pytest.mark.parametrize("regime", REGIMES)
 def test_decode_oracle_matches_reference(golden_dir, regime):
     g = np.load(golden_dir / f"decode_nms_{regime}.npz")
