@@ -212,6 +212,9 @@ class DetectionPredictor:
                 im = im.float() / 255.0
             yield [f"image{i}.jpg" for i in range(im.shape[0])], None, im
             return
+        if hasattr(source, "__next__"):
+            yield from self._iter_batches(source)
+            return
         items = source if isinstance(source, (list, tuple)) else [source]
         if items and all(isinstance(s, (str, Path)) for s in items):
             yield from self._file_batches(source)
@@ -227,6 +230,37 @@ class DetectionPredictor:
                 imgs.append(np.asarray(s)[:, :, ::-1] if np.asarray(s).ndim == 3 else np.asarray(s))
                 paths.append(getattr(s, "filename", "") or f"image{i}.jpg")
         yield paths, imgs, None                                   # in-memory images: ONE batch (LoadPilAndNumpy, loaders.py:451-513)
+
+    def _iter_batches(self, it):
+        """A frame stream (any iterator / generator), consumed as it is needed like the reference's stream loaders
+        (data/loaders.py:32-220): uint8 HWC BGR frames are grouped `args.batch` at a time (a change of frame shape closes the
+        batch early, so that every batch keeps the batched staging path); a 4-D tensor or a list of frames is one batch."""
+        bs = max(int(self.args.batch), 1)
+        paths, imgs, n = [], [], 0
+        for item in it:
+            if isinstance(item, torch.Tensor) or isinstance(item, (list, tuple)):
+                if imgs:
+                    yield paths, imgs, None
+                    paths, imgs = [], []
+                if isinstance(item, torch.Tensor):
+                    yield from self._batches(item)
+                else:
+                    yield [f"image{n + i}.jpg" for i in range(len(item))], list(item), None
+                    n += len(item)
+                continue
+            if not isinstance(item, np.ndarray):
+                item = np.asarray(item)[:, :, ::-1] if np.asarray(item).ndim == 3 else np.asarray(item)     # PIL
+            if imgs and item.shape != imgs[0].shape:
+                yield paths, imgs, None
+                paths, imgs = [], []
+            imgs.append(item)
+            paths.append(f"image{n}.jpg")
+            n += 1
+            if len(imgs) == bs:
+                yield paths, imgs, None
+                paths, imgs = [], []
+        if imgs:
+            yield paths, imgs, None
 
     def _file_batches(self, source):
         """Paths -> batches of `args.batch` decoded frames (LoadImagesAndVideos, data/loaders.py:284-446): a `.txt` list, a
@@ -323,6 +357,51 @@ class DetectionPredictor:
               and all(x.ndim == 3 and x.shape[2] == 3 and x.dtype == np.uint8 for x in im0s))
         return H, W, (geo if ok else None)
 
+    def _upload_raw(self, eng, slot, im0s, geo, lo, hi):
+        """Frames lo..hi -> device staging -> letterbox kernel -> input slot, all on the copy stream.  A frame that already
+        lives in pinned host memory (e.g. a view of a capture ring) is uploaded from where it is and must stay unchanged
+        until its Results arrive; any other frame goes through a pinned staging buffer, filled by a few host threads
+        (a single-threaded memcpy of a 64 x 640 x 640 batch costs more than the whole device step)."""
+        n = hi - lo
+        if n <= 0:
+            return
+        cs = self._copy_stream
+        frames = [im0s[j] if im0s[j].flags.c_contiguous else np.ascontiguousarray(im0s[j]) for j in range(lo, hi)]
+        same = all(f.shape == frames[0].shape for f in frames) and all(geo[j] == geo[lo] for j in range(lo, hi))
+        pinned = [torch.from_numpy(f).is_pinned() if f.flags.writeable else False for f in frames]
+        if same:
+            host, dev = self._staging(("rawb", slot), (n,) + frames[0].shape)
+            hosts, devs = list(host), list(dev)
+        else:
+            pairs = [self._staging(("raw", slot, k), f.shape) for k, f in enumerate(frames)]
+            hosts, devs = [h for h, _ in pairs], [d for _, d in pairs]
+        todo = [k for k in range(n) if not pinned[k]]
+        if len(todo) > 1:
+            list(self._pool().map(lambda k: np.copyto(hosts[k].numpy(), frames[k]), todo))
+        elif todo:
+            np.copyto(hosts[todo[0]].numpy(), frames[todo[0]])
+        with torch.cuda.stream(cs):
+            if same and not any(pinned):
+                dev.copy_(host, non_blocking=True)
+            else:
+                for k in range(n):
+                    devs[k].copy_(torch.from_numpy(frames[k]) if pinned[k] else hosts[k], non_blocking=True)
+            if same:
+                g = geo[lo]
+                K.letterbox_u8_batch(dev, eng.image_slots[slot][:n], g[0], g[1], g[2], g[3])
+            else:
+                for k in range(n):
+                    g = geo[lo + k]
+                    K.letterbox_u8(devs[k], eng.image_slots[slot][k], g[0], g[1], g[2], g[3])
+
+    def _pool(self):
+        if getattr(self, "_threads", None) is None:
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._threads = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)))
+        return self._threads
+
     # ---- the loop (predictor.py:221-306) ------------------------------------------------------------------
     def __call__(self, source=None, model=None, stream=False):
         gen = self.stream_inference(source, model)
@@ -368,16 +447,9 @@ class DetectionPredictor:
                         host.copy_(arr)
                         eng.image_slots[slot][: hi - lo].copy_(host, non_blocking=True)
             else:
-                # raw frames cross PCIe as they are; ONE kernel per frame does resize + border + BGR->RGB + HWC->CHW straight
-                # into the engine's input slot (dy_letterbox_u8)
-                with torch.cuda.stream(cs):
-                    for j in range(lo, hi):
-                        x = np.ascontiguousarray(im0s[j])
-                        host, dev = self._staging(("raw", slot, j - lo), x.shape)
-                        host.copy_(torch.from_numpy(x))
-                        dev.copy_(host, non_blocking=True)
-                        g = geo[j]
-                        K.letterbox_u8(dev, eng.image_slots[slot][j - lo], g[0], g[1], g[2], g[3])
+                # raw frames cross PCIe as they are; the letterbox kernel does resize + border + BGR->RGB + HWC->CHW straight
+                # into the engine's input slot (dy_letterbox_u8): ONE launch for a batch of equally shaped frames
+                self._upload_raw(eng, slot, im0s, geo, lo, hi)
             oshapes = [tuple(o.shape[:2]) for o in im0s]
             in_shape = (H, W)
         # per-image scale_boxes / clip_boxes parameters for the NMS output phase (this rank's shard)
@@ -469,7 +541,7 @@ class DetectionPredictor:
         host, cnt = rec["host"]
         world, b_local, n_items = rec["world"], rec["b_local"], rec["n"]
         counts = cnt.tolist()
-        rows = host.clone()                                                # the pinned pair is reused two batches later
+        rows = host.clone().unbind(0)                                      # the pinned pair is reused two batches later
         names = self.model.names
         orig_imgs, tensor, paths, oshapes = rec["im0s"], rec["tensor"], rec["paths"], rec["oshapes"]
         results = []
@@ -486,7 +558,7 @@ class DetectionPredictor:
                     return ops.convert_torch2numpy_batch(t[j:j + 1].float())[0]
             else:
                 orig = orig_imgs[i]
-            results.append(Results(orig, path=paths[i], names=names, boxes=rows[k, :counts[k]], orig_shape=oshapes[i]))
+            results.append(Results(orig, path=paths[i], names=names, boxes=rows[k][:counts[k]], orig_shape=oshapes[i]))
         return results
 
     def postprocess(self, preds, img, orig_imgs, paths):

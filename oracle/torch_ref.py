@@ -137,6 +137,20 @@ def forward(model, x, return_features=False):
     raise RuntimeError("model has no Detect head")
 
 
+@torch.no_grad()
+def forward_raw(model, x):
+    """The conv stack only: the per-level raw head maps (B, no, H_l, W_l) (Detect.forward before _inference, head.py:64-71)."""
+    y = []
+    for m in model.model:
+        if m.f != -1:
+            x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+        if type(m).__name__ == "Detect":
+            return detect_raw(m, x)
+        x = module_forward(m, x)
+        y.append(x if m.i in model.save else None)
+    raise RuntimeError("model has no Detect head")
+
+
 def fuse_like_reference(model):
     """What the reference's BaseModel.fuse does on this graph (nn/tasks.py:193-221): Conv+BN folded, RepVGGBlock left
     as two conv+BN branches (it never calls switch_to_deploy).  Used by the CPU baseline timing."""

@@ -48,6 +48,27 @@ def test_struct_layouts_match_header_sizes():
     assert sizes == [ctypes.sizeof(_C.ConvDesc), ctypes.sizeof(_C.DecodeDesc), ctypes.sizeof(_C.NmsDesc)]
 
 
+def test_integration_md_struct_stubs_match_the_library_mirrors():
+    """Every `class X(C.Structure)` stub printed in INTEGRATION.md (what a reference maintainer would paste) has the very
+    fields, in order and of the same ctypes, of the mirror the package itself uses (a stale stub makes the library read
+    past the struct)."""
+    import re
+
+    from drone_yolo_b200 import _C
+
+    text = (ROOT / "INTEGRATION.md").read_text()
+    stubs = re.findall(r"^class (\w+)\(C\.Structure\):.*?\n(    _fields_ = \[.*?\])[ \t]*(?:#[^\n]*)?$", text, flags=re.S | re.M)
+    assert {n for n, _ in stubs} >= {"NmsDesc", "DecodeDesc"}
+    for name, body in stubs:
+        ns = {"C": ctypes}
+        exec("class %s(C.Structure):\n%s\n" % (name, body), ns)
+        mine = getattr(_C, name)
+        assert ctypes.sizeof(ns[name]) == ctypes.sizeof(mine), name
+        for (fa, ta), (fb, tb) in zip(ns[name]._fields_, mine._fields_):
+            assert fa.rstrip("_") == fb.rstrip("_") and ctypes.sizeof(ta) == ctypes.sizeof(tb), (name, fa, fb)
+        assert len(ns[name]._fields_) == len(mine._fields_), name
+
+
 @pytest.mark.parametrize("cfg,n_params", sorted(PARAMS.items()))
 def test_model_builds_with_reference_param_count(cfg, n_params):
     from drone_yolo_b200.nn.tasks import DetectionModel

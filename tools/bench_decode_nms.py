@@ -18,67 +18,78 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from drone_yolo_b200 import kernels as K  # noqa: E402
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--batch", type=int, default=256)
-ap.add_argument("--imgsz", type=int, nargs="+", default=[640, 1280])
-ap.add_argument("--iters", type=int, default=20)
-ap.add_argument("--nc", type=int, default=10)
-a = ap.parse_args()
-dev = torch.device("cuda:0")
-peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-bw = float(peaks.get("hbm_gbs", 6553.6))
-B, nc = a.batch, a.nc
-no = 64 + nc
-ld = (no + 15) // 16 * 16
+
+def run_config4(dev, batch=256, imgszs=(640, 1280), iters=20, nc=10, layouts=True, multi_label=True, emit=None):
+    """Every case of config 4 on `dev`; returns the list of result dicts (and passes each to `emit` as it is measured)."""
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    bw = float(peaks.get("hbm_gbs", 6553.6))
+    B = batch
+    no = 64 + nc
+    ld = (no + 15) // 16 * 16
+    rows = []
+
+    def out(d):
+        rows.append(d)
+        if emit:
+            emit(d)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    for imgsz in imgszs:
+        shapes = [(imgsz // s, imgsz // s) for s in (4, 8, 16, 32)]
+        A = sum(h * w for h, w in shapes)
+        strides = [4.0, 8.0, 16.0, 32.0]
+        for mu, regime in ((-11.0, "sparse"), (-10.0, "val-like"), (-7.5, "dense")):
+            g = torch.Generator(device=dev).manual_seed(1234)
+            bufs = []
+            for h, w in shapes:                              # NHWC fp32, pixel stride `ld` (the engine's raw-map layout)
+                t = torch.zeros((B, h, w, ld), device=dev, dtype=torch.float32)
+                t[..., :64] = 1.5 * torch.randn((B, h, w, 64), device=dev, generator=g)
+                t[..., 64:no] = mu + 1.5 * torch.randn((B, h, w, nc), device=dev, generator=g)
+                bufs.append(t)
+            y = torch.empty((B, 4 + nc, A), device=dev, dtype=torch.float32)
+            for layout in (("nhwc_f32", "nhwc_bf16", "nchw_f32") if (regime == "val-like" and layouts) else ("nhwc_f32",)):
+                if layout == "nhwc_f32":
+                    lv = [t.permute(0, 3, 1, 2)[:, :no] for t in bufs]; esz = 4
+                elif layout == "nhwc_bf16":
+                    lv = [t.to(torch.bfloat16).permute(0, 3, 1, 2)[:, :no] for t in bufs]; esz = 2
+                else:
+                    lv = [t.permute(0, 3, 1, 2)[:, :no].contiguous() for t in bufs]; esz = 4
+                ms = timed(lambda: K.detect_decode(lv, strides, nc, out=y))
+                gb = B * A * (no * esz + (4 + nc) * 4) / 1e9
+                out({"case": "decode", "layout": layout, "imgsz": imgsz, "B": B, "A": A, "regime": regime,
+                     "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "frac_of_measured_hbm": round(gb / ms * 1e3 / bw, 3)})
+                del lv
+            K.detect_decode([t.permute(0, 3, 1, 2)[:, :no] for t in bufs], strides, nc, out=y)
+            for ml in ((False, True) if multi_label else (False,)):
+                nb = K.NmsBuffers(B, nc, A, 300, ml, dev)
+                ms = timed(lambda: K.nms(y, 0.001, 0.7, max_det=300, multi_label=ml, bufs=nb))
+                gb = (B * A * (4 + nc) * 4 + B * (300 * 24 + 4)) / 1e9
+                cand = float((y[:, 4:].amax(1) > 0.001).sum()) / B
+                out({"case": "nms", "multi_label": ml, "imgsz": imgsz, "B": B, "A": A, "regime": regime,
+                     "candidates_per_image": round(cand), "kept_per_image": round(float(nb.counts.float().mean()), 1),
+                     "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "frac_of_measured_hbm": round(gb / ms * 1e3 / bw, 3)})
+                del nb
+            del bufs, y
+            torch.cuda.empty_cache()
+    return rows
 
 
-def timed(fn):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / a.iters
-
-
-for imgsz in a.imgsz:
-    shapes = [(imgsz // s, imgsz // s) for s in (4, 8, 16, 32)]
-    A = sum(h * w for h, w in shapes)
-    strides = [4.0, 8.0, 16.0, 32.0]
-    for mu, regime in ((-11.0, "sparse"), (-10.0, "val-like"), (-7.5, "dense")):
-        g = torch.Generator(device=dev).manual_seed(1234)
-        bufs = []
-        for h, w in shapes:                              # NHWC fp32, pixel stride `ld` (the engine's raw-map layout)
-            t = torch.zeros((B, h, w, ld), device=dev, dtype=torch.float32)
-            t[..., :64] = 1.5 * torch.randn((B, h, w, 64), device=dev, generator=g)
-            t[..., 64:no] = mu + 1.5 * torch.randn((B, h, w, nc), device=dev, generator=g)
-            bufs.append(t)
-        y = torch.empty((B, 4 + nc, A), device=dev, dtype=torch.float32)
-        for layout in (("nhwc_f32", "nhwc_bf16", "nchw_f32") if regime == "val-like" else ("nhwc_f32",)):
-            if layout == "nhwc_f32":
-                lv = [t.permute(0, 3, 1, 2)[:, :no] for t in bufs]; esz = 4
-            elif layout == "nhwc_bf16":
-                lv = [t.to(torch.bfloat16).permute(0, 3, 1, 2)[:, :no] for t in bufs]; esz = 2
-            else:
-                lv = [t.permute(0, 3, 1, 2)[:, :no].contiguous() for t in bufs]; esz = 4
-            ms = timed(lambda: K.detect_decode(lv, strides, nc, out=y))
-            gb = B * A * (no * esz + (4 + nc) * 4) / 1e9
-            print(json.dumps({"case": "decode", "layout": layout, "imgsz": imgsz, "B": B, "A": A, "regime": regime,
-                              "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "frac_of_measured_hbm": round(gb / ms * 1e3 / bw, 3)}))
-            del lv
-        K.detect_decode([t.permute(0, 3, 1, 2)[:, :no] for t in bufs], strides, nc, out=y)
-        for ml in (False, True):
-            nb = K.NmsBuffers(B, nc, A, 300, ml, dev)
-            ms = timed(lambda: K.nms(y, 0.001, 0.7, max_det=300, multi_label=ml, bufs=nb))
-            gb = (B * A * (4 + nc) * 4 + B * (300 * 24 + 4)) / 1e9
-            cand = float((y[:, 4:].amax(1) > 0.001).sum()) / B
-            print(json.dumps({"case": "nms", "multi_label": ml, "imgsz": imgsz, "B": B, "A": A, "regime": regime,
-                              "candidates_per_image": round(cand), "kept_per_image": round(float(nb.counts.float().mean()), 1),
-                              "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1), "frac_of_measured_hbm": round(gb / ms * 1e3 / bw, 3)}))
-            del nb
-        del bufs, y
-        torch.cuda.empty_cache()
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--imgsz", type=int, nargs="+", default=[640, 1280])
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--nc", type=int, default=10)
+    a = ap.parse_args()
+    run_config4(torch.device("cuda:0"), a.batch, a.imgsz, a.iters, a.nc, emit=lambda d: print(json.dumps(d), flush=True))
