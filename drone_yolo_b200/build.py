@@ -18,7 +18,8 @@ CSRC = PKG / "csrc"
 OUT_DIR = PKG / "lib"
 DEBUG = bool(os.environ.get("DY_CONV_DEBUG_BUILD"))           # knock-outs + in-kernel timeline (tools/bench_conv.py, trace_conv.py)
 KNOCK = os.environ.get("DY_CONV_KNOCKOUT_BUILD", "")          # compile-time knock-out mask: release-speed "what bounds it" builds
-_TAG = "_dbg" if DEBUG else (f"_k{KNOCK}" if KNOCK else "")
+EXTRA = os.environ.get("DY_EXTRA_NVCC_FLAGS", "")              # experiment builds: extra -D flags, library tagged DY_LIB_TAG
+_TAG = "_dbg" if DEBUG else (f"_k{KNOCK}" if KNOCK else (("_" + os.environ.get("DY_LIB_TAG", "x")) if EXTRA else ""))
 LIB = OUT_DIR / f"libdroneyolo{_TAG}.so"
 OBJ_DIR = PKG / f"build{_TAG}"
 
@@ -26,7 +27,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
 ] + (["-DDY_CONV_DEBUG"] if os.environ.get("DY_CONV_DEBUG_BUILD") else []) + (
-    [f"-DDY_CONV_DBG_CONST={int(os.environ['DY_CONV_KNOCKOUT_BUILD'])}"] if os.environ.get("DY_CONV_KNOCKOUT_BUILD") else [])
+    [f"-DDY_CONV_DBG_CONST={int(os.environ['DY_CONV_KNOCKOUT_BUILD'])}"] if os.environ.get("DY_CONV_KNOCKOUT_BUILD") else []) + EXTRA.split()
 
 
 def _nvcc() -> str:

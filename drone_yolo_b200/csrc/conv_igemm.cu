@@ -1268,6 +1268,10 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   p->eg = ((mode == 4 || (mode == 3 && !fuse2 && env_int("DY_CONV_EG3_M3", 1))) && cw == 32 && !f32 && p->BN <= 64 && !env_int("DY_CONV_EG2", 0)) ? 3 : 2;   // epilogue groups
   // fused Detect tails: ~6000 cycles of serial epilogue chain per tile and group against a ~1750-cycle mainloop -> a third group
   if (fuse2 && mode == 3 && env_int("DY_TAIL_EG3", 1)) p->eg = 3;
+  // the stride-2 conv with a hidden 1x1 + SiLU tail (layer 1 + C2f.cv1): SiLU, staging, tail GEMM, SiLU, two stores per tile and group
+  if (fuse2 && mode == 5 && env_int("DY_S2TAIL_EG3", 0)) p->eg = 3;
+  // 32-channel halo layers: a fourth group when asked for (640 threads)
+  if (mode == 4 && p->eg == 3 && env_int("DY_K32_EG4", 0)) p->eg = 4;
   int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
   if (p->nbuf == 1 && halo && !paired && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
@@ -1326,6 +1330,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     if (halo) nacc &= ~1;
     if (paired) nacc = nacc >= 4 ? 4 : 0;                                   // the issuer addresses accumulator slots as tile & 3
     if (p->eg == 3 && !fuse2) nacc = nacc >= 6 ? 6 : 0;                     // even (two MMA issuers) and a multiple of the three groups
+    if (p->eg == 4) nacc = nacc >= 8 ? 8 : 0;
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;
   }
@@ -1385,9 +1390,11 @@ int conv_launch(const ConvParams* p, const ConvLaunch* l, cudaStream_t stream) {
     case 2: return conv_launch_m<2>(p, l, stream);
     case 3: return p->fuse2 ? (p->eg == 3 ? conv_launch_t<3, 32, false, true, 3>(p, l, stream) : conv_launch_t<3, 32, false, true>(p, l, stream))
                             : (p->eg == 3 ? conv_launch_t<3, 32, false, false, 3>(p, l, stream) : conv_launch_m<3>(p, l, stream));
-    case 4: return p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream);
+    case 4: return p->eg == 4 ? conv_launch_t<4, 32, false, false, 4>(p, l, stream)
+                              : (p->eg == 3 ? conv_launch_t<4, 32, false, false, 3>(p, l, stream) : conv_launch_m<4>(p, l, stream));
     case 6: return conv_launch_t<6, 32, false>(p, l, stream);
-    default: return p->fuse2 ? conv_launch_t<5, 32, false, true>(p, l, stream) : conv_launch_m<5>(p, l, stream);
+    default: return p->fuse2 ? (p->eg == 3 ? conv_launch_t<5, 32, false, true, 3>(p, l, stream) : conv_launch_t<5, 32, false, true>(p, l, stream))
+                             : conv_launch_m<5>(p, l, stream);
   }
 }
 

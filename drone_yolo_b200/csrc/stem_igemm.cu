@@ -28,11 +28,14 @@ static constexpr int kStemPH = 2 * kStemTH + 1;                 // input rows pe
 // 16 bytes (16 uint8 / 4 fp32 columns) left of the tile instead of 1 column: 16 + 64 + 1 (4 + 64 + 1) columns, padded to 16 B.
 static constexpr int kStemPWu8 = 96, kStemPWf32 = 72;
 static constexpr int kStemLeftU8 = 16, kStemLeftF32 = 4;
-static constexpr int kStemEG = 3;                                // epilogue groups (the in-kernel timeline shows the epilogue chain, ~2100 cycles per tile and group, as the limiter)
-static constexpr int kStemMaxNP = 16, kStemNA = 4, kStemNAcc = 6;   // patch stages (HBM latency x bandwidth: >= 12 tiles in flight per SM), A stages, accumulator stages (even: two MMA issuers; multiple of kStemEG)
+#ifndef DY_STEM_EG
+#define DY_STEM_EG 3
+#endif
+static constexpr int kStemEG = DY_STEM_EG;                                // epilogue groups (the in-kernel timeline shows the epilogue chain, ~2100 cycles per tile and group, as the limiter)
+static constexpr int kStemMaxNP = 16, kStemNA = 4, kStemNAcc = 2 * kStemEG;   // patch stages (HBM latency x bandwidth: >= 12 tiles in flight per SM), A stages, accumulator stages (even: two MMA issuers; multiple of kStemEG)
 static constexpr int kStemThreads = 128 + 256 + 128 * kStemEG;  // 4 control warps + 2 x 4 builder warps + kStemEG x 4 epilogue warps
 static constexpr int kStemABytes = 128 * 64;                    // A tile: 128 rows x 32 bf16
-static constexpr int kStemMaxN = 80;                            // kStemNAcc * N + 16 columns of ragged read must fit 512
+static constexpr int kStemMaxN = ((512 - 16) / kStemNAcc) / 16 * 16;                            // kStemNAcc * N + 16 columns of ragged read must fit 512
 
 struct StemParams {
   CUtensorMap tmIn;        // input planes [B*3][H][W]
@@ -350,8 +353,8 @@ int stem_tc_launch(const void* in, int in_dtype, int B, int H, int W, const floa
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   static unsigned long long seen[2] = {0, 0};                // the opt-in is per device
   if (first_use_on_device(&seen[u8 ? 1 : 0])) {
-    if (u8) DY_CUDA(cudaFuncSetAttribute(stem_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    else DY_CUDA(cudaFuncSetAttribute(stem_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (u8) DY_CUDA(cudaFuncSetAttribute(stem_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    else DY_CUDA(cudaFuncSetAttribute(stem_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStemThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;

@@ -52,6 +52,16 @@ class Model(nn.Module):
         cfg = obj["yaml"]
         self.model = DetectionModel(cfg, nc=obj.get("nc", nc), verbose=False)
         self.model.load(obj["model"], verbose=False)
+        got, want, missing = self.model.transferred
+        if got != want:
+            # the reference logs "Transferred x/y items" and carries on with random weights for the rest (tasks.py:277-279); a
+            # predictor silently running on random weights is worse than an error
+            from .._C import DroneYoloError
+
+            fused = not any(".bn." in k for k in obj["model"])
+            why = ("the checkpoint was saved after fuse() (no BatchNorm entries): load the unfused weights, fuse() runs here"
+                   if fused else "the checkpoint belongs to another scale / YAML")
+            raise DroneYoloError(f"{weights}: only {got} of {want} tensors match the model built from its YAML ({why}); first missing: {missing}")
         if "names" in obj:
             self.model.names = obj["names"]
         self.overrides = {"model": weights, "task": "detect"}

@@ -6,8 +6,11 @@ Replaces `torch_safe_load` / `attempt_load_one_weight` (ultralytics/nn/tasks.py:
 name.  Here every `ultralytics.*` class resolves to a stand-in (an `nn.Module` subclass for modules, a plain object for
 the rest), which is enough for the generic `nn.Module` machinery to rebuild the module tree and hand back its `yaml` dict,
 `names` and `state_dict()`; the real model is then built from that YAML with this package's modules and loaded with the
-weights.  Anything that is neither `ultralytics.*` nor on the short allow-list below is refused (unlike the reference's
-plain `torch.load`, which executes whatever the pickle names).
+weights.  Outside `ultralytics.*` only an EXACT set of (module, name) pairs resolves: torch's tensor / storage rebuild
+helpers, `torch.nn.modules.*` classes that are `nn.Module` subclasses, a few plain containers (OrderedDict, numpy array
+reconstruction, pathlib paths, Namespace).  Dotted names, functions and every other global are refused, so a crafted file
+cannot reach `torch.hub.load`, `numpy.testing...runstring`, `types.FunctionType` and the like (the reference's plain
+`torch.load` executes whatever the pickle names).
 """
 from __future__ import annotations
 
@@ -18,7 +21,25 @@ from typing import Any
 import torch
 import torch.nn as nn
 
-_ALLOWED_PREFIXES = ("torch", "collections", "numpy", "pathlib", "types", "copyreg", "_codecs", "argparse")
+# Exact (module, name) pairs a reference checkpoint may name outside `ultralytics.*`.  A prefix rule ("anything under torch /
+# numpy / types") is not a protection: `numpy.testing._private.utils.runstring`, `types.FunctionType`, `torch.hub.load`, ...
+# all live under such prefixes and execute their arguments.  Everything here is a data constructor or a class whose
+# construction runs no caller-supplied code.
+_TORCH_STORAGES = ("FloatStorage", "HalfStorage", "BFloat16Storage", "DoubleStorage", "LongStorage", "IntStorage", "ShortStorage",
+                   "CharStorage", "ByteStorage", "BoolStorage", "UntypedStorage")
+_ALLOWED_GLOBALS = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"), ("torch._utils", "_rebuild_parameter_with_state"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "dtype"), ("torch", "Tensor"),
+    ("torch.nn.parameter", "Parameter"), ("torch.serialization", "_get_layout"),
+    ("numpy", "dtype"), ("numpy", "ndarray"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"),
+    ("_codecs", "encode"),
+    ("pathlib", "PosixPath"), ("pathlib", "PurePosixPath"), ("pathlib", "WindowsPath"), ("pathlib", "PureWindowsPath"), ("pathlib", "Path"),
+    ("argparse", "Namespace"), ("types", "SimpleNamespace"),
+} | {("torch", n) for n in _TORCH_STORAGES}
+_TORCH_DTYPES = {"float32", "float16", "bfloat16", "float64", "int64", "int32", "int16", "int8", "uint8", "bool"}
 _ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "bytearray", "complex",
                      "slice", "range", "object"}
 _stubs: dict = {}
@@ -53,8 +74,14 @@ class _Unpickler(pickle.Unpickler):
             return _stub(module, name)
         if module in ("builtins", "__builtin__") and name in _ALLOWED_BUILTINS:
             return super().find_class("builtins", name)
-        if module.split(".")[0] in _ALLOWED_PREFIXES:
+        if "." in name:                                       # dotted names walk attributes (pickle protocol 4): never needed here
+            raise pickle.UnpicklingError(f"checkpoint refers to the dotted name {module}.{name}: refused")
+        if (module, name) in _ALLOWED_GLOBALS or (module == "torch" and name in _TORCH_DTYPES):
             return super().find_class(module, name)
+        if module.startswith("torch.nn.modules."):            # torch's own layer classes (Conv2d, BatchNorm2d, SiLU, ...): classes only
+            obj = super().find_class(module, name)
+            if isinstance(obj, type) and issubclass(obj, nn.Module):
+                return obj
         raise pickle.UnpicklingError(f"checkpoint refers to {module}.{name}, which is outside ultralytics / torch: refused")
 
 

@@ -223,6 +223,7 @@ class BaseModel(nn.Module):
         for m in self.modules():
             if hasattr(m, "invalidate"):
                 m.invalidate()
+        self.transferred = (len(csd), len(own), [k for k in own if k not in csd][:8])   # callers decide how strict to be
         if verbose:
             print(f"Transferred {len(csd)}/{len(own)} items from pretrained weights")
         return self

@@ -170,6 +170,54 @@ def test_letterbox_oracle_vs_cv2(h, w, imgsz, auto):
         assert d.max() <= 1 and (d > 0).mean() < 1e-3
 
 
+def test_checkpoint_unpickler_allow_list_is_exact():
+    """a prefix allow-list ("anything under torch / numpy / types") resolves code-executing globals.  Only exact
+    (module, name) pairs, torch.nn.modules.* Module classes and ultralytics.* stand-ins resolve; dotted names never do."""
+    import io
+    import pickle
+
+    import torch.nn as nn
+
+    from drone_yolo_b200.nn.ckpt import _Unpickler
+
+    u = _Unpickler(io.BytesIO(b""))
+    for mod, name in (("numpy.testing._private.utils", "runstring"), ("types", "FunctionType"), ("types", "CodeType"),
+                      ("torch.hub", "load"), ("torch.utils.cpp_extension", "load_inline"), ("os", "system"), ("builtins", "eval"),
+                      ("builtins", "getattr"), ("torch", "load"), ("torch.serialization", "load"), ("numpy", "load"),
+                      ("torch.nn.modules.module", "register_module_forward_hook"), ("torch", "Tensor.__reduce_ex__")):
+        with pytest.raises(pickle.UnpicklingError):
+            u.find_class(mod, name)
+    assert u.find_class("torch.nn.modules.conv", "Conv2d") is nn.Conv2d
+    assert u.find_class("collections", "OrderedDict").__name__ == "OrderedDict"
+    assert u.find_class("torch._utils", "_rebuild_tensor_v2") is torch._utils._rebuild_tensor_v2
+    assert u.find_class("torch", "float16") is torch.float16
+    stub = u.find_class("ultralytics.nn.modules.block", "C2f")
+    assert issubclass(stub, nn.Module) and stub.__module__ == "ultralytics.nn.modules.block"
+
+
+def test_checkpoint_of_another_scale_fails_loudly(golden_dir, tmp_path):
+    """`load` keeps intersecting keys only; a checkpoint whose tensors do not match the model built from its YAML
+    must raise instead of predicting with random weights (the reference only logs 'Transferred x/y items')."""
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200._C import DroneYoloError
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    m = DetectionModel("yolov8n-p2-repvgg.yaml", nc=10, verbose=False)
+    sd = m.state_dict()
+    ok = tmp_path / "ok.pt"
+    torch.save({"yaml": "yolov8n-p2-repvgg.yaml", "model": sd, "nc": 10}, ok)
+    assert YOLO(str(ok)).model.transferred[0] == len(sd)
+    bad = tmp_path / "bad.pt"
+    torch.save({"yaml": "yolov8s-p2-repvgg.yaml", "model": sd, "nc": 10}, bad)       # n-scale tensors, s-scale YAML
+    with pytest.raises(DroneYoloError, match="tensors match"):
+        YOLO(str(bad))
+    fused = tmp_path / "fused.pt"
+    torch.save({"yaml": "yolov8n-p2-repvgg.yaml", "model": {k: v for k, v in sd.items() if ".bn." not in k}, "nc": 10}, fused)
+    with pytest.raises(DroneYoloError, match="fuse"):
+        YOLO(str(fused))
+
+
 def test_reference_pickled_checkpoint_ingestion(golden_dir):
     """A `.pt` written by the REAL reference (tools/make_ckpt_fixture.py: torch.save of its DetectionModel, the format
     mix6.py:18 loads) is read without the reference package: same YAML, names and weights (nn/tasks.py:786-926)."""

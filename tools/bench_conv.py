@@ -38,6 +38,10 @@ LAYERS = [  # name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32
     ("P4 1x1 512->256", 64, 512, 256, 40, 40, 1, 1, False, 512, 256, False),
     ("P3 3x3 s2 128->256", 64, 128, 256, 80, 80, 3, 2, False, 128, 256, False),
     ("P4 3x3 256->128", 64, 256, 128, 40, 40, 3, 1, False, 256, 128, False),
+    ("P5 1x1 512->512", 64, 512, 512, 20, 20, 1, 1, False, 512, 768, False),
+    ("P5 1x1 768->512", 64, 768, 512, 20, 20, 1, 1, False, 768, 512, False),
+    ("P4 3x3 s2 256->512", 64, 256, 512, 40, 40, 3, 2, False, 256, 512, False),
+    ("P4 1x1 384->256", 64, 384, 256, 40, 40, 1, 1, False, 384, 256, False),
 ]
 
 
@@ -55,13 +59,27 @@ def run(name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32, iters=10):
     for _ in range(2):
         K.conv2d(x, wp, bp, cout, k, s, True, residual=r, out=out)
     torch.cuda.synchronize()
+    # the launches are replayed from a CUDA graph (as the engine does): issued from Python, every call re-encodes its tensor
+    # maps on the host (~20 us) and the GPU idles between launches, which hides everything below that
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(iters):
+                K.conv2d(x, wp, bp, cout, k, s, True, residual=r, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        K.conv2d(x, wp, bp, cout, k, s, True, residual=r, out=out)
+    for _ in range(reps):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / iters
+    us = e0.elapsed_time(e1) * 1e3 / (iters * reps)
     M = B * Ho * Wo
     flop = 2.0 * M * cout * cin * k * k
     byts = B * H * W * cin * 2 + M * cout * (4 if f32 else 2) + (M * cout * 2 if res else 0)
