@@ -1187,6 +1187,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       if (env_int("DY_CONV_CW", 0) == 32 && cw == 64 && p->BN % 32 == 0) cw = 32;
     }
     if (d->residual && f32) cw = 0;                            // fp32 + residual: generic path (not used by the model)
+    if (mode == 4 && env_int("DY_K32_DIRECT", 0)) cw = 0;      // experiment: registers -> global instead of staging + TMA store
     if (fuse2) {
       p->fuse2 = 1; p->N2 = round_up(d->Cout2, 16); p->bias2 = d->bias2;
       {

@@ -109,9 +109,23 @@ class Model(nn.Module):
         return self.predictor(source=source, stream=stream)
 
 
+    def val(self, validator=None, batches=None, **kwargs):
+        """Validate on an iterable of batch dicts (engine/model.py:596-626; datasets / dataloaders are outside the hot path, so the
+        batches are passed in): returns the validator's metrics object (`box`-level numbers: mp, mr, map50, map, results_dict)."""
+        from .validator import DetectionValidator
+
+        args = {**{k: v for k, v in self.overrides.items() if k not in ("model", "task")}, **kwargs}
+        v = (validator or DetectionValidator)(args=args)
+        v(model=self.model, batches=batches)
+        self.metrics = v.metrics
+        return v.metrics
+
+
 class YOLO(Model):
     """YOLO(model='yolov8s-p2-repvgg.yaml') — detection task only (models/yolo/model.py:35-40)."""
 
     @property
     def task_map(self):
-        return {"detect": {"model": DetectionModel, "predictor": DetectionPredictor}}
+        from .validator import DetectionValidator
+
+        return {"detect": {"model": DetectionModel, "predictor": DetectionPredictor, "validator": DetectionValidator}}

@@ -935,3 +935,38 @@ def test_predict_directory_and_video_sources(dev, tmp_path):
     wr.release()
     out = list(model.predict(str(vid), batch=2, stream=True, **kw))
     assert len(out) == 5 and all(r.path.endswith("clip.avi") and r.orig_shape == (96, 128) for r in out)
+
+
+# ---------------------------------------------------------------------------------------------- validator caller
+@pytest.mark.parametrize("tag", ["n128", "n128_hybrid"])
+def test_validator_vs_reference_golden(golden_dir, dev, tag):
+    """DetectionValidator on the GPU against the REAL reference's validator (tools/make_golden_val.py):
+    (1) postprocess (multi-label NMS at conf 0.001, with the a-priori label rows when save_hybrid) on the reference's own pre-NMS
+        tensor gives bit-identical rows, hence the identical correct matrix and metrics;
+    (2) the whole path - uint8 batch -> conv stack (bf16) + decode -> NMS -> matching -> AP - gives mAP50 / mAP50-95 within 0.03 of
+        the reference's fp32 run (boxes move by < 0.5 px, scores by < 1 %: a handful of matches change IoU bucket)."""
+    from test_oracle_golden import _val_batch, build_model
+
+    from drone_yolo_b200 import YOLO
+    from drone_yolo_b200.engine.validator import DetectionValidator
+
+    g = np.load(golden_dir / f"val_{tag}.npz")
+    model = build_model(g)
+    model.names = {i: f"cls{i}" for i in range(int(g["nc"]))}
+    args = dict(conf=0.001, iou=0.7, max_det=300, save_hybrid=bool(g["save_hybrid"]), device=dev)
+    # (1) the reference's y through our postprocess + metrics
+    v = DetectionValidator(args=args)
+    v.device = dev
+    v.init_metrics(model)
+    batch = v.preprocess(_val_batch(g))
+    rows = v.postprocess(torch.from_numpy(g["y"]).to(dev))
+    assert [len(r) for r in rows] == g["n_rows"].tolist()
+    assert np.array_equal(torch.cat(rows, 0).cpu().numpy().view(np.uint32), g["rows"].view(np.uint32))
+    v.update_metrics(rows, batch)
+    res = v.get_stats()
+    assert np.array_equal(v.last_stats["tp"], g["tp"])
+    np.testing.assert_allclose([res["metrics/mAP50(B)"], res["metrics/mAP50-95(B)"]], g["results"][2:4], rtol=0, atol=1e-12)
+    # (2) end to end through Model.val
+    m = YOLO(copy.deepcopy(model)).val(batches=[_val_batch(g)], **args)
+    assert abs(m.map50 - g["results"][2]) < 0.03 and abs(m.map - g["results"][3]) < 0.03, (m.results_dict, g["results"])
+    assert m.speed["inference"] > 0

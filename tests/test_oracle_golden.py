@@ -262,3 +262,57 @@ def test_slicer_merge_nms_agrees_with_torchvision_on_tie_free_rows():
         agn = np.zeros(n, dtype=bool)
         agn[t] = True
         assert np.array_equal(slicer_np.box_nms_keep(rows, thr, class_agnostic=True), agn)
+
+
+# ---------------------------------------------------------------------------------------------- validator caller
+def _val_batch(g, device="cpu"):
+    rp = g["ratio_pad"]
+    B = int(g["B"])
+    return {"img": torch.from_numpy(g["img"]).to(device), "cls": torch.from_numpy(g["cls"]).to(device),
+            "bboxes": torch.from_numpy(g["bboxes"]).to(device), "batch_idx": torch.from_numpy(g["batch_idx"]).to(device),
+            "ori_shape": [tuple(int(v) for v in g["ori_shape"])] * B,
+            "ratio_pad": [((float(rp[0]), float(rp[1])), (float(rp[2]), float(rp[3])))] * B}
+
+
+@pytest.mark.parametrize("tag", ["n128", "n128_hybrid"])
+def test_validator_metrics_restatement_vs_reference(golden_dir, tag):
+    """utils/metrics.py + the validator's update_metrics / get_stats against the REAL reference's DetectionValidator
+    (tools/make_golden_val.py): from the reference's own NMS rows the correct matrix is identical and P / R / AP per class /
+    mAP50 / mAP50-95 agree to 1e-12; from the stored stats `ap_per_class` alone agrees too."""
+    from types import SimpleNamespace
+
+    from drone_yolo_b200.engine.validator import DetectionValidator
+    from drone_yolo_b200.utils.metrics import ap_per_class
+
+    g = np.load(golden_dir / f"val_{tag}.npz")
+    p, r, f1, ap, classes = ap_per_class(g["tp"], g["conf"], g["pred_cls"], g["target_cls"])
+    np.testing.assert_allclose(ap, g["all_ap"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(p, g["p"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(r, g["r"], rtol=0, atol=1e-12)
+    assert classes.tolist() == g["ap_class_index"].tolist()
+
+    v = DetectionValidator(args=dict(conf=0.001, iou=0.7, max_det=300, save_hybrid=bool(g["save_hybrid"])))
+    v.device = torch.device("cpu")
+    v.init_metrics(SimpleNamespace(names={i: f"cls{i}" for i in range(int(g["nc"]))}))
+    rows = np.split(g["rows"], np.cumsum(g["n_rows"])[:-1])
+    batch = _val_batch(g)
+    v.update_metrics([torch.from_numpy(x.copy()) for x in rows], batch)
+    res = v.get_stats()
+    assert np.array_equal(v.last_stats["tp"], g["tp"])
+    assert np.array_equal(v.last_stats["conf"], g["conf"]) and np.array_equal(v.last_stats["pred_cls"], g["pred_cls"])
+    assert np.array_equal(v.last_stats["target_cls"], g["target_cls"])
+    got = np.array([res[k] for k in ("metrics/precision(B)", "metrics/recall(B)", "metrics/mAP50(B)", "metrics/mAP50-95(B)", "fitness")])
+    np.testing.assert_allclose(got, g["results"], rtol=0, atol=1e-12)
+    assert 0.2 < g["results"][3] < 0.99                                   # the fixture is not vacuous
+
+
+def test_validator_argument_checks():
+    from drone_yolo_b200._C import DroneYoloError
+    from drone_yolo_b200.engine.validator import DetectionValidator
+
+    assert DetectionValidator().args.conf == 0.001                         # engine/validator.py:101-102
+    for bad in (dict(half=True), dict(plots=True), dict(save_json=True)):
+        with pytest.raises(DroneYoloError):
+            DetectionValidator(args=bad)
+    with pytest.raises(DroneYoloError):
+        DetectionValidator()(model=None, batches=[])
