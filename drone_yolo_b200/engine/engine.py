@@ -7,8 +7,6 @@ one CUDA graph that replays [plan x micro-batches, NMS].
 """
 from __future__ import annotations
 
-import os
-
 import ctypes as C
 from typing import Optional
 
@@ -36,7 +34,7 @@ class Engine:
                  max_det: int = 300, classes=None, agnostic: bool = False, multi_label: bool = False,
                  max_nms: int = 30000, max_wh: float = 7680.0, cuda_graph: bool = True,
                  input_dtype: torch.dtype = torch.float32, fuse_decode: bool = True, input_slots: int = 1,
-                 head_lanes: Optional[int] = None, rescale: bool = False, dual: Optional[bool] = None):
+                 head_lanes: Optional[int] = None, rescale: bool = False):
         device = torch.device(device)
         if device.type != "cuda":
             raise _C.DroneYoloError("drone_yolo_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
@@ -57,20 +55,8 @@ class Engine:
             self.image_slots = [self._all_images[k * batch:(k + 1) * batch] for k in range(self.input_slots)]
             self.images = self.image_slots[0]
             self.y = torch.empty((batch, 4 + self.nc, self.A), device=device, dtype=torch.float32)
-            # `dual`: the batch as two half-batch plans (own arenas) on two streams.  Every conv kernel is persistent with one
-            # CTA per SM, so two chains cannot share an SM, but the CTAs of one chain start on the SMs the other chain's kernel
-            # has already left: the epilogue tail / pipeline fill of one layer overlaps the steady state of the other chain's.
-            self.dual = bool(int(os.environ.get("DY_DUAL_STREAM", "0")) if dual is None else dual) and batch % 2 == 0 and batch >= 2
-            if self.dual:
-                self.mb = batch // 2
-                self.plans = [LayerPlan(model, self.mb, H, W, device, self._all_images, self.y[k * self.mb:(k + 1) * self.mb],
-                                        fuse_decode=fuse_decode, head_lanes=head_lanes) for k in range(2)]
-                self.plan = self.plans[0]
-                self._side = torch.cuda.Stream(device=device, priority=-1)
-            else:
-                self.plan = LayerPlan(model, self.mb, H, W, device, self._all_images, self.y, fuse_decode=fuse_decode,
-                                      head_lanes=head_lanes)
-                self.plans = [self.plan]
+            self.plan = LayerPlan(model, self.mb, H, W, device, self._all_images, self.y, fuse_decode=fuse_decode,
+                                  head_lanes=head_lanes)
             ml = bool(multi_label) and self.nc > 1
             self.nms_bufs = K.NmsBuffers(batch, self.nc, self.A, max_det, ml, device)
             classes = K.normalize_classes(classes)
@@ -94,7 +80,7 @@ class Engine:
                 self._nms_progs.append(h)
                 _C.check(_C.lib().dy_program_add_nms(h, C.byref(d)), "dy_program_add_nms")
             self._nms_prog = self._nms_progs[0]
-            self.launches_per_step = (sum(p.launches for p in self.plans) if self.dual else self.plan.launches * (batch // self.mb)) + _C.lib().dy_program_num_launches(self._nms_prog)
+            self.launches_per_step = self.plan.launches * (batch // self.mb) + _C.lib().dy_program_num_launches(self._nms_prog)
             self.graph: Optional[torch.cuda.CUDAGraph] = None
             self.graphs: list = []
             self.enqueue()                       # eager warm-up (sets kernel attributes, pages in code)
@@ -117,18 +103,8 @@ class Engine:
             in_bytes = self.mb * 3 * self.H * self.W * self.images.element_size()
             out_bytes = self.mb * (4 + self.nc) * self.A * 4
             slot_bytes = self.batch * 3 * self.H * self.W * self.images.element_size()
-            if self.dual and stream is None:
-                cur = torch.cuda.current_stream(self.device)
-                self._side.wait_stream(cur)
-                self.plans[0].run(slot * slot_bytes, 0, cur.cuda_stream)
-                self.plans[1].run(slot * slot_bytes + in_bytes, 0, self._side.cuda_stream)
-                cur.wait_stream(self._side)
-            elif self.dual:
-                for k in range(2):
-                    self.plans[k].run(slot * slot_bytes + k * in_bytes, 0, s)
-            else:
-                for m in range(self.batch // self.mb):
-                    self.plan.run(slot * slot_bytes + m * in_bytes, m * out_bytes, s)
+            for m in range(self.batch // self.mb):
+                self.plan.run(slot * slot_bytes + m * in_bytes, m * out_bytes, s)
             if nms:
                 _C.check(_C.lib().dy_program_run(self._nms_progs[slot % len(self._nms_progs)], 0, 0, s), "dy_program_run(nms)")
 

@@ -32,9 +32,21 @@ def shift_cls_bias(model: nn.Module, delta: float = 4.0) -> None:
             seq[-1].bias.add_(delta)
 
 
-def apply_recipe(model: nn.Module, bn_seed: int = 1, cls_delta: float = 4.0) -> nn.Module:
+def scale_cls_weight(model: nn.Module, gain: float) -> None:
+    """Multiply the class-logit weights of every Detect level (model.model[-1].cv3[l][-1].weight) by `gain`: at the default
+    initialisation the class logits hardly vary over the anchors, so the scores tie by the hundred; metrics that sort by score
+    (AP) then depend on the order inside ties.  A gain of a few spreads the scores."""
+    det = model.model[-1]
+    with torch.no_grad():
+        for seq in det.cv3:
+            seq[-1].weight.mul_(gain)
+
+
+def apply_recipe(model: nn.Module, bn_seed: int = 1, cls_delta: float = 4.0, cls_gain: float = 1.0) -> nn.Module:
     randomize_bn(model, bn_seed)
     shift_cls_bias(model, cls_delta)
+    if cls_gain != 1.0:
+        scale_cls_weight(model, cls_gain)
     for m in model.modules():
         if hasattr(m, "invalidate"):
             m.invalidate()

@@ -35,7 +35,7 @@ def build_model(g):
 
     torch.manual_seed(int(g["model_seed"]))
     m = DetectionModel(str(g["yaml"]), nc=int(g["nc"]), verbose=False)
-    recipe.apply_recipe(m, int(g["bn_seed"]), float(g["cls_delta"]))
+    recipe.apply_recipe(m, int(g["bn_seed"]), float(g["cls_delta"]), float(g["cls_gain"]) if "cls_gain" in g.files else 1.0)
     return m.eval()
 
 
@@ -303,7 +303,7 @@ def test_validator_metrics_restatement_vs_reference(golden_dir, tag):
     assert np.array_equal(v.last_stats["target_cls"], g["target_cls"])
     got = np.array([res[k] for k in ("metrics/precision(B)", "metrics/recall(B)", "metrics/mAP50(B)", "metrics/mAP50-95(B)", "fitness")])
     np.testing.assert_allclose(got, g["results"], rtol=0, atol=1e-12)
-    assert 0.2 < g["results"][3] < 0.99                                   # the fixture is not vacuous
+    assert 0.15 < g["results"][3] < 0.99                                  # the fixture is not vacuous
 
 
 def test_validator_argument_checks():

@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT))
 from oracle import recipe, ref_shim  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
-YAML, IMGSZ, B, NC, CLS_DELTA = "yolov8n-p2-repvgg.yaml", 128, 4, 10, 4.0
+YAML, IMGSZ, B, NC, CLS_DELTA, CLS_GAIN = "yolov8n-p2-repvgg.yaml", 128, 8, 10, 0.0, 40.0   # spread scores: AP sorts by score
 ORI = (100, 128)                                 # original frames 100 x 128, letterboxed into 128 x 128: gain 1, pad (0, 14)
 RATIO_PAD = ((1.0, 1.0), (0.0, 14.0))
 
@@ -76,7 +76,7 @@ def run_case(tasks, model, img_u8, labels, save_hybrid, tag):
     stats = {k: torch.cat(x, 0).cpu().numpy() for k, x in v.stats.items()}
     m = v.metrics.box
     np.savez_compressed(
-        OUT / f"val_{tag}.npz", yaml=YAML, imgsz=IMGSZ, B=B, nc=NC, model_seed=0, bn_seed=1, cls_delta=CLS_DELTA, save_hybrid=save_hybrid,
+        OUT / f"val_{tag}.npz", yaml=YAML, imgsz=IMGSZ, B=B, nc=NC, model_seed=0, bn_seed=1, cls_delta=CLS_DELTA, cls_gain=CLS_GAIN, save_hybrid=save_hybrid,
         img=img_u8.numpy(), cls=cls.numpy(), bboxes=boxes.numpy(), batch_idx=bidx.numpy(), ori_shape=np.array(ORI),
         ratio_pad=np.array([RATIO_PAD[0][0], RATIO_PAD[0][1], RATIO_PAD[1][0], RATIO_PAD[1][1]]),
         y=y.numpy().astype(np.float32), n_rows=np.array([len(r) for r in rows]), rows=np.concatenate(rows, 0),
@@ -84,14 +84,14 @@ def run_case(tasks, model, img_u8, labels, save_hybrid, tag):
         all_ap=np.asarray(m.all_ap), ap_class_index=np.asarray(m.ap_class_index), p=np.asarray(m.p), r=np.asarray(m.r),
         results=np.array([res[k] for k in ("metrics/precision(B)", "metrics/recall(B)", "metrics/mAP50(B)", "metrics/mAP50-95(B)", "fitness")]))
     print(tag, "rows", [len(r) for r in rows], "labels", len(cls), "tp@.5", int(stats["tp"][:, 0].sum()), "tp@.95", int(stats["tp"][:, 9].sum()),
-          {k: round(float(x), 4) for k, x in res.items()})
+          {k: round(float(x), 4) for k, x in res.items()}, "distinct conf", len(np.unique(stats["conf"])), "of", len(stats["conf"]))
 
 
 def main():
     tasks = ref_shim.load()
     torch.manual_seed(0)
     model = tasks.DetectionModel(YAML, nc=NC, verbose=False)
-    recipe.apply_recipe(model, cls_delta=CLS_DELTA)
+    recipe.apply_recipe(model, cls_delta=CLS_DELTA, cls_gain=CLS_GAIN)
     model.eval()
     model.names = {i: f"cls{i}" for i in range(NC)}
     model.fuse(verbose=False)
