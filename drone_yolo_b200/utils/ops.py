@@ -99,16 +99,18 @@ def scale_boxes_batch(img1_shape, boxes, img0_shapes):
 
 def rescale_params(img1_shape, img0_shapes) -> torch.Tensor:
     """(B, 8) float32 rows (pad_x, pad_y, gain, w0, h0, 0, 0, 0): what `scale_boxes` + `clip_boxes` (reference ops.py:92-127,
-    335-354) need per image, for the fused post-step of dy_nms (`dy_nms_desc.rescale`)."""
-    out = torch.zeros((len(img0_shapes), 8), dtype=torch.float32)
+    335-354) need per image, for the fused post-step of dy_nms (`dy_nms_desc.rescale`).  One row per DISTINCT shape is computed
+    with the reference's Python arithmetic (float64 gain, `round(... - 0.1)`), then broadcast."""
+    out = np.zeros((len(img0_shapes), 8), dtype=np.float32)
+    rows = {}
     for i, s in enumerate(img0_shapes):
-        g = min(img1_shape[0] / s[0], img1_shape[1] / s[1])
-        out[i, 0] = round((img1_shape[1] - s[1] * g) / 2 - 0.1)
-        out[i, 1] = round((img1_shape[0] - s[0] * g) / 2 - 0.1)
-        out[i, 2] = g
-        out[i, 3] = s[1]
-        out[i, 4] = s[0]
-    return out
+        s = (s[0], s[1])
+        r = rows.get(s)
+        if r is None:
+            g = min(img1_shape[0] / s[0], img1_shape[1] / s[1])
+            r = rows[s] = (round((img1_shape[1] - s[1] * g) / 2 - 0.1), round((img1_shape[0] - s[0] * g) / 2 - 0.1), g, s[1], s[0])
+        out[i, :5] = r
+    return torch.from_numpy(out)
 
 
 def convert_torch2numpy_batch(batch: torch.Tensor) -> np.ndarray:
