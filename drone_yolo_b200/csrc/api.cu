@@ -193,8 +193,12 @@ int dy_program_add_sync(dy_program* p, int waiter, int signaller) {
 int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream_) {
   DY_CHECK_ARG(p, "program_run: null program");
   cudaStream_t main_stream = static_cast<cudaStream_t>(stream_);
+  // DY_PROGRAM_SYNC=1 (bring-up): wait for every op and name the one that faulted (eager replays only, not under graph capture)
+  static const bool sync_each = getenv("DY_PROGRAM_SYNC") != nullptr;
+  int op_index = -1;
   for (dy::Op* o : p->ops) {
     int rc = DY_OK;
+    ++op_index;
     cudaStream_t stream = o->lane == 0 ? main_stream : p->side[o->lane - 1];
     switch (o->kind) {
       case dy::OP_SYNC: {
@@ -218,6 +222,13 @@ int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_byte
       case dy::OP_NMS: rc = dy::nms_launch(&o->nms, stream); break;
     }
     if (rc) return rc;
+    if (sync_each && o->kind != dy::OP_SYNC) {
+      cudaError_t e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess)
+        return dy::fail(DY_ERR_CUDA, "program op %d (kind %d; conv: mode %d, Cout %d, BN %d, map %dx%dx%d, tile %dx%dx%d, m_tiles %d, stages %d, eg %d, fuse2 %d): %s",
+                        op_index, int(o->kind), o->conv.mode, o->conv.Cout, o->conv.BN, o->conv.B, o->conv.Ho, o->conv.Wo, o->conv.TW, o->conv.TH,
+                        o->conv.TB, o->conv.m_tiles, o->conv.stages, o->conv.eg, o->conv.fuse2, cudaGetErrorString(e));
+    }
   }
   return DY_OK;
 }

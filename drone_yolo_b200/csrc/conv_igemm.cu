@@ -580,7 +580,12 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
         // ---------------- fused Detect tail: SiLU tile (2 x 32 channels, bf16, 64B swizzle) -> second GEMM -> fp32 out ----------------
         static_assert(!FUSE2 || ((MODE == 3 || MODE == 5) && CW == 32 && !F32), "fused tail: 64 output channels, 32-wide chunks");
         const uint32_t d2b = smem_u32(&d2_bar[g]);
-        const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(kTmemCols - 64 * EG + 64 * g);   // this group's private columns
+        // D2 is written over the tile's own accumulator stage (N2 <= 64 == BN columns; the stage has been read into the staging
+        // tiles by then), and the stage goes back to the MMA issuers only after D2 has been read.  Private D2 columns per group
+        // left 5 stages for three groups and two issuers, and the parity protocol needs every stage to belong to ONE (issuer,
+        // group) pair, i.e. a multiple of lcm(2, EG) stages: with 4 stages a group that ran ahead of the others passed its
+        // tfull wait on the completion of an EARLIER tile of the same parity (dead-lock about once per 25 steps of x@640).
+        const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(acc * p.BN);
         if (leader) bulk_wait_group_read<0>();       // the previous tile's output stores have read the staging memory
         named_bar_sync(barid, 128);
 #pragma unroll
@@ -592,11 +597,6 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (c == 1) {                              // accumulator fully read
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
-          }
           const uint32_t rowp = stg + c * STG_BYTES + row * 64;
 #pragma unroll
           for (int gi = 0; gi < 4; ++gi) {
@@ -657,6 +657,9 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
               }
               dist[sd] = dfl_expect(x);
             }
+            tc_fence_before();                       // D2 (and with it the accumulator stage) fully read: hand it back
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
             float bx[4];
             dist2bbox_xywh(static_cast<float>(w) + 0.5f, static_cast<float>(h) + 0.5f, dist, p.y_stride, bx);
             if (inside) {
@@ -671,6 +674,9 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
             tmem_ld_32x32b_x16(t2addr, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
             if (p.N2 > 16) tmem_ld_32x32b_x16(t2addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
             tmem_ld_wait();
+            tc_fence_before();                       // D2 (and with it the accumulator stage) fully read: hand it back
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
             if (inside) {
               const float bl[16] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w,
                                     bq[2].x, bq[2].y, bq[2].z, bq[2].w, bq[3].x, bq[3].y, bq[3].z, bq[3].w};
@@ -684,7 +690,6 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
               }
             }
           }
-          tc_fence_before();                         // D2 fully read before the next tile's tail GEMM overwrites it
         } else if (p.tail_decode == 3) {
           // ---- a hidden 1x1 Conv + SiLU as the tail (C2f.cv1 behind the stride-2 conv that feeds it, block.py:227-249):
           //      SiLU(D2 + bias2) -> bf16 -> the two staging tiles (the tail GEMM has consumed them) -> two TMA stores ----
@@ -711,6 +716,8 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
           }
           fence_proxy_async_smem();
           tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);   // D2 fully read: the accumulator stage goes back to the MMA issuer
           named_bar_sync(barid, 128);
           if (leader) {
             for (int oc = 0; oc < nout; ++oc) tma_store_4d_a(&p.tmO2, stg + oc * STG_BYTES, oc * 32, w0, h0, b0);
@@ -743,6 +750,8 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
             bulk_commit_group();
           }
         }
+        __syncwarp();                                // (every chunk's tcgen05 fence has been issued above) D2 fully read
+        if (lane == 0) mbar_arrive_a(tempty0 + acc * 8);
         }
         ++sctr;
       } else if constexpr (CW > 0) {
@@ -1327,10 +1336,13 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     const int overrun = cw ? (ceil_div(p->BN, cw) * cw - p->BN) : (ceil_div(p->BN, 32) * 32 - p->BN);
     int nacc = (kTmemCols - overrun) / p->BN;
     if (nacc > kMaxAcc) nacc = kMaxAcc;
-    if (fuse2 && nacc > (kTmemCols - 64 * p->eg) / p->BN) nacc = (kTmemCols - 64 * p->eg) / p->BN;   // the last 64 columns per group hold the tail accumulators
+    // (the fused tail's second accumulator overwrites the tile's own stage: no columns are set aside for it)
     if (halo) nacc &= ~1;
     if (paired) nacc = nacc >= 4 ? 4 : 0;                                   // the issuer addresses accumulator slots as tile & 3
-    if (p->eg == 3 && !fuse2) nacc = nacc >= 6 ? 6 : 0;                     // even (two MMA issuers) and a multiple of the three groups
+    // Two MMA issuers on alternate tiles + EG epilogue groups on every EG-th tile: the mbarrier parity protocol (a waiter may be
+    // at most ONE phase ahead) holds only if every stage always meets the same issuer and the same group, i.e. the ring is a
+    // multiple of lcm(2, EG).  A single issuer completes tiles in order, which bounds every group's lead by itself.
+    if (p->eg == 3 && halo) nacc = nacc >= 6 ? 6 : 0;
     if (p->eg == 4) nacc = nacc >= 8 ? 8 : 0;
     DY_CHECK_ARG(nacc >= 2, "conv: BN %d leaves fewer than two accumulator stages", p->BN);
     p->nacc = nacc;

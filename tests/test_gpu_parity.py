@@ -973,3 +973,28 @@ def test_validator_vs_reference_golden(golden_dir, dev, tag):
     assert abs(m.map50 - g["results"][2]) < 0.08 and abs(m.map - g["results"][3]) < 0.08, (m.results_dict, g["results"])
     assert abs(v.last_stats["tp"].shape[0] - len(g["tp"])) <= 0.05 * len(g["tp"])
     assert m.speed["inference"] > 0
+
+
+@pytest.mark.parametrize("scale,imgsz,batch,steps", [("x", 640, 32, 120), ("l", 640, 32, 120), ("s", 640, 64, 200)])
+def test_engine_step_is_stable_under_repetition(dev, scale, imgsz, batch, steps):
+    """Regression guard for the warp-specialised pipelines (compute-sanitizer is closed on this pool): many back-to-back eager
+    steps at full map sizes, synchronised one by one - a protocol dead-lock traps through the bounded mbarrier spin and
+    surfaces here as a launch failure - with bit-identical results from step to step.  Found in round 2: three epilogue
+    groups on the raw-map Detect tail of the x scale dead-locked about once per 25 steps."""
+    from drone_yolo_b200.engine.engine import Engine
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    m = DetectionModel(f"yolov8{scale}-p2-repvgg.yaml", nc=10, verbose=False)
+    recipe.apply_recipe(m, cls_delta=2.5)
+    eng = Engine(m.eval().to(dev).fuse(verbose=False), batch, imgsz, dev, micro_batch=batch, conf=0.001, iou=0.7, cuda_graph=False)
+    eng.images.copy_(recipe.images(batch, imgsz, imgsz).to(dev))
+    ref = None
+    for i in range(steps):
+        eng.step()
+        torch.cuda.synchronize(dev)
+        if i == 0:
+            ref = (eng.y.clone(), eng.nms_bufs.out.clone(), eng.nms_bufs.counts.clone())
+        elif i % 40 == 0 or i == steps - 1:
+            assert torch.equal(eng.y, ref[0]) and torch.equal(eng.nms_bufs.counts, ref[2])
+            assert torch.equal(eng.nms_bufs.out, ref[1])
