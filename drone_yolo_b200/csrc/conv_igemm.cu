@@ -1192,7 +1192,8 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       else if (p->n_tiles == 1) cw = p->BN > 32 ? 64 : 32;
       // K-heavy tiles: the epilogue has time to spare, shared memory does not -> narrow staging tiles.  The 64-channel halo
       // mode needs the room for a fourth activation stage (HBM latency x bandwidth ~ 64 KB in flight per SM).
-      if (cw == 64 && (mode == 3 || paired || (!halo && (kiters >= 8 || p->BN >= 128))) && p->BN % 32 == 0) cw = 32;
+      if (cw == 64 && (mode == 3 || paired || (!halo && (kiters >= 8 || p->BN >= 128))) && p->BN % 32 == 0 &&
+          !(mode == 0 && env_int("DY_CONV_CW64_1X1", 0))) cw = 32;
       if (env_int("DY_CONV_CW", 0) == 32 && cw == 64 && p->BN % 32 == 0) cw = 32;
     }
     if (d->residual && f32) cw = 0;                            // fp32 + residual: generic path (not used by the model)
