@@ -96,6 +96,8 @@ SYMBOLS = {
     "dy_program_add_sync": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "dy_program_run": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "dy_program_num_launches": (C.c_int, [C.c_void_p]),
+    "dy_program_profile": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
+    "dy_program_num_ops": (C.c_int, [C.c_void_p]),
     "dy_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
 }
 

@@ -190,6 +190,30 @@ int dy_program_add_sync(dy_program* p, int waiter, int signaller) {
   return DY_OK;
 }
 
+static int program_launch_op(dy_program* p, dy::Op* o, size_t in_offset_bytes, size_t out_offset_bytes, cudaStream_t main_stream) {
+  cudaStream_t stream = o->lane == 0 ? main_stream : p->side[o->lane - 1];
+  switch (o->kind) {
+    case dy::OP_SYNC: {
+      cudaStream_t sig = o->signaller == 0 ? main_stream : p->side[o->signaller - 1];
+      cudaStream_t wai = o->waiter == 0 ? main_stream : p->side[o->waiter - 1];
+      DY_CUDA(cudaEventRecord(o->event, sig));
+      DY_CUDA(cudaStreamWaitEvent(wai, o->event, 0));
+      return DY_OK;
+    }
+    case dy::OP_CONV: return dy::conv_launch(&o->conv, &o->conv_launch, stream);
+    case dy::OP_STEM:
+      return dy::stem_launch(static_cast<const char*>(o->in) + in_offset_bytes, o->Cin, o->B, o->H, o->W,
+                             o->w, o->b, o->C, o->out, o->out_ld, stream);
+    case dy::OP_POOL: return dy::sppf_pool_launch(o->out, o->B, o->H, o->W, o->C, o->out_ld, stream);
+    case dy::OP_UPSAMPLE: return dy::upsample2x_launch(o->in, o->in_ld, o->B, o->H, o->W, o->C, o->out, o->out_ld, stream);
+    case dy::OP_DWCONV:
+      return dy::dwconv_launch(o->in, o->in_ld, o->B, o->H, o->W, o->Cin, o->w, o->b, o->C, o->out, o->out_ld, stream);
+    case dy::OP_DECODE: return dy::decode_launch(&o->dec, out_offset_bytes, stream);
+    case dy::OP_NMS: return dy::nms_launch(&o->nms, stream);
+  }
+  return DY_OK;
+}
+
 int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream_) {
   DY_CHECK_ARG(p, "program_run: null program");
   cudaStream_t main_stream = static_cast<cudaStream_t>(stream_);
@@ -197,33 +221,11 @@ int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_byte
   static const bool sync_each = getenv("DY_PROGRAM_SYNC") != nullptr;
   int op_index = -1;
   for (dy::Op* o : p->ops) {
-    int rc = DY_OK;
     ++op_index;
-    cudaStream_t stream = o->lane == 0 ? main_stream : p->side[o->lane - 1];
-    switch (o->kind) {
-      case dy::OP_SYNC: {
-        cudaStream_t sig = o->signaller == 0 ? main_stream : p->side[o->signaller - 1];
-        cudaStream_t wai = o->waiter == 0 ? main_stream : p->side[o->waiter - 1];
-        DY_CUDA(cudaEventRecord(o->event, sig));
-        DY_CUDA(cudaStreamWaitEvent(wai, o->event, 0));
-        break;
-      }
-      case dy::OP_CONV: rc = dy::conv_launch(&o->conv, &o->conv_launch, stream); break;
-      case dy::OP_STEM:
-        rc = dy::stem_launch(static_cast<const char*>(o->in) + in_offset_bytes, o->Cin, o->B, o->H, o->W,
-                             o->w, o->b, o->C, o->out, o->out_ld, stream);
-        break;
-      case dy::OP_POOL: rc = dy::sppf_pool_launch(o->out, o->B, o->H, o->W, o->C, o->out_ld, stream); break;
-      case dy::OP_UPSAMPLE: rc = dy::upsample2x_launch(o->in, o->in_ld, o->B, o->H, o->W, o->C, o->out, o->out_ld, stream); break;
-      case dy::OP_DWCONV:
-        rc = dy::dwconv_launch(o->in, o->in_ld, o->B, o->H, o->W, o->Cin, o->w, o->b, o->C, o->out, o->out_ld, stream);
-        break;
-      case dy::OP_DECODE: rc = dy::decode_launch(&o->dec, out_offset_bytes, stream); break;
-      case dy::OP_NMS: rc = dy::nms_launch(&o->nms, stream); break;
-    }
+    int rc = program_launch_op(p, o, in_offset_bytes, out_offset_bytes, main_stream);
     if (rc) return rc;
     if (sync_each && o->kind != dy::OP_SYNC) {
-      cudaError_t e = cudaStreamSynchronize(stream);
+      cudaError_t e = cudaStreamSynchronize(o->lane == 0 ? main_stream : p->side[o->lane - 1]);
       if (e != cudaSuccess)
         return dy::fail(DY_ERR_CUDA, "program op %d (kind %d; conv: mode %d, Cout %d, BN %d, map %dx%dx%d, tile %dx%dx%d, m_tiles %d, stages %d, eg %d, fuse2 %d): %s",
                         op_index, int(o->kind), o->conv.mode, o->conv.Cout, o->conv.BN, o->conv.B, o->conv.Ho, o->conv.Wo, o->conv.TW, o->conv.TH,
@@ -232,6 +234,41 @@ int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_byte
   }
   return DY_OK;
 }
+
+// Per-op device times of one eager replay (the role of the reference's per-layer profile, nn/tasks.py:171-191): every op that
+// launches kernels is bracketed by CUDA events on its stream, `reps` back-to-back launches each (the first one is untimed), and
+// the mean of the timed ones lands in ms[i]; sync ops get 0.  Not capturable; synchronises the device.
+int dy_program_profile(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream_, int reps, float* ms, int n_ms) {
+  DY_CHECK_ARG(p && ms && reps >= 1, "program_profile: bad arguments");
+  DY_CHECK_ARG(n_ms >= static_cast<int>(p->ops.size()), "program_profile: ms[] holds %d entries, the program has %d ops", n_ms, (int)p->ops.size());
+  cudaStream_t main_stream = static_cast<cudaStream_t>(stream_);
+  cudaEvent_t e0, e1;
+  DY_CUDA(cudaEventCreate(&e0));
+  DY_CUDA(cudaEventCreate(&e1));
+  int rc = DY_OK, i = 0;
+  for (dy::Op* o : p->ops) {
+    ms[i] = 0.f;
+    cudaStream_t stream = o->lane == 0 ? main_stream : p->side[o->lane - 1];
+    if (o->kind == dy::OP_SYNC) { rc = program_launch_op(p, o, in_offset_bytes, out_offset_bytes, main_stream); if (rc) break; ++i; continue; }
+    rc = program_launch_op(p, o, in_offset_bytes, out_offset_bytes, main_stream);          // warm (and the one whose result counts)
+    if (rc) break;
+    if (cudaEventRecord(e0, stream) != cudaSuccess) { rc = dy::fail(DY_ERR_CUDA, "program_profile: event record failed"); break; }
+    for (int r = 0; r < reps && rc == DY_OK; ++r) rc = program_launch_op(p, o, in_offset_bytes, out_offset_bytes, main_stream);
+    if (rc) break;
+    cudaEventRecord(e1, stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { rc = dy::fail(DY_ERR_CUDA, "program_profile: op %d: %s", i, cudaGetErrorString(e)); break; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    ms[i] = t / static_cast<float>(reps);
+    ++i;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+int dy_program_num_ops(const dy_program* p) { return p ? static_cast<int>(p->ops.size()) : 0; }
 
 int dy_program_num_launches(const dy_program* p) { return p ? p->launches : 0; }
 

@@ -127,6 +127,22 @@ class Engine:
             self.images.copy_(images, non_blocking=True)
         return self.step()
 
+    def profile(self, reps: int = 5, verbose: bool = False):
+        """Per-layer device times of the resident batch (the reference's `predict(profile=True)`, nn/tasks.py:116,151-152,171-191):
+        [(op, ms)] for every op of the conv-stack plan (first micro-batch) and the NMS program."""
+        rows = self.plan.profile(0, 0, reps)
+        lib = _C.lib()
+        n = lib.dy_program_num_ops(self._nms_prog)
+        ms = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            _C.check(lib.dy_program_profile(self._nms_prog, 0, 0, _C.stream_ptr(self.device), int(reps), ms, n), "dy_program_profile(nms)")
+        rows += [("nms (filter + select)", float(ms[i])) for i in range(n)]
+        if verbose:
+            for nm, t in rows:
+                print(f"{t * 1e3:9.1f} us  {nm}")
+            print(f"{sum(t for _, t in rows) * 1e3:9.1f} us  total ({len(rows)} ops, micro-batch {self.mb})")
+        return rows
+
     def raw_maps(self):
         return self.plan.raw_maps()
 

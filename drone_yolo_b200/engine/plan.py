@@ -435,6 +435,51 @@ class LayerPlan:
                 raise AssertionError(kind)
         self.launches = lib.dy_program_num_launches(h)
 
+    def describe(self) -> list[str]:
+        """One line per op, in program order (what `profile` times)."""
+        names = []
+        for op in self.ops:
+            kind = op["kind"]
+            if kind == "sync":
+                names.append(f"sync lane {op['waiter']} <- lane {op['signaller']}")
+            elif kind == "conv":
+                if "mod" in op:
+                    cout, k, s = self._conv_geom(op["mod"])
+                else:
+                    cout, k, s = op["cout"], op["k"], op["s"]
+                inp, tail = op["inp"], op.get("tail")
+                txt = f"conv{k}x{k}s{s} {inp.c}->{cout} @{inp.H // s}x{inp.W // s}"
+                if op.get("res") is not None:
+                    txt += " +res"
+                if op.get("up") is not None:
+                    txt += " +up2x"
+                if tail:
+                    txt += f" +1x1->{tail[2]}" + (" +decode" if len(tail) > 4 else "")
+                names.append(txt)
+            elif kind == "stem":
+                names.append(f"stem 3->{op['out'].c} @{op['out'].H}x{op['out'].W}")
+            elif kind == "pool":
+                names.append(f"sppf pool c={op['c']} @{op['inp'].H}x{op['inp'].W}")
+            elif kind == "decode":
+                names.append(f"detect decode ({len(op['levels'])} levels)")
+            else:
+                names.append(kind)
+        return names
+
+    def profile(self, in_offset_bytes: int = 0, out_offset_bytes: int = 0, reps: int = 5, stream: Optional[int] = None):
+        """Per-op device milliseconds of one eager replay (`dy_program_profile`): the role of the reference's per-layer profile
+        (`BaseModel._profile_one_layer`, nn/tasks.py:171-191).  Returns [(description, ms)], sync ops left out."""
+        lib = _C.lib()
+        n = lib.dy_program_num_ops(self.handle)
+        names = self.describe()
+        if n != len(names):
+            raise _C.DroneYoloError(f"plan holds {len(names)} ops, the program {n}")
+        ms = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            s = _C.stream_ptr(self.device) if stream is None else stream
+            _C.check(lib.dy_program_profile(self.handle, in_offset_bytes, out_offset_bytes, s, int(reps), ms, n), "dy_program_profile")
+        return [(nm, float(t)) for nm, t, op in zip(names, ms, self.ops) if op["kind"] != "sync"]
+
     def run(self, in_offset_bytes: int, out_offset_bytes: int, stream: int):
         _C.check(_C.lib().dy_program_run(self.handle, in_offset_bytes, out_offset_bytes, stream), "dy_program_run")
 

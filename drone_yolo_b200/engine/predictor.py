@@ -415,6 +415,8 @@ class DetectionPredictor:
         """Stage + upload one batch into a free input slot (copy stream), enqueue its engine step and the D2H of its padded
         detections (compute stream).  Nothing here waits for the device."""
         world, rank = self._dist()
+        nvtx = torch.cuda.nvtx
+        nvtx.range_push("dy.preprocess")          # staging + upload + letterbox (copy stream)
         n_items = tensor.shape[0] if tensor is not None else len(im0s)
         lo, hi = (0, n_items) if world == 1 else shard_bounds(n_items, world, rank)
         b_local = n_items if world == 1 else -(-n_items // world)            # equal shards (the last ones padded): one collective
@@ -467,10 +469,13 @@ class DetectionPredictor:
         eng._next_slot = slot ^ 1
         t1 = time.perf_counter()
         compute.wait_event(uploaded)
+        nvtx.range_pop()
+        nvtx.range_push("dy.inference")           # conv stack + decode + NMS (+ rescale): one graph replay
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(compute)
         out, counts = eng.step(slot)
         e1.record(compute)
+        nvtx.range_pop()
         if world > 1:
             if self._gather is None or self._gather.key != (b_local, self.args.max_det):
                 self._gather = DetectionGather(b_local, self.args.max_det, self.device)
@@ -492,12 +497,14 @@ class DetectionPredictor:
         """Wait for ONE batch (its own event, not the device), build Results on the host, run the callbacks."""
         rec["done"].synchronize()
         t2 = time.perf_counter()
+        torch.cuda.nvtx.range_push("dy.postprocess")  # Results on the host
         self.batch = (rec["paths"], rec["im0s"], None)
         if rec["rank"] != 0:
             self.results = []                                              # rank 0 holds every detection of the batch
         else:
             self.results = self.construct_results(rec)
         t3 = time.perf_counter()
+        torch.cuda.nvtx.range_pop()
         self.run_callbacks("on_predict_postprocess_end")
         n = max(rec["n"], 1)
         speed = {"preprocess": rec["pre_ms"] / n, "inference": rec["e0"].elapsed_time(rec["e1"]) / n, "postprocess": (t3 - t2) * 1e3 / n}

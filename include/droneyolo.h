@@ -231,6 +231,12 @@ int dy_program_add_sync(dy_program* p, int waiter, int signaller);
  * pointer: the same program serves successive micro-batches of one large resident batch. */
 int dy_program_run(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream);
 int dy_program_num_launches(const dy_program* p);   /* kernels enqueued by one dy_program_run */
+/* Per-op device times of one eager replay: the role of the reference's per-layer profile (`BaseModel._profile_one_layer`,
+ * ultralytics/nn/tasks.py:171-191, enabled by predict(profile=True), :116,151-152).  Every op is launched `reps` + 1 times in place
+ * (idempotent: an op only reads its inputs and rewrites its outputs), the last `reps` bracketed by CUDA events; ms[i] = mean
+ * milliseconds of op i in the order the ops were added (sync ops: 0).  Synchronises the device; not capturable. */
+int dy_program_profile(dy_program* p, size_t in_offset_bytes, size_t out_offset_bytes, void* stream, int reps, float* ms, int n_ms);
+int dy_program_num_ops(const dy_program* p);        /* ops (including sync ops) added so far */
 
 /* Self-test of the tcgen05 / TMA descriptor encodings (one 128xN tile), used by tests and smoke. */
 int dy_selftest_umma(int N, int K, float* max_abs_err_host, void* stream);

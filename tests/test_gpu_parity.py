@@ -998,3 +998,27 @@ def test_engine_step_is_stable_under_repetition(dev, scale, imgsz, batch, steps)
         elif i % 40 == 0 or i == steps - 1:
             assert torch.equal(eng.y, ref[0]) and torch.equal(eng.nms_bufs.counts, ref[2])
             assert torch.equal(eng.nms_bufs.out, ref[1])
+
+
+def test_engine_profile_per_layer_times(dev):
+    """`Engine.profile` (dy_program_profile: the reference's per-layer `predict(profile=True)`, nn/tasks.py:171-191): one positive
+    time per kernel-launching op, in plan order, summing to about the step; profiling re-launches ops in place and must leave the
+    results of the next step unchanged."""
+    from drone_yolo_b200.engine.engine import Engine
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    m = DetectionModel("yolov8n-p2-repvgg.yaml", nc=10, verbose=False)
+    recipe.apply_recipe(m, cls_delta=2.5)
+    eng = Engine(m.eval().to(dev).fuse(verbose=False), 4, 256, dev, conf=0.001, iou=0.7, cuda_graph=False)
+    eng.images.copy_(recipe.images(4, 256, 256).to(dev))
+    eng.step()
+    torch.cuda.synchronize(dev)
+    ref = (eng.y.clone(), eng.nms_bufs.out.clone(), eng.nms_bufs.counts.clone())
+    rows = eng.profile(reps=3)
+    n_ops = sum(op["kind"] != "sync" for op in eng.plan.ops)
+    assert len(rows) == n_ops + 1 and all(t > 0 for _, t in rows), rows
+    assert rows[0][0].startswith("stem") and rows[-1][0].startswith("nms") and any("+1x1" in nm for nm, _ in rows)
+    eng.step()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(eng.y, ref[0]) and torch.equal(eng.nms_bufs.out, ref[1]) and torch.equal(eng.nms_bufs.counts, ref[2])
