@@ -38,6 +38,7 @@ class ConvDesc(C.Structure):
         ("Cout2", C.c_int32), ("out2", C.c_void_p), ("out2_ld", C.c_int32),
         ("tail_decode", C.c_int32), ("y", C.c_void_p), ("y_A", C.c_int32), ("y_nc", C.c_int32), ("y_anchor_off", C.c_int32),
         ("y_stride", C.c_float),
+        ("pre_add", C.c_void_p), ("pre_ld", C.c_int32),
     ]
 
 

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
   __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t res_bar[2 * EG];     // [group][staging buffer]: residual tile landed
+  __shared__ __align__(8) uint64_t pre_bar[4 * EG];     // [group][buffer]: half-resolution addend tile landed
   __shared__ __align__(8) uint64_t d2_bar[3];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ __align__(8) uint64_t afull_bar[kMaxStages];     // mode 6: the halo-tile ring (full_bar / empty_bar then serve the weight ring)
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
     prefetch_tmap(&p.tmB);
     if (CW > 0 && !FUSE2) prefetch_tmap(&p.tmO);
     if (CW > 0 && p.has_res_tma) prefetch_tmap(&p.tmR);
+    if (CW > 0 && p.pre != nullptr) prefetch_tmap(&p.tmP);
     if (CW > 0 && p.has_up) for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmU[i]);
     if (FUSE2) { prefetch_tmap(&p.tmW2); prefetch_tmap(&p.tmO2); }
   }
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
     if constexpr (PAIRED) { for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); } }
     for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int i = 0; i < 2 * EG; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 4 * EG; ++i) mbar_init(&pre_bar[i], 1);
     mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1); mbar_init(&d2_bar[2], 1);
     mbar_init(&bres_bar, 1);
     fence_mbar_init();
@@ -559,6 +562,36 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
     int acc = g % nacc; uint32_t acc_phase = static_cast<uint32_t>(g / nacc) & 1u;
     uint32_t sctr = 0;
     const int nbuf = p.nbuf;
+    // half-resolution fp32 addend (dy_conv_desc.pre_add): the tile of a chunk - box {32 channels, TW/2, TH/2, TB} = 32 rows x 128 B,
+    // 128B swizzle - is brought by TMA THREE chunks ahead into a ring of four 4 KB buffers per group, and every thread reads the
+    // row of its pixel (w/2, h/2) from shared memory.  (Per-thread 16-byte global loads of the same rows cost +100 us on the
+    // 64 -> 64 @160 layer, a TMA tile requested one chunk ahead +67 us: a chunk lasts ~1000 cycles, a DRAM round trip under load twice that.)
+    const bool has_pre = CW == 32 && !F32 && !FUSE2 && p.pre != nullptr;
+    const uint32_t preb0 = smem_u32(&pre_bar[g * 4]);
+    const uint32_t pre_s = smem_base + static_cast<uint32_t>(p.pre_off) + static_cast<uint32_t>(g) * 16384u;
+    const uint32_t pre_tx = static_cast<uint32_t>((p.TW >> 1) * (p.TH >> 1) * p.TB) * 128u;
+    uint32_t pre_row = 0;
+    TileIter pit = it;                                // the leader's prefetch stream: (tile, chunk) of the next request
+    int pc = 0; uint32_t pissued = 0;
+    const int pre_chunks = CW > 0 ? (p.BN + CW - 1) / (CW > 0 ? CW : 1) : 1;
+    auto issue_pre = [&]() {
+      if (!pit.valid()) return;
+      const uint32_t bi = pissued & 3u;
+      mbar_arrive_expect_tx_a(preb0 + bi * 8, pre_tx);
+      tma_load_4d_a(pre_s + bi * 4096u, &p.tmP, preb0 + bi * 8, pit.n_tile * p.BN + pc * (CW > 0 ? CW : 1), (pit.tw_i * p.TW) >> 1, (pit.th_i * p.TH) >> 1,
+                    pit.tb_i * p.TB);
+      ++pissued;
+      if (++pc == pre_chunks) {
+        pc = 0;
+#pragma unroll
+        for (int k = 0; k < EG; ++k) pit.next(n_iter, p.tiles_w, p.tiles_h);
+      }
+    };
+    if (has_pre) {
+      const int wl = row % p.TW, hl = (row / p.TW) % p.TH, bl = row / (p.TW * p.TH);
+      pre_row = static_cast<uint32_t>((bl * (p.TH >> 1) + (hl >> 1)) * (p.TW >> 1) + (wl >> 1));
+      if (leader) { issue_pre(); issue_pre(); issue_pre(); }
+    }
     if (nbuf == 2 && has_res && leader && it.valid()) {          // residual of this group's first chunk
       mbar_arrive_expect_tx_a(resb0, res_tx);
       tma_load_4d_a(stg, &p.tmR, resb0, it.n_tile * p.BN, it.tw_i * p.TW, it.th_i * p.TH, it.tb_i * p.TB);
@@ -785,6 +818,18 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
             }
           }
           tmem_ld_wait();
+          if constexpr (CW == 32 && !F32 && !FUSE2) {
+            if (has_pre) {                           // acc += addend (fp32, before bias and activation)
+              mbar_wait_a(preb0 + (sctr & 3u) * 8, (sctr >> 2) & 1u);
+              const uint32_t prow = pre_s + (sctr & 3u) * 4096u + pre_row * 128u;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 t = lds128(prow + ((static_cast<uint32_t>(i) ^ (pre_row & 7u)) << 4));
+                r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + __uint_as_float(t.x)); r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + __uint_as_float(t.y));
+                r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + __uint_as_float(t.z)); r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + __uint_as_float(t.w));
+              }
+            }
+          }
           if (c == 0) DY_TRE(2);
           if (c == nchunks - 1) {                    // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
@@ -839,6 +884,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
               }
               bulk_commit_group();
             }
+            if (has_pre) issue_pre();                // chunk sctr + 3 into the buffer read one chunk ago (every thread has passed this chunk's barrier since)
             if (has_res && nbuf == 2) {              // prefetch the next chunk's residual into the buffer that just became free
               const bool same_tile = c + 1 < nchunks;
               if (same_tile || nx.valid()) {
@@ -1008,13 +1054,14 @@ static int pick_bn(int cout_pad, int m_tiles, int kiters, int max_bn) {
 }
 
 // Pixel-tile shape (TW x TH x TB <= 128 rows) maximising the fraction of MMA rows that are real pixels.
-static void pick_tile(int Wo, int Ho, int B, int* TW, int* TH, int* TB) {
+static void pick_tile(int Wo, int Ho, int B, int* TW, int* TH, int* TB, bool even = false) {
   double best = -1.0; int bw = 1, bh = 1, bb = 1;
   const bool flat_ties = env_int("DY_TILE_FLAT", 0) != 0;
   for (int tw = 1; tw <= Wo && tw <= 128; ++tw) {
     for (int th = 1; th <= Ho && tw * th <= 128; ++th) {
       const int tb_max = 128 / (tw * th);                                // a tile may span several images
       for (int tb = 1; tb <= tb_max && tb <= B; ++tb) {
+        if (even && ((tw | th) & 1)) continue;                                // half-resolution addend: the tile maps onto whole low-resolution pixels
         const double tiles = double(ceil_div(Wo, tw)) * ceil_div(Ho, th) * ceil_div(B, tb);
         const double eff = double(Wo) * Ho * B / (tiles * 128.0);
         // ties: compact 2-D tiles first (a 16x8 tile re-reads 10 input rows per 8 output rows through its 3x3 taps, a
@@ -1113,7 +1160,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   p->mode = mode;
   p->kblocks = ((halo && !paired) || mode == 5) ? 1 : cin_pad / kBlockK;
   const int kiters = p->ntaps * p->kblocks;
-  const bool flat = (k == 1 && d->up_out == nullptr);         // 1x1: flat GEMM over all pixels unless a spatial tile is needed
+  const bool flat = (k == 1 && d->up_out == nullptr && d->pre_add == nullptr);   // 1x1: flat GEMM over all pixels unless a spatial tile is needed
   if (d->up_out) {
     DY_CHECK_ARG(!f32 && d->up_ld % 8 == 0 && d->up_ld >= d->Cout && (reinterpret_cast<uintptr_t>(d->up_out) & 15) == 0,
                  "conv: up_out needs a bf16 primary output and a 16B-aligned slice");
@@ -1126,7 +1173,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   } else {
     p->Ho = Ho; p->Wo = Wo; p->B = d->B;
     if (halo) { p->TW = kHaloTW; p->TH = kHaloTH; p->TB = 1; }
-    else pick_tile(Wo, Ho, d->B, &p->TW, &p->TH, &p->TB);
+    else pick_tile(Wo, Ho, d->B, &p->TW, &p->TH, &p->TB, d->pre_add != nullptr);
   }
   p->tiles_w = ceil_div(p->Wo, p->TW);
   p->tiles_h = ceil_div(p->Ho, p->TH);
@@ -1195,6 +1242,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
       if (cw == 64 && (mode == 3 || paired || (!halo && (kiters >= 8 || p->BN >= 128))) && p->BN % 32 == 0 &&
           !(mode == 0 && env_int("DY_CONV_CW64_1X1", 0))) cw = 32;
       if (env_int("DY_CONV_CW", 0) == 32 && cw == 64 && p->BN % 32 == 0) cw = 32;
+      if (d->pre_add && cw == 64 && p->BN % 32 == 0) cw = 32;   // the addend of a chunk is held in registers next to the accumulator
     }
     if (d->residual && f32) cw = 0;                            // fp32 + residual: generic path (not used by the model)
     if (mode == 4 && env_int("DY_K32_DIRECT", 0)) cw = 0;      // experiment: registers -> global instead of staging + TMA store
@@ -1265,6 +1313,19 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     }
   }
   if (d->up_out && !p->has_up) return fail(DY_ERR_UNSUPPORTED, "conv: up_out needs the TMA-store epilogue (Cout %% 8 == 0)");
+  if (d->pre_add) {
+    if (!(k == 1 && s == 1 && !fuse2 && !f32 && p->use_tma_store == 32 && d->Cout % 8 == 0 && Ho % 2 == 0 && Wo % 2 == 0 && d->pre_ld % 4 == 0 &&
+          d->pre_ld >= d->Cout && (reinterpret_cast<uintptr_t>(d->pre_add) & 15) == 0))
+      return fail(DY_ERR_UNSUPPORTED, "conv: pre_add needs ksize 1, stride 1, a bf16 output with Cout %% 8 == 0, even Ho / Wo and a 16B-aligned fp32 slice");
+    if (p->TW % 2 || p->TH % 2 || (p->TW / 2) * (p->TH / 2) * p->TB > 32)
+      return fail(DY_ERR_UNSUPPORTED, "conv: pre_add needs an even pixel tile (got %dx%dx%d)", p->TW, p->TH, p->TB);
+    p->pre = d->pre_add; p->pre_ld = d->pre_ld;
+    const uint64_t pdims[4] = {uint64_t(d->Cout), uint64_t(Wo / 2), uint64_t(Ho / 2), uint64_t(d->B)};
+    const uint64_t pstr[3] = {uint64_t(d->pre_ld) * 4, uint64_t(Wo / 2) * d->pre_ld * 4, uint64_t(Ho / 2) * (Wo / 2) * d->pre_ld * 4};
+    const uint32_t pbox[4] = {32, uint32_t(p->TW / 2), uint32_t(p->TH / 2), uint32_t(p->TB)};
+    int rc = encode_map(&p->tmP, d->pre_add, 4, pdims, pstr, pbox, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    if (rc) return rc;
+  }
 
   // ---- shared-memory plan ----
   // Small layers keep ALL their weights resident (loaded once per CTA): the per-stage traffic and TMA issue then only
@@ -1284,13 +1345,14 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   // 32-channel halo layers: a fourth group when asked for (640 threads)
   if (mode == 4 && p->eg == 3 && env_int("DY_K32_EG4", 0)) p->eg = 4;
   int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
+  const int pre_bytes = d->pre_add ? p->eg * 16384 : 0;                     // half-resolution addend: a ring of four 4 KB tiles per group
   if (p->nbuf == 1 && halo && !paired && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
     // previous chunk's store (~1700 cycles per 32-column chunk); take the second one whenever two halo stages still fit
     const int halo_stage = round_up(p->halo_pitch * kHaloRows * rowb, 1024);
     if (kMaxDynSmem - 1024 - 2 * staging - bias_bytes - b_all >= 2 * halo_stage) { p->nbuf = 2; staging *= 2; }
   }
-  const int budget = kMaxDynSmem - 1024 - staging - bias_bytes;
+  const int budget = kMaxDynSmem - 1024 - staging - pre_bytes - bias_bytes;
   if (paired) {
     // two rings: halo tiles (one per pixel tile and 64-channel block; a pair holds two while the next two load) and weight
     // tiles (one per tap and block, 8 MMAs each when paired): the weight ring takes what the halo ring leaves
@@ -1349,7 +1411,8 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     p->nacc = nacc;
   }
   p->stg_off = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + (paired ? p->a_stages * p->a_stage_bytes : 0);
-  p->bias_off = p->stg_off + staging;
+  p->pre_off = p->stg_off + staging;
+  p->bias_off = p->pre_off + pre_bytes;
   l->smem_bytes = p->bias_off + bias_bytes + 1024;
   const int total = p->m_tiles * p->n_tiles;
   if (p->n_split > 1) {

@@ -16,6 +16,7 @@ struct ConvParams {
   CUtensorMap tmU[4];      // fused 2x nearest upsample: the four (dy,dx) parity views of the upsampled destination
   CUtensorMap tmW2;        // fused 1x1 tail: packed weights [1][N2][64], box = one 32-channel k-block (64B swizzle)
   CUtensorMap tmO2;        // fused 1x1 tail: fp32 output slice, box {32, TW, TH, TB}
+  CUtensorMap tmP;         // half-resolution fp32 addend (dy_conv_desc.pre_add), box {32, TW/2, TH/2, TB}
   int nmaps, ntaps, kblocks;
   int BN, n_tiles, n_split;            // n_split > 1: every CTA owns ONE n tile for its whole life (weights resident per CTA)
   int TW, TH, TB, tiles_w, tiles_h, m_tiles;
@@ -39,6 +40,8 @@ struct ConvParams {
   void* out; int out_ld; int out_f32;
   const __nv_bfloat16* res; int res_ld;
   const float* bias; int act;
+  const float* pre; int pre_ld;        // half-resolution fp32 addend in front of the activation (dy_conv_desc.pre_add), or null
+  int pre_off;                         // byte offset of its tiles in shared memory: [group][2] x (TW/2 * TH/2 * TB rows x 128 B)
 };
 
 struct ConvLaunch { int grid; int smem_bytes; };

@@ -52,6 +52,10 @@ class LayerPlan:
         # decode inside the Detect tails: the raw maps of those levels are never materialised (Engine.raw_maps() is then
         # unavailable); needs the whole batch in one replay because the prediction tensor's address is baked into tensor maps
         self.fuse_cv1 = not os.environ.get("DY_NO_FUSE_CV1")
+        # C2f.cv1 behind Concat([Upsample(a), b]) split across the upsample (a 1x1 conv commutes with nearest upsampling):
+        # W_a * a at low resolution, then act(W_b * b + bias + up(W_a * a)); the upsampled tensor is never materialised
+        self.split_up = not os.environ.get("DY_NO_SPLIT_UP")
+        self.up_split: dict[int, tuple] = {}           # concat layer -> (low-resolution source Ref, channels of the upsampled part)
         # side lanes for the Detect branches (dy_program_set_lane): 0 = everything on the caller's stream in layer order,
         # 1 = the branches of every level on one side stream, 2 = box branch and class branch on two side streams.  A level's
         # branches are emitted as soon as its source layer is done, so they overlap the rest of the neck.  Measured on the
@@ -86,7 +90,7 @@ class LayerPlan:
                 self.bufs[r.buf].last = max(self.bufs[r.buf].last, t)
 
     def _op(self, **kw):
-        self._touch(kw.get("inp"), kw.get("out"), kw.get("res"), kw["tail"][3] if kw.get("tail") else None)
+        self._touch(kw.get("inp"), kw.get("out"), kw.get("res"), kw.get("pre"), kw["tail"][3] if kw.get("tail") else None)
         for r in kw.get("levels", ()):
             self._touch(r)
         kw["lane"] = self.lane
@@ -160,7 +164,7 @@ class LayerPlan:
                 j = i - 1 if f == -1 else f
                 private = (self.fuse_cv1 and isinstance(f, int) and j not in home and j not in getattr(self.model, "save", ())
                            and self.ops and self.ops[-1]["kind"] == "conv" and self.ops[-1].get("out") == src)
-                self._emit_c2f(m, src, out, len(self.ops) - 1 if private else None)
+                self._emit_c2f(m, src, out, len(self.ops) - 1 if private else None, split=self.up_split.get(j))
             elif isinstance(m, SPPF):
                 out = dest(i, m.cv2.conv.out_channels, src.H, src.W)
                 c_ = m.cv1.conv.out_channels
@@ -171,7 +175,17 @@ class LayerPlan:
             elif isinstance(m, Upsample):
                 out = dest(i, src.c, src.H * 2, src.W * 2)
                 prod = self._producer_of(src)
-                if prod is not None and self.fuse_upsample:
+                ci = home[i][0] if i in home else None
+                nxt = layers[ci + 1] if ci is not None and ci + 1 < n else None
+                users = [li for li, l in enumerate(layers) for f_ in (l.f if isinstance(l.f, (list, tuple)) else [l.f])
+                         if (li + f_ if f_ < 0 else f_) == ci] if ci is not None else []
+                if (self.split_up and isinstance(nxt, C2f) and users == [ci + 1] and home[i][1] == 0
+                        and ci not in getattr(self.model, "save", ()) and nxt.cv1.conv.kernel_size[0] == 1
+                        and isinstance(nxt.cv1.act, nn.SiLU) and src.c % 8 == 0 and (2 * nxt.c) % 8 == 0
+                        and src.H * 2 == out.H and src.W * 2 == out.W):
+                    # the Concat only feeds that C2f, the upsampled part sits first (channels [0, src.c)): nothing is written here
+                    self.up_split[ci] = (src, src.c)
+                elif prod is not None and self.fuse_upsample:
                     # nn.Upsample(2x nearest) folded into its producer: the conv's epilogue also stores every output tile
                     # into the four (dy, dx) parity views of this destination (dy_conv_desc.up_out)
                     self.ops[prod]["up"] = out
@@ -214,11 +228,22 @@ class LayerPlan:
         cout, s = m._geom()
         return cout, 3, s
 
-    def _emit_c2f(self, m: C2f, src: Ref, out: Ref, prod: Optional[int] = None):
+    def _emit_c2f(self, m: C2f, src: Ref, out: Ref, prod: Optional[int] = None, split=None):
         c, n = m.c, len(m.m)
         H, W = src.H, src.W
         cat = self._new_buf((2 + n) * c, H, W)
         fused = False
+        if split is not None:
+            lo, ca = split                                   # low-resolution source of the upsampled part, its channels
+            w, b = m.cv1.fused_weight_bias()                 # fp32 [2c, ca + cb, 1, 1], [2c]
+            wa, _ = K.pack_conv_weight(w[:, :ca].contiguous(), None)
+            wb, bb = K.pack_conv_weight(w[:, ca:].contiguous(), b)
+            zero = torch.zeros_like(bb)
+            t = Ref(self._new_buf(2 * c, lo.H, lo.W, esz=4), 0, 2 * c, lo.H, lo.W)
+            self._op(kind="conv", w=(wa, zero), cout=2 * c, k=1, s=1, act=False, inp=lo, out=t)
+            self._op(kind="conv", w=(wb, bb), cout=2 * c, k=1, s=1, act=True, inp=Ref(src.buf, src.c0 + ca, src.c - ca, H, W),
+                     out=Ref(cat, 0, 2 * c, H, W), pre=t)
+            fused = True
         if prod is not None:
             # cv1 (1x1 Conv + SiLU, block.py:236) as the fused tail of the 3x3 stride-2 conv in front of it (the RepVGG
             # downsample at P2 of the s scale: 32 -> 64, then 64 -> 64): the 64-channel tensor between them, 3.3 MB per
@@ -405,7 +430,8 @@ class LayerPlan:
                     else:
                         tail = (w2, b2, cout2, self.tensor(r2))
                 out_t = self.tensor(op["out"]) if op.get("out") is not None else None
-                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, out_t, res, up, tail)
+                pre = self.tensor(op["pre"]) if op.get("pre") is not None else None
+                d = K.conv_desc(self.tensor(op["inp"]), w, b, cout, k, s, act, out_t, res, up, tail, pre)
                 _C.check(lib.dy_program_add_conv(h, C.byref(d)), "add_conv")
             elif kind == "pool":
                 t = self.tensor(op["inp"])
@@ -453,6 +479,8 @@ class LayerPlan:
                     txt += " +res"
                 if op.get("up") is not None:
                     txt += " +up2x"
+                if op.get("pre") is not None:
+                    txt += " +pre(up)"
                 if tail:
                     txt += f" +1x1->{tail[2]}" + (" +decode" if len(tail) > 4 else "")
                 names.append(txt)

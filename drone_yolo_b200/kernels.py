@@ -88,7 +88,7 @@ def pack_conv_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
 
 def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, k: int, s: int, act: bool,
               out: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None, up_out: Optional[torch.Tensor] = None,
-              tail=None) -> _C.ConvDesc:
+              tail=None, pre_add: Optional[torch.Tensor] = None) -> _C.ConvDesc:
     """`tail` = (w2_packed, bias2, cout2, out2): fused 1x1 conv behind this one; `out` may then be None.  out2 fp32 = raw
     output conv (no activation; Detect), out2 bf16 = Conv + SiLU (C2f.cv1); a fifth element selects the fused decode."""
     xp, xld, B, H, W, Cin = nhwc_view(x, "conv input")
@@ -134,6 +134,14 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
     else:
         d.up_out, d.up_ld = None, 0
     d.tail_decode, d.y, d.y_A, d.y_nc, d.y_anchor_off, d.y_stride = 0, None, 0, 0, 0, 0.0
+    if pre_add is not None:
+        # half-resolution fp32 addend in front of the activation: out = act(conv(x) + bias + up2x(pre_add))
+        pp, pld, Bp, Hp, Wp, Cp = nhwc_view(pre_add, "conv pre_add")
+        if (Bp, 2 * Hp, 2 * Wp, Cp) != (B, eh, ew, cout) or pre_add.dtype != torch.float32:
+            raise _C.DroneYoloError("conv pre_add must be fp32 (B, Cout, Ho/2, Wo/2)")
+        d.pre_add, d.pre_ld = pp, pld
+    else:
+        d.pre_add, d.pre_ld = None, 0
     if tail is not None:
         w2, b2, cout2, out2 = tail[:4]
         dec = tail[4] if len(tail) > 4 else None
@@ -162,14 +170,14 @@ def conv_desc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
 
 @_on_tensor_device
 def conv2d(x, w_packed, bias, cout: int, k: int, s: int, act: bool = True, residual=None, out=None,
-           out_dtype=torch.bfloat16, up_out=None, tail=None) -> torch.Tensor:
+           out_dtype=torch.bfloat16, up_out=None, tail=None, pre_add=None) -> torch.Tensor:
     """act(conv(x) + bias) [+ residual] on tcgen05 tensor cores (dy_conv2d).  With `tail` (see conv_desc) the fused
     1x1 output conv's fp32 tensor is returned instead and the intermediate is never written."""
     B, _, H, W = x.shape
     p = k // 2
     if out is None and tail is None:
         out = empty_nhwc(B, cout, (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1, x.device, out_dtype)
-    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual, up_out, tail)
+    d = conv_desc(x, w_packed, bias, cout, k, s, act, out, residual, up_out, tail, pre_add)
     _C.check(_C.lib().dy_conv2d(C.byref(d), _C.stream_ptr(x.device)), "dy_conv2d")
     if tail is not None:
         return tail[4][1] if len(tail) > 4 and tail[4] is not None else tail[3]

@@ -68,6 +68,11 @@ int dy_device_check(int device);            /* DY_OK iff `device` is compute cap
  *           head.py:100-131, for this level and branch): 1 = box branch (Cout2 == 64: DFL expectation, dist2bbox, * stride
  *           -> rows 0..3 of y), 2 = class branch (sigmoid -> rows 4..4+y_nc-1 of y).  y = fp32 [B, 4+y_nc, y_A] (the
  *           dy_detect_decode output layout), y_anchor_off = first anchor of this level; out2 is then unused.
+ * pre_add : optional fp32 NHWC [B,Ho/2,Wo/2,Cout] slice (pixel stride pre_ld) added BEFORE the activation at half resolution:
+ *           out = act(conv(in) + bias + pre_add[b, y/2, x/2, :]).  A 1x1 conv commutes with nearest upsampling, so the first conv
+ *           behind `Concat([nn.Upsample(2x)(a), b])` (C2f.cv1 of the top-down neck, cfg/models/v8/yolov8-p2-repvgg.yaml:30-41;
+ *           nn/modules/block.py:236) is W_b*b + up(W_a*a): W_a*a is computed once at LOW resolution (this tensor) and the upsampled
+ *           tensor is never written or read back.  Requires ksize 1, stride 1, bf16 out, even Ho and Wo, Cout % 8 == 0.
  *           3 = the tail is a hidden Conv + SiLU (C2f.cv1 behind the stride-2 conv that feeds it, nn/modules/block.py:227-249):
  *           out2 = SiLU(conv1x1(...) + bias2) as a bf16 NHWC slice; also accepted for ksize 3, stride 2, Cin <= 32, Cout == 64.
  * ksize in {1,3}; stride in {1,2} (stride 2 needs even H and W); no dilation, no groups.
@@ -84,6 +89,7 @@ typedef struct dy_conv_desc {
   const void* weight2; const float* bias2;
   int32_t Cout2;       void* out2;      int32_t out2_ld;
   int32_t tail_decode; float* y;        int32_t y_A, y_nc, y_anchor_off; float y_stride;
+  const float* pre_add; int32_t pre_ld;
 } dy_conv_desc;
 
 int dy_conv2d(const dy_conv_desc* d, void* stream);

@@ -29,6 +29,7 @@ def plan_ops(scale, imgsz, batch):
     lp.fuse_tail = True
     lp.fuse_decode = True
     lp.fuse_cv1 = True
+    lp.split_up, lp.up_split = True, {}
     lp.head_lanes, lp.lane = 0, 0
     lp._build_symbolic()
     rows = []
