@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
   __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
-  __shared__ __align__(8) uint64_t res_bar[2 * EG];     // [group][staging buffer]: residual tile landed
+  __shared__ __align__(8) uint64_t res_bar[3 * EG];     // [group][ring slot]: residual tile landed
   __shared__ __align__(8) uint64_t pre_bar[4 * EG];     // [group][buffer]: half-resolution addend tile landed
   __shared__ __align__(8) uint64_t d2_bar[3];           // [group]: fused 1x1 tail finished
   __shared__ __align__(8) uint64_t bres_bar;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
     for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], PAIRED ? 2 : 1); }
     if constexpr (PAIRED) { for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); } }
     for (int a = 0; a < nacc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
-    for (int i = 0; i < 2 * EG; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 3 * EG; ++i) mbar_init(&res_bar[i], 1);
     for (int i = 0; i < 4 * EG; ++i) mbar_init(&pre_bar[i], 1);
     mbar_init(&d2_bar[0], 1); mbar_init(&d2_bar[1], 1); mbar_init(&d2_bar[2], 1);
     mbar_init(&bres_bar, 1);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
 #endif
     const int rows_valid = p.TW * p.TH * p.TB;
     const uint32_t stg = smem_base + static_cast<uint32_t>(p.stg_off) + static_cast<uint32_t>(g * p.nbuf) * STG_BYTES;
-    const uint32_t resb0 = smem_u32(&res_bar[g * 2]);
+    const uint32_t resb0 = smem_u32(&res_bar[g * 3]);
     const bool has_res = CW > 0 && !F32 && p.has_res_tma != 0;
     const uint32_t res_tx = static_cast<uint32_t>(rows_valid) * CW * 2u;
     TileIter it(p, blockIdx.x, gridDim.x);
@@ -592,10 +592,31 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
       pre_row = static_cast<uint32_t>((bl * (p.TH >> 1) + (hl >> 1)) * (p.TW >> 1) + (wl >> 1));
       if (leader) { issue_pre(); issue_pre(); issue_pre(); }
     }
-    if (nbuf == 2 && has_res && leader && it.valid()) {          // residual of this group's first chunk
-      mbar_arrive_expect_tx_a(resb0, res_tx);
-      tma_load_4d_a(stg, &p.tmR, resb0, it.n_tile * p.BN, it.tw_i * p.TW, it.th_i * p.TH, it.tb_i * p.TB);
-    }
+    // Residual tiles (same box as the output tile) arrive by TMA.  res_mode 2: TWO chunks ahead in a ring of three staging-sized
+    // buffers per group (a chunk lasts ~1000 cycles, a DRAM round trip under load about twice that: one chunk ahead cost the
+    // 32 -> 32 @160 layer 57 -> 89 us); where shared memory has no room for the ring: res_mode 1, one chunk ahead into the OTHER
+    // staging tile (each thread then overwrites the residual it has read with its result), or res_mode 0, per chunk into the
+    // single staging tile (K-heavy tiles: the epilogue has slack).
+    const int res_mode = p.res_mode;
+    const uint32_t res_slots = res_mode == 2 ? 3u : (res_mode == 1 ? 2u : 1u);
+    const uint32_t res_s = res_mode == 2 ? smem_base + static_cast<uint32_t>(p.res_off) + static_cast<uint32_t>(g) * 3u * STG_BYTES : stg;
+    TileIter rit = it;                                // the leader's request stream
+    int rc_ = 0; uint32_t rslot_i = 0;                // chunk inside rit's tile, slot of the next request
+    uint32_t rslot = 0, rphase = 0;                   // slot / phase of the chunk being consumed
+    const int res_chunks = CW > 0 ? (p.BN + CW - 1) / (CW > 0 ? CW : 1) : 1;
+    auto issue_res = [&]() {
+      if (!rit.valid()) return;
+      mbar_arrive_expect_tx_a(resb0 + rslot_i * 8, res_tx);
+      tma_load_4d_a(res_s + rslot_i * STG_BYTES, &p.tmR, resb0 + rslot_i * 8, rit.n_tile * p.BN + rc_ * (CW > 0 ? CW : 1), rit.tw_i * p.TW, rit.th_i * p.TH,
+                    rit.tb_i * p.TB);
+      if (++rslot_i == res_slots) rslot_i = 0;
+      if (++rc_ == res_chunks) {
+        rc_ = 0;
+#pragma unroll
+        for (int k = 0; k < EG; ++k) rit.next(n_iter, p.tiles_w, p.tiles_h);
+      }
+    };
+    if (has_res && leader && res_mode >= 1) { issue_res(); if (res_mode == 2) issue_res(); }
     while (it.valid()) {
       const int w0 = it.tw_i * p.TW, h0 = it.th_i * p.TH, b0 = it.tb_i * p.TB;
       const int n0 = it.n_tile * p.BN;
@@ -803,20 +824,13 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
           }
           tmem_ld_32x32b_x32(taddr + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
           if constexpr (CW == 64) tmem_ld_32x32b_x32(taddr + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-          if (nbuf == 2) {
-            if (has_res) mbar_wait_a(resb0 + buf * 8, (sctr >> 1) & 1u);   // the residual tile has landed in `st`
-          } else {
-            // single staging tile: wait until the previous store has read it, then (residual) fetch this chunk's tile into it
+          if (nbuf != 2) {
+            // single staging tile: wait until the previous store has read it (res_mode 0: then fetch this chunk's residual into it)
             if (leader) bulk_wait_group_read<0>();
             named_bar_sync(barid, 128);
-            if (has_res) {
-              if (leader) {
-                mbar_arrive_expect_tx_a(resb0, res_tx);
-                tma_load_4d_a(st, &p.tmR, resb0, n0 + c * CW, w0, h0, b0);
-              }
-              mbar_wait_a(resb0, sctr & 1u);
-            }
+            if (has_res && res_mode == 0 && leader) issue_res();
           }
+          if (has_res) mbar_wait_a(resb0 + rslot * 8, rphase);             // this chunk's residual tile has landed
           tmem_ld_wait();
           if constexpr (CW == 32 && !F32 && !FUSE2) {
             if (has_pre) {                           // acc += addend (fp32, before bias and activation)
@@ -860,7 +874,7 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
                 float v6 = act1(r[8 * gi + 6], hb1.z, silu), v7 = act1(r[8 * gi + 7], hb1.w, silu);
                 const uint32_t sp = rowp + (pos << 4);
                 if (has_res) {
-                  const uint4 rr = lds128(sp);
+                  const uint4 rr = lds128(res_s + rslot * STG_BYTES + row * ROWO + (pos << 4));
                   v0 += bf16_lo(rr.x); v1 += bf16_hi(rr.x); v2 += bf16_lo(rr.y); v3 += bf16_hi(rr.y);
                   v4 += bf16_lo(rr.z); v5 += bf16_hi(rr.z); v6 += bf16_lo(rr.w); v7 += bf16_hi(rr.w);
                 }
@@ -885,16 +899,9 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
               bulk_commit_group();
             }
             if (has_pre) issue_pre();                // chunk sctr + 3 into the buffer read one chunk ago (every thread has passed this chunk's barrier since)
-            if (has_res && nbuf == 2) {              // prefetch the next chunk's residual into the buffer that just became free
-              const bool same_tile = c + 1 < nchunks;
-              if (same_tile || nx.valid()) {
-                const uint32_t rb = resb0 + (buf ^ 1) * 8;
-                mbar_arrive_expect_tx_a(rb, res_tx);
-                if (same_tile) tma_load_4d_a(stg + (buf ^ 1) * STG_BYTES, &p.tmR, rb, n0 + (c + 1) * CW, w0, h0, b0);
-                else tma_load_4d_a(stg + (buf ^ 1) * STG_BYTES, &p.tmR, rb, nx.n_tile * p.BN, nx.tw_i * p.TW, nx.th_i * p.TH, nx.tb_i * p.TB);
-              }
-            }
+            if (has_res && res_mode >= 1) issue_res();   // ring: chunk + 2 into the slot read one chunk ago; res_mode 1: chunk + 1 into the other staging tile
           }
+          if (has_res) { if (++rslot == res_slots) { rslot = 0; rphase ^= 1u; } }
           if (c == 0) DY_TRE(5);
           ++sctr;
         }
@@ -1345,7 +1352,11 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
   // 32-channel halo layers: a fourth group when asked for (640 threads)
   if (mode == 4 && p->eg == 3 && env_int("DY_K32_EG4", 0)) p->eg = 4;
   int staging = p->eg * p->nbuf * 128 * cw * out_esz;                       // groups x nbuf tiles
-  const int pre_bytes = d->pre_add ? p->eg * 16384 : 0;                     // half-resolution addend: a ring of four 4 KB tiles per group
+  // residual staging (see the kernel): the ring where it fits without starving the activation pipeline - the 32-channel halo mode
+  // (18 KB of weights) and the paired halo mode; the 64-channel halo mode keeps 72 KB of weights resident and needs its four stages
+  p->res_mode = !p->has_res_tma ? 0 : ((mode == 4 || paired) && !env_int("DY_NO_RES_RING", 0) ? 2 : (p->nbuf == 2 ? 1 : 0));
+  const int ring_bytes = p->res_mode == 2 ? p->eg * 3 * 128 * cw * 2 : 0;
+  const int pre_bytes = (d->pre_add ? p->eg * 16384 : 0) + ring_bytes;      // half-resolution addend: a ring of four 4 KB tiles per group
   if (p->nbuf == 1 && halo && !paired && !env_int("DY_CONV_NBUF1", 0)) {
     // wide halo tile (64 -> 128, 147 KB of resident weights): a single staging tile serialises every chunk behind the
     // previous chunk's store (~1700 cycles per 32-column chunk); take the second one whenever two halo stages still fit
@@ -1411,8 +1422,9 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     p->nacc = nacc;
   }
   p->stg_off = (p->b_resident ? b_all : 0) + p->stages * p->stage_bytes + (paired ? p->a_stages * p->a_stage_bytes : 0);
-  p->pre_off = p->stg_off + staging;
-  p->bias_off = p->pre_off + pre_bytes;
+  p->res_off = p->stg_off + staging;
+  p->pre_off = p->res_off + ring_bytes;
+  p->bias_off = p->res_off + pre_bytes;
   l->smem_bytes = p->bias_off + bias_bytes + 1024;
   const int total = p->m_tiles * p->n_tiles;
   if (p->n_split > 1) {

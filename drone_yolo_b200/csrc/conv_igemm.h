@@ -41,6 +41,8 @@ struct ConvParams {
   const __nv_bfloat16* res; int res_ld;
   const float* bias; int act;
   const float* pre; int pre_ld;        // half-resolution fp32 addend in front of the activation (dy_conv_desc.pre_add), or null
+  int res_off;                         // byte offset of the residual ring: [group][3] staging-sized tiles (TMA-prefetched two chunks ahead)
+  int res_mode;                        // residual staging: 2 = that ring, 1 = one chunk ahead into the other staging tile, 0 = per chunk into the single staging tile
   int pre_off;                         // byte offset of its tiles in shared memory: [group][2] x (TW/2 * TH/2 * TB rows x 128 B)
 };
 
