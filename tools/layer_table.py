@@ -58,7 +58,9 @@ def plan_ops(scale, imgsz, batch):
                 byts += M * cout * 2
             if op.get("up") is not None:
                 byts += 4 * M * cout * 2
-            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (f" +1x1->{op['tail'][2]}" if op.get("tail") else "") + (" +decode" if dec else "") + (" f32" if oes == 4 else ""),
+            if op.get("pre") is not None:
+                byts += (M // 4) * cout * 4                   # half-resolution fp32 addend, read once
+            rows.append(dict(name=f"conv{k}x{k}s{s} {cin}->{cout} @{out.H}" + (" +res" if op.get("res") is not None else "") + (" +up2x" if op.get("up") is not None else "") + (" +pre(up)" if op.get("pre") is not None else "") + (f" +1x1->{op['tail'][2]}" if op.get("tail") else "") + (" +decode" if dec else "") + (" f32" if oes == 4 else ""),
                              flops=flops, bytes=byts))
         elif kind == "stem":
             out = op["out"]
@@ -92,10 +94,20 @@ def main():
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     tc = peaks.get("bf16_tflops_sustained", 1397.2) * 1e12
     bw = peaks.get("hbm_gbs", 6553.6) * 1e9
-    rows = list(csv.reader(l for l in open(a.csv) if l.startswith('"')))
-    hdr = rows[0]
-    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    launches = [(r[ki].split("(")[0].replace("void ", ""), float(r[vi].replace(",", "")) / 1e3) for r in rows[1:]]
+    first = open(a.csv).read(4096)
+    if '"Kernel Name"' in first or first.lstrip().startswith(('"', "==")):
+        rows = list(csv.reader(l for l in open(a.csv) if l.startswith('"')))
+        hdr = rows[0]
+        ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+        launches = [(r[ki].split("(")[0].replace("void ", ""), float(r[vi].replace(",", "")) / 1e3) for r in rows[1:] if r[mi] == "gpu__time_duration.sum"]
+    else:
+        # the text of Engine.profile(verbose=True) / tools/profile_layers.py: warm per-op device times, "<us> us  <op>"
+        import re
+        launches = []
+        for line in open(a.csv):
+            m = re.match(r"\s*([\d.]+) us  (.*)", line)
+            if m and "total (" not in m.group(2):
+                launches.append(("(Engine.profile)" if not m.group(2).startswith("nms") else "nms_filter + nms_select", float(m.group(1))))
     ops = plan_ops(a.scale, a.imgsz, a.batch)
     # the NMS kernels follow the plan
     out = []
