@@ -637,58 +637,55 @@ __global__ void __launch_bounds__(kSelThreads) nms_select_kernel(const __grid_co
       }
       const unsigned dead_bits = __ballot_sync(0xffffffffu, dead);
       if (lane == 0) { s.remv[warp] = dead_bits; s.undw[warp] = ~dead_bits; s.keptw[warp] = 0u; }
-      for (int i = tid; i < kWords * (kK + 1); i += kSelThreads) s.mask[i] = 0u;
       __syncthreads();
       NMS_TP(4);
       // ---- (e) suppression pairs (i suppresses j, i < j) among the candidates that survived (d), stored by COLUMN:
-      //      bit (i & 31) of mask[i >> 5][j] says "row i suppresses j" (what the fixed point of (f) needs).  The triangle is
-      //      cut into (row, 32-column word) units, word-major: word w has rows 0 .. 32w+31, i.e. 16w(w+1) units precede
-      //      it.  Units are dealt round-robin, so every thread gets the same amount of IoU work (one row per thread left
-      //      thread 0 with 511 tests and thread 511 with none: half of the block idled at the barrier).
+      //      bit (i & 31) of mask[i >> 5][j] says "row i suppresses j" (what the fixed point of (f) needs).  A unit of work is
+      //      (column j, 32-row word w) with 32w <= j: the thread tests the rows of word w against box j and writes the word with ONE
+      //      plain store - no atomics and no zeroing pass (every word (f) reads, w <= j >> 5, is written by exactly one unit).
+      //      Row-major units (row i against a word of 32 columns) needed an atomicOr per suppressed pair: on clustered boxes,
+      //      where almost every pair suppresses, that was 60 % of the kernel.  Row word w meets columns 32w .. K-1, i.e. with
+      //      v = nwords-1-w there are 32(v+1) units and 16v(v+1) precede them; units are dealt round-robin over the block.
       {
         const int nwords = (K + 31) / 32;
         const int units = 16 * nwords * (nwords + 1);
-        int w = 0;
+        int v = 0;
         for (int u = tid; u < units; u += kSelThreads) {
-          while (16 * (w + 1) * (w + 2) <= u) ++w;                      // u only grows: w is carried
-          const int i = u - 16 * w * (w + 1);
-          const int j0 = w * 32;
+          while (16 * (v + 1) * (v + 2) <= u) ++v;                      // u only grows: v is carried
+          const int w = nwords - 1 - v;
+          const int j = w * 32 + (u - 16 * v * (v + 1));
+          if (j >= K) continue;
           unsigned int bits = 0u;
-          if (i < K && !((s.remv[i >> 5] >> (i & 31)) & 1u)) {
-            unsigned int todo = ~s.remv[w];                              // columns still alive after (d)
-            if (K - j0 < 32) todo &= (1u << (K - j0)) - 1u;
-            if (i >= j0) todo &= ~((2u << (i - j0)) - 1u);               // only j > i
+          const int i0 = w * 32;
+          if (!((s.remv[j >> 5] >> (j & 31)) & 1u)) {
+            unsigned int todo = ~s.remv[w];                              // rows still alive after (d)
+            if (j - i0 < 32) todo &= (1u << (j - i0)) - 1u;              // only i < j (none when j == i0)
             if (todo) {
-              const float4 bi = s.box[i]; const float sli = s.sarea[i];
-              // screen the 32 columns four at a time (s.box / s.sarea have kK entries: j < kK always), then look again at
-              // the few pairs that were not ruled out
+              const float4 bj = s.box[j]; const float slj = s.sarea[j];
+              // screen the 32 rows four at a time (i0 + 31 < kK always), then look again at the few pairs that were not ruled out
               unsigned int maybe = 0u;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 if (!((todo >> (4 * g)) & 0xfu)) continue;
-                const float4 sl4 = *reinterpret_cast<const float4*>(&s.sarea[j0 + 4 * g]);
+                const float4 sl4 = *reinterpret_cast<const float4*>(&s.sarea[i0 + 4 * g]);
                 const float sl[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float inter = box_inter(bi, s.box[j0 + 4 * g + u]);
-                  if (!(inter < __fadd_rn(sli, sl[u]))) maybe |= 1u << (4 * g + u);
+                for (int t = 0; t < 4; ++t) {
+                  const float inter = box_inter(s.box[i0 + 4 * g + t], bj);
+                  if (!(inter < __fadd_rn(sl[t], slj))) maybe |= 1u << (4 * g + t);
                 }
               }
               maybe &= todo;
               while (maybe) {
-                const int jj = __ffs(maybe) - 1;
+                const int ii = __ffs(maybe) - 1;
                 maybe &= maybe - 1u;
-                const float4 bj = s.box[j0 + jj];
-                if (iou_decide(bi, s.area[i], bj, s.area[j0 + jj], box_inter(bi, bj), __fadd_rn(sli, s.sarea[j0 + jj]),
-                               p.iou_f, p.iou_inclusive)) bits |= 1u << jj;
+                const float4 bi = s.box[i0 + ii];
+                if (iou_decide(bi, s.area[i0 + ii], bj, s.area[j], box_inter(bi, bj), __fadd_rn(s.sarea[i0 + ii], slj),
+                               p.iou_f, p.iou_inclusive)) bits |= 1u << ii;
               }
             }
           }
-          while (bits) {                                                  // sparse: a few suppressed columns per row
-            const int jj = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            atomicOr(&s.mask[(i >> 5) * (kK + 1) + j0 + jj], 1u << (i & 31));
-          }
+          s.mask[w * (kK + 1) + j] = bits;
         }
       }
       __syncthreads();
