@@ -22,6 +22,7 @@
 #include "dy_ptx.cuh"
 #include "conv_igemm.h"
 #include <cstring>
+#include <type_traits>
 #include <cstdlib>
 
 namespace dy {
@@ -656,10 +657,10 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
           for (int gi = 0; gi < 4; ++gi) {
             const float4 hb0 = hbv[2 * gi], hb1 = hbv[2 * gi + 1];
             uint4 o;
-            o.x = pack_bf16(act1(r[8 * gi + 0], hb0.x, silu), act1(r[8 * gi + 1], hb0.y, silu));
-            o.y = pack_bf16(act1(r[8 * gi + 2], hb0.z, silu), act1(r[8 * gi + 3], hb0.w, silu));
-            o.z = pack_bf16(act1(r[8 * gi + 4], hb1.x, silu), act1(r[8 * gi + 5], hb1.y, silu));
-            o.w = pack_bf16(act1(r[8 * gi + 6], hb1.z, silu), act1(r[8 * gi + 7], hb1.w, silu));
+            o.x = pack_bf16(act1(r[8 * gi + 0], hb0.x, true), act1(r[8 * gi + 1], hb0.y, true));      // (a fused tail always follows a SiLU conv:
+            o.y = pack_bf16(act1(r[8 * gi + 2], hb0.z, true), act1(r[8 * gi + 3], hb0.w, true));      //  checked on the host)
+            o.z = pack_bf16(act1(r[8 * gi + 4], hb1.x, true), act1(r[8 * gi + 5], hb1.y, true));
+            o.w = pack_bf16(act1(r[8 * gi + 6], hb1.z, true), act1(r[8 * gi + 7], hb1.w, true));
             sts128(rowp + ((gi ^ ((row >> 1) & 3)) << 4), o);
           }
         }
@@ -853,36 +854,47 @@ __global__ void __launch_bounds__(128 + 128 * EG, 1) conv_igemm_kernel(const __g
           if (!(dbg & 1)) {
             const uint32_t rowp = st + row * ROWO;
             [[maybe_unused]] const float* bs = s_bias + n0 + c * CW;
-            if constexpr (F32) {
+            // The activation and the residual are run-time flags of the layer; as conditions inside the unrolled loops they were
+            // if-converted, and every thread issued BOTH variants of every element (64 predicated MUFU per 32 elements: ~550
+            // instructions per chunk where ~300 do the work) - in kernels whose P2-level layers are bound by instruction issue.
+            // One uniform branch per chunk selects a loop body specialised at compile time instead.
+            auto body = [&](auto silu_c, auto res_c) {
+              constexpr bool SILU = decltype(silu_c)::value;
+              [[maybe_unused]] constexpr bool RES = decltype(res_c)::value;
+              if constexpr (F32) {
 #pragma unroll
-              for (int gi = 0; gi < CW / 4; ++gi) {
-                const float4 hb = hbv[gi];
-                float4 o;
-                o.x = act1(r[4 * gi + 0], hb.x, silu); o.y = act1(r[4 * gi + 1], hb.y, silu);
-                o.z = act1(r[4 * gi + 2], hb.z, silu); o.w = act1(r[4 * gi + 3], hb.w, silu);
-                sts128(rowp + ((gi ^ (row & 7)) << 4), make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
-              }
-            } else {
-#pragma unroll
-              for (int gi = 0; gi < CW / 8; ++gi) {
-                const int pos = (ROWO == 128) ? (gi ^ (row & 7)) : (gi ^ ((row >> 1) & 3));
-                const float4 hb0 = CW == 32 ? hbv[(2 * gi) % (CW == 32 ? 8 : 1)] : *reinterpret_cast<const float4*>(bs + 8 * gi);
-                const float4 hb1 = CW == 32 ? hbv[(2 * gi + 1) % (CW == 32 ? 8 : 1)] : *reinterpret_cast<const float4*>(bs + 8 * gi + 4);
-                float v0 = act1(r[8 * gi + 0], hb0.x, silu), v1 = act1(r[8 * gi + 1], hb0.y, silu);
-                float v2 = act1(r[8 * gi + 2], hb0.z, silu), v3 = act1(r[8 * gi + 3], hb0.w, silu);
-                float v4 = act1(r[8 * gi + 4], hb1.x, silu), v5 = act1(r[8 * gi + 5], hb1.y, silu);
-                float v6 = act1(r[8 * gi + 6], hb1.z, silu), v7 = act1(r[8 * gi + 7], hb1.w, silu);
-                const uint32_t sp = rowp + (pos << 4);
-                if (has_res) {
-                  const uint4 rr = lds128(res_s + rslot * STG_BYTES + row * ROWO + (pos << 4));
-                  v0 += bf16_lo(rr.x); v1 += bf16_hi(rr.x); v2 += bf16_lo(rr.y); v3 += bf16_hi(rr.y);
-                  v4 += bf16_lo(rr.z); v5 += bf16_hi(rr.z); v6 += bf16_lo(rr.w); v7 += bf16_hi(rr.w);
+                for (int gi = 0; gi < CW / 4; ++gi) {
+                  const float4 hb = hbv[gi];
+                  float4 o;
+                  o.x = act1(r[4 * gi + 0], hb.x, SILU); o.y = act1(r[4 * gi + 1], hb.y, SILU);
+                  o.z = act1(r[4 * gi + 2], hb.z, SILU); o.w = act1(r[4 * gi + 3], hb.w, SILU);
+                  sts128(rowp + ((gi ^ (row & 7)) << 4), make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
                 }
-                uint4 o;
-                o.x = pack_bf16(v0, v1); o.y = pack_bf16(v2, v3); o.z = pack_bf16(v4, v5); o.w = pack_bf16(v6, v7);
-                sts128(sp, o);
+              } else {
+#pragma unroll
+                for (int gi = 0; gi < CW / 8; ++gi) {
+                  const int pos = (ROWO == 128) ? (gi ^ (row & 7)) : (gi ^ ((row >> 1) & 3));
+                  const float4 hb0 = CW == 32 ? hbv[(2 * gi) % (CW == 32 ? 8 : 1)] : *reinterpret_cast<const float4*>(bs + 8 * gi);
+                  const float4 hb1 = CW == 32 ? hbv[(2 * gi + 1) % (CW == 32 ? 8 : 1)] : *reinterpret_cast<const float4*>(bs + 8 * gi + 4);
+                  float v0 = act1(r[8 * gi + 0], hb0.x, SILU), v1 = act1(r[8 * gi + 1], hb0.y, SILU);
+                  float v2 = act1(r[8 * gi + 2], hb0.z, SILU), v3 = act1(r[8 * gi + 3], hb0.w, SILU);
+                  float v4 = act1(r[8 * gi + 4], hb1.x, SILU), v5 = act1(r[8 * gi + 5], hb1.y, SILU);
+                  float v6 = act1(r[8 * gi + 6], hb1.z, SILU), v7 = act1(r[8 * gi + 7], hb1.w, SILU);
+                  const uint32_t sp = rowp + (pos << 4);
+                  if constexpr (RES) {
+                    const uint4 rr = lds128(res_s + rslot * STG_BYTES + row * ROWO + (pos << 4));
+                    v0 += bf16_lo(rr.x); v1 += bf16_hi(rr.x); v2 += bf16_lo(rr.y); v3 += bf16_hi(rr.y);
+                    v4 += bf16_lo(rr.z); v5 += bf16_hi(rr.z); v6 += bf16_lo(rr.w); v7 += bf16_hi(rr.w);
+                  }
+                  uint4 o;
+                  o.x = pack_bf16(v0, v1); o.y = pack_bf16(v2, v3); o.z = pack_bf16(v4, v5); o.w = pack_bf16(v6, v7);
+                  sts128(sp, o);
+                }
               }
-            }
+            };
+            using T = std::true_type; using Fa = std::false_type;
+            if (silu) { if (has_res) body(T{}, T{}); else body(T{}, Fa{}); }
+            else { if (has_res) body(Fa{}, T{}); else body(Fa{}, Fa{}); }
           }
           if (c == 0) DY_TRE(3);
           fence_proxy_async_smem();
