@@ -1400,7 +1400,7 @@ int conv_build_params(const dy_conv_desc* d, ConvParams* p, ConvLaunch* l) {
     // issuer, which the mbarrier parity test needs (a waiter may be at most one phase ahead of the barrier)
     p->stages &= ~1;
   } else {
-    p->b_resident = (p->n_tiles == 1 && b_all <= budget - 4 * kABytes && !env_int("DY_NO_BRES", 0)) ? 1 : 0;   // leave room for >= 4 activation stages
+    p->b_resident = (p->n_tiles == 1 && b_all <= budget - env_int("DY_BRES_MIN_STAGES", 3) * kABytes && !env_int("DY_NO_BRES", 0)) ? 1 : 0;   // leave room for >= 3 activation stages (the 64 -> 128 stride-2 layer keeps its 147 KB of weights resident: 91 -> 83 us)
     if (fuse2 && !p->b_resident) return fail(DY_ERR_UNSUPPORTED, "conv: fused 1x1 tail needs resident weights");
     const int per_k = a_blk + (p->b_resident ? 0 : b_tile);
     const int avail = budget - (p->b_resident ? b_all : 0);

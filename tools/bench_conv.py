@@ -38,6 +38,7 @@ LAYERS = [  # name, B, cin, cout, H, W, k, s, res, in_ld, out_ld, f32
     ("P4 1x1 512->256", 64, 512, 256, 40, 40, 1, 1, False, 512, 256, False),
     ("P3 3x3 s2 128->256", 64, 128, 256, 80, 80, 3, 2, False, 128, 256, False),
     ("P4 3x3 256->128", 64, 256, 128, 40, 40, 3, 1, False, 256, 128, False),
+    ("P2->P3 3x3 s2 64->128", 64, 64, 128, 160, 160, 3, 2, False, 64, 128, False),
     ("P5 1x1 512->512", 64, 512, 512, 20, 20, 1, 1, False, 512, 768, False),
     ("P5 1x1 768->512", 64, 768, 512, 20, 20, 1, 1, False, 768, 512, False),
     ("P4 3x3 s2 256->512", 64, 256, 512, 40, 40, 3, 2, False, 256, 512, False),
