@@ -181,7 +181,7 @@ class LayerPlan:
                          if (li + f_ if f_ < 0 else f_) == ci] if ci is not None else []
                 if (self.split_up and isinstance(nxt, C2f) and users == [ci + 1] and home[i][1] == 0
                         and ci not in getattr(self.model, "save", ()) and nxt.cv1.conv.kernel_size[0] == 1
-                        and isinstance(nxt.cv1.act, nn.SiLU) and src.c % 8 == 0 and (2 * nxt.c) % 8 == 0
+                        and isinstance(nxt.cv1.act, nn.SiLU) and src.c % 8 == 0 and ((2 * nxt.c) % 32 == 0 or 2 * nxt.c in (8, 16, 24, 32))
                         and src.H * 2 == out.H and src.W * 2 == out.W):
                     # the Concat only feeds that C2f, the upsampled part sits first (channels [0, src.c)): nothing is written here
                     self.up_split[ci] = (src, src.c)

@@ -144,6 +144,34 @@ def test_conv_fused_upsample(K, dev, shape):
     assert bool((cat[..., cout:] == 3.0).all()), "wrote outside its slice"
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 160, 160, 128), (3, 128, 128, 80, 80, 256), (2, 256, 256, 40, 40, 512), (1, 64, 32, 20, 12, 32),
+                                   (5, 32, 96, 6, 10, 16)])
+def test_conv_pre_add_splits_cv1_across_the_upsample(K, dev, shape):
+    """`dy_conv_desc.pre_add`: act(conv1x1(b) + bias + up2x(t)) with t fp32 at half resolution.  A 1x1 conv commutes with nearest
+    upsampling, so C2f.cv1 over Concat([Upsample(a), b]) (cfg/models/v8/yolov8-p2-repvgg.yaml:30-41, nn/modules/block.py:236) equals
+    act(W_b*b + bias + up(W_a*a)): checked against the concatenated fp32 conv, on whole and ragged tiles, inside a concat slice."""
+    B, cb, cout, H, W, ca = shape
+    g = torch.Generator().manual_seed(cb * 7 + H)
+    a = torch.randn(B, ca, H // 2, W // 2, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    skip = torch.randn(B, H, W, ca + cb, generator=g).to(dev).to(torch.bfloat16)         # the Concat buffer: [up(a) (never written) | b]
+    b_in = skip.permute(0, 3, 1, 2)[:, ca:]
+    w = (torch.randn(cout, ca + cb, 1, 1, generator=g) / (ca + cb) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    wa, _ = K.pack_conv_weight(w[:, :ca].contiguous(), None)
+    wb, bb = K.pack_conv_weight(w[:, ca:].contiguous(), bias)
+    t = K.conv2d(a, wa, torch.zeros_like(bb), cout, 1, 1, False, out_dtype=torch.float32)      # W_a * a at low resolution
+    catbuf = torch.full((B, H, W, cout + 24), 5.0, device=dev, dtype=torch.bfloat16)
+    out = catbuf.permute(0, 3, 1, 2)[:, 8:8 + cout]
+    K.conv2d(b_in, wb, bb, cout, 1, 1, True, out=out, pre_add=t)
+    x_full = torch.cat((F.interpolate(a.float(), scale_factor=2, mode="nearest"), b_in.float()), 1)
+    ref = F.silu(F.conv2d(x_full, w.to(torch.bfloat16).float(), bias))
+    close(out, ref, 2e-2, 2e-2)
+    assert bool((catbuf[..., :8] == 5.0).all()) and bool((catbuf[..., 8 + cout:] == 5.0).all()), "wrote outside its slice"
+    with pytest.raises(Exception):                                                             # a 3x3 conv does not commute with the upsample
+        w3, b3 = K.pack_conv_weight(torch.randn(cout, cb, 3, 3, device=dev), bias)
+        K.conv2d(b_in, w3, b3, cout, 3, 1, True, pre_add=t)
+
+
 @pytest.mark.parametrize("B,H,W,cout2", [(2, 48, 40, 64), (4, 160, 160, 64), (4, 160, 160, 10), (3, 80, 80, 16), (2, 40, 40, 10)])
 def test_conv_fused_detect_tail(K, dev, B, H, W, cout2):
     """Detect branch tail `Conv(64,64,3) -> nn.Conv2d(64,n,1)` (nn/modules/head.py:41-47) in ONE kernel: the SiLU tile is the
