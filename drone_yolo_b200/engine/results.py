@@ -79,6 +79,9 @@ class Boxes:
         return Boxes(torch.as_tensor(self.data).to(*args, **kwargs), self.orig_shape)
 
 
+_NO_SPEED = {"preprocess": None, "inference": None, "postprocess": None}
+
+
 class Results:
     """One image's detections.  `orig_img` may be a callable producing the uint8 HWC image lazily (tensor sources:
     the reference pays a D2H round trip of the whole input batch for it, utils/ops.py:851)."""
@@ -86,12 +89,33 @@ class Results:
     def __init__(self, orig_img, path, names, boxes=None, orig_shape=None, speed=None):
         self._orig_img = orig_img
         self.orig_shape = orig_shape if orig_shape is not None else orig_img.shape[:2]
-        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
+        # (n, 6) rows, or (block (B, max_det, 6), image index, row count): the slice and the Boxes view are made on first access
+        # (rank 0 of an 8-GPU run receives 512 Results per engine step; most consumers touch a few fields of each)
+        self._rows = boxes
+        self._boxes = None
         self.masks = self.probs = self.keypoints = self.obb = None
-        self.speed = speed or {"preprocess": None, "inference": None, "postprocess": None}
+        self.speed = speed or _NO_SPEED
         self.names = names
         self.path = path
         self.save_dir = None
+
+    def _resolve(self):
+        r = self._rows
+        if type(r) is tuple:
+            block, i, cnt = r
+            r = self._rows = block[i, :cnt]
+        return r
+
+    @property
+    def boxes(self):
+        if self._boxes is None and self._rows is not None:
+            self._boxes = Boxes(self._resolve(), self.orig_shape)
+        return self._boxes
+
+    @boxes.setter
+    def boxes(self, value):
+        self._boxes = value
+        self._rows = value.data if value is not None else None
 
     @property
     def orig_img(self):
@@ -100,7 +124,10 @@ class Results:
         return self._orig_img
 
     def __len__(self):
-        return len(self.boxes) if self.boxes is not None else 0
+        r = self._rows
+        if type(r) is tuple:
+            return r[2]
+        return 0 if r is None else (1 if r.ndim == 1 else r.shape[0])
 
     def _with(self, boxes):
         r = Results(self._orig_img, self.path, self.names, None, self.orig_shape, self.speed)
