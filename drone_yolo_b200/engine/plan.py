@@ -179,12 +179,13 @@ class LayerPlan:
                 nxt = layers[ci + 1] if ci is not None and ci + 1 < n else None
                 users = [li for li, l in enumerate(layers) for f_ in (l.f if isinstance(l.f, (list, tuple)) else [l.f])
                          if (li + f_ if f_ < 0 else f_) == ci] if ci is not None else []
-                if (self.split_up and isinstance(nxt, C2f) and users == [ci + 1] and home[i][1] == 0
+                if (self.split_up and isinstance(nxt, C2f) and users == [ci + 1] and (home[i][1] == 0 or home[i][1] + src.c == cat_ch[ci])
                         and ci not in getattr(self.model, "save", ()) and nxt.cv1.conv.kernel_size[0] == 1
                         and isinstance(nxt.cv1.act, nn.SiLU) and src.c % 8 == 0 and ((2 * nxt.c) % 32 == 0 or 2 * nxt.c in (8, 16, 24, 32))
                         and src.H * 2 == out.H and src.W * 2 == out.W):
-                    # the Concat only feeds that C2f, the upsampled part sits first (channels [0, src.c)): nothing is written here
-                    self.up_split[ci] = (src, src.c)
+                    # the Concat only feeds that C2f and the upsampled part sits first or last in it (the -sf graphs put it last):
+                    # nothing is written here
+                    self.up_split[ci] = (src, src.c, home[i][1])
                 elif prod is not None and self.fuse_upsample:
                     # nn.Upsample(2x nearest) folded into its producer: the conv's epilogue also stores every output tile
                     # into the four (dy, dx) parity views of this destination (dy_conv_desc.up_out)
@@ -234,14 +235,15 @@ class LayerPlan:
         cat = self._new_buf((2 + n) * c, H, W)
         fused = False
         if split is not None:
-            lo, ca = split                                   # low-resolution source of the upsampled part, its channels
-            w, b = m.cv1.fused_weight_bias()                 # fp32 [2c, ca + cb, 1, 1], [2c]
-            wa, _ = K.pack_conv_weight(w[:, :ca].contiguous(), None)
-            wb, bb = K.pack_conv_weight(w[:, ca:].contiguous(), b)
+            lo, ca, c0 = split                               # low-resolution source of the upsampled part, its channels and offset
+            w, b = m.cv1.fused_weight_bias()                 # fp32 [2c, C, 1, 1], [2c]; the upsampled part is channels [c0, c0 + ca)
+            wa, _ = K.pack_conv_weight(w[:, c0:c0 + ca].contiguous(), None)
+            sk0 = ca if c0 == 0 else 0                       # the skip tensors: the rest of the Concat, before or behind it
+            wb, bb = K.pack_conv_weight(w[:, sk0:sk0 + src.c - ca].contiguous(), b)
             zero = torch.zeros_like(bb)
             t = Ref(self._new_buf(2 * c, lo.H, lo.W, esz=4), 0, 2 * c, lo.H, lo.W)
             self._op(kind="conv", w=(wa, zero), cout=2 * c, k=1, s=1, act=False, inp=lo, out=t)
-            self._op(kind="conv", w=(wb, bb), cout=2 * c, k=1, s=1, act=True, inp=Ref(src.buf, src.c0 + ca, src.c - ca, H, W),
+            self._op(kind="conv", w=(wb, bb), cout=2 * c, k=1, s=1, act=True, inp=Ref(src.buf, src.c0 + sk0, src.c - ca, H, W),
                      out=Ref(cat, 0, 2 * c, H, W), pre=t)
             fused = True
         if prod is not None:

@@ -423,3 +423,71 @@ def test_inference_slicer_argument_checks():
     with pytest.raises(ValueError):
         generate_offsets((100, 100), (10, 10), (1.0, 0.2))
     assert generate_offsets((100, 50), (200, 200), (0.2, 0.2)).tolist() == [[0, 0, 100, 50]]      # frame smaller than a tile
+
+
+def test_frame_stream_batching_fast_and_ragged_paths():
+    """DetectionPredictor._iter_batches: a stream of equally shaped frames is cut into `batch`-sized lists (one islice per batch);
+    a change of frame shape closes the batch early; a 4-D tensor or a list inside the stream is its own batch; names count on."""
+    from types import SimpleNamespace
+
+    from drone_yolo_b200.engine.predictor import DetectionPredictor
+
+    p = DetectionPredictor.__new__(DetectionPredictor)
+    p.args = SimpleNamespace(batch=4)
+    a, b = np.zeros((4, 6, 3), np.uint8), np.zeros((8, 6, 3), np.uint8)
+    got = [(len(i), i[0].shape, pa[0], pa[-1]) for pa, i, _ in p._iter_batches(iter([a] * 9))]
+    assert got == [(4, a.shape, "image0.jpg", "image3.jpg"), (4, a.shape, "image4.jpg", "image7.jpg"), (1, a.shape, "image8.jpg", "image8.jpg")]
+    got = [(len(i), i[0].shape, pa[0]) for pa, i, _ in p._iter_batches(iter([a] * 5 + [b] * 3 + [a] * 2))]
+    assert got == [(4, a.shape, "image0.jpg"), (1, a.shape, "image4.jpg"), (3, b.shape, "image5.jpg"), (2, a.shape, "image8.jpg")]
+    got = [(len(i), pa[0]) for pa, i, _ in p._iter_batches(iter([a, a, [b, b, b], a]))]
+    assert got == [(2, "image0.jpg"), (3, "image2.jpg"), (1, "image5.jpg")]
+    assert list(p._iter_batches(iter([]))) == []
+
+
+def test_results_are_lazy_views_of_one_block():
+    """Results built from (block, image, count): len() without touching the rows, boxes sliced on first access, `_with` /
+    the boxes setter keep working, and the rows are a copy (the predictor's pinned read-back buffer is reused)."""
+    from drone_yolo_b200.engine.results import Boxes, Results
+
+    block = torch.arange(2 * 5 * 6, dtype=torch.float32).reshape(2, 5, 6)
+    r = Results(np.zeros((8, 8, 3), np.uint8), "image1.jpg", {0: "a"}, boxes=(block, 1, 3), orig_shape=(8, 8))
+    assert len(r) == 3 and r._boxes is None
+    assert torch.equal(r.boxes.data, block[1, :3]) and r.boxes.conf.shape == (3,) and r.boxes.xywh.shape == (3, 4)
+    assert len(r.numpy()) == 3 and isinstance(r.numpy().boxes.data, np.ndarray)
+    r.boxes = Boxes(block[0, :2], (8, 8))
+    assert len(r) == 2
+    assert len(Results(np.zeros((8, 8, 3), np.uint8), "x", {}, boxes=None)) == 0
+    assert len(Results(np.zeros((8, 8, 3), np.uint8), "x", {}, boxes=torch.zeros(0, 6))) == 0
+
+
+@pytest.mark.parametrize("yaml_name,expect", [("yolov8n-p2-repvgg.yaml", 3), ("yolov8s-p2-repvgg.yaml", 3), ("yolov8n-p2-repvgg-sf.yaml", 3)])
+def test_plan_splits_cv1_across_the_upsample_symbolically(yaml_name, expect):
+    """The plan's symbolic pass (no GPU): in the Drone-YOLO graphs every `Upsample -> Concat -> C2f` of the top-down neck is lowered as
+    a low-resolution 1x1 conv (fp32, no activation) + a 1x1 conv over the skip tensor with `pre`; no op carries a fused upsample store."""
+    from drone_yolo_b200.engine.plan import LayerPlan
+    from drone_yolo_b200.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    model = DetectionModel(yaml_name, nc=10, verbose=False).eval().fuse(verbose=False)
+    lp = LayerPlan.__new__(LayerPlan)
+    lp.model, lp.mb, lp.H, lp.W, lp.device = model, 2, 128, 128, None
+    lp.bufs, lp.ops, lp.keep = [], [], []
+    lp.fuse_upsample = lp.fuse_tail = lp.fuse_decode = lp.fuse_cv1 = True
+    lp.split_up, lp.up_split = True, {}
+    lp.head_lanes, lp.lane = 0, 0
+    lp._build_symbolic()
+    pre = [op for op in lp.ops if op.get("pre") is not None]
+    assert len(pre) == expect == len(lp.up_split) and not any(op.get("up") is not None for op in lp.ops)
+    for op in pre:
+        t = op["pre"]
+        assert lp.bufs[t.buf].esz == 4 and (2 * t.H, 2 * t.W) == (op["out"].H, op["out"].W) and op["k"] == 1 and op["act"]
+        prod = [o for o in lp.ops if o.get("out") == t]
+        assert len(prod) == 1 and prod[0]["k"] == 1 and not prod[0]["act"]
+    names = lp.describe()
+    assert sum("+pre(up)" in nm for nm in names) == expect and len(names) == len(lp.ops)
+    # with the split switched off the same graph carries the fused upsample stores instead
+    lp2 = LayerPlan.__new__(LayerPlan)
+    lp2.__dict__.update({k: v for k, v in lp.__dict__.items() if k not in ("bufs", "ops", "keep", "up_split")})
+    lp2.bufs, lp2.ops, lp2.keep, lp2.split_up, lp2.up_split = [], [], [], False, {}
+    lp2._build_symbolic()
+    assert sum(op.get("up") is not None for op in lp2.ops) == expect and not any(op.get("pre") is not None for op in lp2.ops)
