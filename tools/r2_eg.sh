@@ -1,4 +1,5 @@
 #!/bin/bash
+# (round-2 experiment, measured neutral: build the stem variant with DY_EXTRA_NVCC_FLAGS=-DDY_STEM_EG=4 DY_LIB_TAG=stem4 python -m drone_yolo_b200.build)
 # A/B of epilogue-group counts: parity of the touched kernels, then the step time (plan order, no side lanes) per variant, twice
 tag=${1:-r2eg}
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "conv or stem or engine_vs_cpu_oracle or model_vs_reference" > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest(default) exit $?"; tail -2 gpurun_out/${tag}_pytest.log
