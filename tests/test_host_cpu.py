@@ -491,3 +491,26 @@ def test_plan_splits_cv1_across_the_upsample_symbolically(yaml_name, expect):
     lp2.bufs, lp2.ops, lp2.keep, lp2.split_up, lp2.up_split = [], [], [], False, {}
     lp2._build_symbolic()
     assert sum(op.get("up") is not None for op in lp2.ops) == expect and not any(op.get("pre") is not None for op in lp2.ops)
+
+
+def test_rescale_params_match_scale_boxes_arithmetic():
+    """ops.rescale_params (the per-image block the NMS output phase reads, dy_nms_desc.rescale): pad / gain / clamp values are
+    the ones `scale_boxes` + `clip_boxes` use (reference ops.py:92-127, 335-354), for mixed shapes incl. repeated ones."""
+    from drone_yolo_b200.utils import ops
+
+    shapes = [(1080, 1920), (480, 640), (1080, 1920), (333, 777), (640, 640)]
+    rs = ops.rescale_params((640, 640), shapes)
+    assert rs.shape == (5, 8) and rs.dtype == torch.float32 and torch.equal(rs[0], rs[2])
+    for i, s in enumerate(shapes):
+        gain = min(640 / s[0], 640 / s[1])
+        pad = (round((640 - s[1] * gain) / 2 - 0.1), round((640 - s[0] * gain) / 2 - 0.1))
+        assert rs[i, :5].tolist() == [float(pad[0]), float(pad[1]), float(np.float32(gain)), float(s[1]), float(s[0])]
+        box = torch.tensor([[100.0, 120.0, 500.0, 630.0]])
+        ref = ops.scale_boxes((640, 640), box.clone(), s)
+        got = box.clone()
+        got[:, [0, 2]] -= rs[i, 0]
+        got[:, [1, 3]] -= rs[i, 1]
+        got /= rs[i, 2]
+        got[:, [0, 2]] = got[:, [0, 2]].clamp(0, float(rs[i, 3]))
+        got[:, [1, 3]] = got[:, [1, 3]].clamp(0, float(rs[i, 4]))
+        assert torch.equal(got, ref)
