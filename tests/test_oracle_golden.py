@@ -316,3 +316,48 @@ def test_validator_argument_checks():
             DetectionValidator(args=bad)
     with pytest.raises(DroneYoloError):
         DetectionValidator()(model=None, batches=[])
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("seed", range(12))
+def test_metrics_restatement_vs_live_reference(seed):
+    """utils/metrics.py against the LIVE reference functions (authoring container only; skipped where /root/reference is absent):
+    box_iou, match_predictions (validator.py:224-264) and ap_per_class (metrics.py:537-623) on random detections / labels incl.
+    empty sides, duplicate scores and classes without predictions."""
+    from oracle import ref_shim
+
+    ref_shim.load()
+    from ultralytics.engine.validator import BaseValidator
+    from ultralytics.utils import metrics as rm
+
+    from drone_yolo_b200.utils import metrics as m
+
+    g = torch.Generator().manual_seed(seed)
+    n, l, nc = (0, 5, 4) if seed == 0 else ((7, 0, 4) if seed == 1 else (int(torch.randint(1, 60, (1,), generator=g)), int(torch.randint(1, 25, (1,), generator=g)), 6))
+
+    def boxes(k):
+        xy = torch.rand(k, 2, generator=g) * 80
+        wh = torch.rand(k, 2, generator=g) * 40 + 2
+        return torch.cat((xy, xy + wh), 1)
+
+    gt = boxes(l)
+    gt_cls = torch.randint(0, nc, (l,), generator=g).float()
+    det = torch.cat((gt[torch.randint(0, max(l, 1), (n,), generator=g)] + torch.randn(n, 4, generator=g) * 3 if l else boxes(n), boxes(n)))[:n]
+    pred_cls = torch.randint(0, nc, (n,), generator=g).float()
+    conf = (torch.rand(n, generator=g) * 8).round() / 8                                   # duplicate scores on purpose
+    iou_ref, iou_got = rm.box_iou(gt, det), m.box_iou(gt, det)
+    assert torch.equal(iou_ref, iou_got)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    v = BaseValidator.__new__(BaseValidator)
+    v.iouv = iouv
+    tp_ref = v.match_predictions(pred_cls, gt_cls, iou_ref)
+    tp_got = m.match_predictions(pred_cls, gt_cls, iou_got, iouv)
+    assert torch.equal(tp_ref, tp_got)
+    if n and l:
+        ref = rm.ap_per_class(tp_ref.numpy(), conf.numpy(), pred_cls.numpy(), gt_cls.numpy())
+        p, r, f1, ap, classes = m.ap_per_class(tp_got.numpy(), conf.numpy(), pred_cls.numpy(), gt_cls.numpy())
+        np.testing.assert_allclose(p, ref[2], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r, ref[3], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(f1, ref[4], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(ap, ref[5], rtol=0, atol=1e-12)
+        assert classes.tolist() == ref[6].tolist()
