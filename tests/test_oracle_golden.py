@@ -361,3 +361,42 @@ def test_metrics_restatement_vs_live_reference(seed):
         np.testing.assert_allclose(f1, ref[4], rtol=0, atol=1e-12)
         np.testing.assert_allclose(ap, ref[5], rtol=0, atol=1e-12)
         assert classes.tolist() == ref[6].tolist()
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("seed", range(8))
+def test_nms_and_decode_oracles_vs_live_reference(seed):
+    """The numpy oracles against the LIVE reference on fresh random inputs (authoring container only): Detect decode
+    (head.py:100-131) to 1e-5 relative, ops.non_max_suppression (ops.py:181-332) rows bit for bit, for a random option set per seed
+    (multi_label, agnostic, class filter, small max_det / max_nms, a-priori labels) and clustered boxes that really suppress."""
+    from oracle import ref_shim
+
+    tasks = ref_shim.load()
+    from ultralytics.utils import ops
+
+    g = torch.Generator().manual_seed(100 + seed)
+    nc, B, imgsz = 10, 2, 64
+    shapes = [(imgsz // s, imgsz // s) for s in (4, 8, 16, 32)]
+    raw = [torch.cat((1.5 * torch.randn(B, 64, h, w, generator=g), -2.0 + 2.0 * torch.randn(B, nc, h, w, generator=g)), 1) for h, w in shapes]
+    det = tasks.Detect(nc=nc, ch=(16, 32, 64, 128)).eval()
+    det.stride = torch.tensor([4.0, 8.0, 16.0, 32.0])
+    with torch.no_grad():
+        y_ref = det._inference([r.clone() for r in raw])
+    y = decode_np.decode([r.numpy() for r in raw], [4.0, 8.0, 16.0, 32.0], nc)
+    np.testing.assert_allclose(y, y_ref.numpy(), rtol=1e-5, atol=1e-4)
+    kw = dict(conf_thres=[0.001, 0.05, 0.25][seed % 3], iou_thres=[0.7, 0.45, 0.6, 0.3][seed % 4], max_det=[300, 20][seed % 2])
+    if seed % 2:
+        kw["multi_label"] = True
+    if seed % 3 == 0:
+        kw["agnostic"] = True
+    if seed % 4 == 1:
+        kw["classes"] = [1, 3, 7]
+    if seed == 5:
+        kw["max_nms"] = 50
+    labels = [[[3.0, 20.0, 22.0, 10.0, 12.0]], []] if seed in (2, 7) else ()
+    yr = y_ref.clone()
+    ref = ops.non_max_suppression(yr, labels=[torch.tensor(l).reshape(-1, 5) for l in labels] if labels else (), **kw)
+    got = nms_np.non_max_suppression(y_ref.numpy(), labels=labels, **kw)
+    for a, b in zip(got, ref):
+        assert a.shape == tuple(b.shape) and np.array_equal(a.view(np.uint32), b.numpy().view(np.uint32))
+    assert sum(len(a) for a in got) > 0
